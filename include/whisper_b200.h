@@ -1,0 +1,131 @@
+/* whisper_b200.h — C-ABI of libwhisper_b200.so: the B200-native (sm_100a) Whisper greedy-inference path.
+ *
+ * Boundary conventions (they mirror the reference's native plugin boundary):
+ *   - `extern "C"`, plain pointers and sizes, no torch / C++ types        (InferPlugin.cpp:149-170 `initLibNvInferPlugins`)
+ *   - every entry point returns 0 on success or a negative wb_status; the message is in wb_last_error()
+ *     (plugin enqueue returns int, 0 = ok; exceptions are caught at the boundary: identityPlugin.cpp:82-108,190-203)
+ *   - device pointers are NON-OWNING, work is enqueued asynchronously on the caller's cudaStream_t and the
+ *     caller synchronises, exactly like Session.run(inputs, outputs, stream)      (runtime/session.py:148-178)
+ *   - workspaces are provided by the caller (plugin `workspace` argument, identityPlugin.cpp:82-85)
+ *   - loaded with ctypes.CDLL(..., RTLD_GLOBAL) + hand-set argtypes like tensorrt_llm/plugin/plugin.py:10-22
+ *
+ * dtype codes: 0 = float32, 1 = bfloat16.
+ */
+#ifndef WHISPER_B200_H_
+#define WHISPER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define WB_API __attribute__((visibility("default")))
+#else
+#define WB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wb_model wb_model;     /* packed device weights of one Whisper checkpoint            */
+typedef struct wb_session wb_session; /* per-batch state: encoder workspace, KV caches, token loop   */
+typedef void* wb_stream;              /* cudaStream_t                                                */
+
+enum wb_status {
+    WB_OK = 0,
+    WB_ERR_INVALID = -1,   /* bad argument / shape / alignment            */
+    WB_ERR_CUDA = -2,      /* CUDA runtime error (message has the call)   */
+    WB_ERR_DRIVER = -3,    /* driver entry point / tensor-map failure     */
+    WB_ERR_STATE = -4,     /* object not ready (missing weights, ...)     */
+    WB_ERR_INTERNAL = -9
+};
+
+/* Hyper-parameters: the subset of the reference's config.pkl (WhisperConfig.to_dict(), build_encoder.py:42-45)
+ * that the path reads.  Mirrors the ctor kwargs of tensorrt_llm.models.WhisperEncoder / WhisperDecoder
+ * (models/whisper/model.py:69-72, 372-382). */
+typedef struct wb_config {
+    int32_t d_model, n_heads, encoder_layers, decoder_layers, ffn_dim, vocab_size;
+    int32_t num_mel_bins, n_frames, max_source_positions, max_target_positions;
+    int32_t decoder_start_token_id, eos_token_id, pad_token_id, max_length;
+} wb_config;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+WB_API const char* wb_last_error(void);                 /* thread-local message of the last failing call   */
+WB_API int wb_version(void);
+WB_API int wb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* debug/bench switches: gemm 0 = tcgen05 for bf16 (default), 1 = CUDA-core; attention likewise */
+WB_API int wb_set_backend(int gemm_backend, int attn_backend);
+/* number of kernels this library launched so far on this thread's device (bench `gpu_launches`) */
+WB_API long long wb_launch_count(void);
+
+/* ---- model: replaces build_encoder.py / build_decoder.py (HF state_dict -> engine)  ---------- */
+WB_API int wb_model_create(const wb_config* cfg, int dtype, wb_model** out);
+WB_API int wb_model_destroy(wb_model* m);
+/* `name` is the oracle's state_dict key (binders build_encoder.py:71-91,
+ * build_decoder.py:71-101); `data` is HOST fp32, contiguous, torch layout.  q/k/v are fused on the fly
+ * (zero K bias), the q scale is folded in, conv weights are re-laid out for the GEMM stem. */
+WB_API int wb_model_load_tensor(wb_model* m, const char* name, const float* data, int64_t numel);
+/* logits processors of run.py:150-162: suppress_tokens, begin_suppress_tokens (+begin_index), forced ids */
+WB_API int wb_model_set_generation(wb_model* m, const int32_t* suppress, int n_suppress, const int32_t* begin_suppress,
+                            int n_begin, int begin_index, const int32_t* forced_pairs, int n_forced);
+WB_API int wb_model_weight_bytes(const wb_model* m, size_t* bytes);
+
+/* ---- session ------------------------------------------------------------------------------------ */
+WB_API int wb_session_workspace_bytes(const wb_model* m, int max_batch, int enc_chunk, size_t* bytes);
+WB_API int wb_session_create(wb_model* m, int max_batch, int enc_chunk, void* workspace, size_t workspace_bytes, wb_session** out);
+WB_API int wb_session_destroy(wb_session* s);
+
+/* WhisperEncoder.__call__(input) -> hidden_states (run.py:81-91): mel fp32 [B, 80, 3000] on device.
+ * Also projects the cross-attention K/V of every decoder layer once (oracle branch modeling_whisper.py:484-487).
+ * enc_out_f32 (optional) receives hidden_states fp32 [B, 1500, d]. */
+WB_API int wb_encode(wb_session* s, const float* mel, int batch, float* enc_out_f32, wb_stream stream);
+/* use encoder states produced elsewhere (decoder drop-in: `encoder_hidden_states` input, model.py:487-490) */
+WB_API int wb_set_encoder_output(wb_session* s, const void* enc_states, int dtype, int batch, wb_stream stream);
+
+/* greedy_search (run.py:171-227 == generation/utils.py:1474-1529), entirely on device.
+ * wb_decode_begin resets ids to [[decoder_start_token_id]] * B; wb_decode_step enqueues ONE step
+ * (WhisperDecoder.__call__ + processors + argmax + EOS bookkeeping); wb_decode_run enqueues up to max_steps
+ * steps (<=0: until max_length), polls the stop flag every `check_every` steps, synchronises and returns the
+ * final sequence length in *final_len. */
+WB_API int wb_decode_begin(wb_session* s, int batch, wb_stream stream);
+WB_API int wb_decode_step(wb_session* s, wb_stream stream);
+WB_API int wb_decode_run(wb_session* s, int max_steps, int check_every, int* final_len, wb_stream stream);
+/* ids int32 [B, max_target_positions] (row stride max_target_positions); device pointer owned by the session */
+WB_API int wb_decode_tokens(wb_session* s, const int32_t** tokens_dev, int* row_stride);
+/* raw next-token logits of the last step, fp32 [B, vocab] (the decoder engine's output tensor, model.py:464) */
+WB_API int wb_decode_logits(wb_session* s, const float** logits_dev);
+/* test hooks: teacher forcing (ids taken from forced[B, max_target_positions]) and per-step logits dump */
+WB_API int wb_decode_set_forced_tokens(wb_session* s, const int32_t* forced_dev);
+WB_API int wb_decode_set_logits_dump(wb_session* s, float* dump_dev, int max_steps);
+/* views of the caches: cross K/V of layer l: [2][max_batch][H][1500][64]; self pages [num_pages][H][64][64] */
+WB_API int wb_session_cross_kv(wb_session* s, int layer, const void** kv_dev, int64_t* kv_stride_elems);
+WB_API int wb_session_self_kv(wb_session* s, int layer, const void** k_pages, const void** v_pages, const int32_t** page_table,
+                       int* pages_per_seq, int* page_tokens);
+
+/* ---- operators (module-level drop-ins and kernel tests) ---------------------------------------- */
+/* LayerNorm eps: x fp32 [rows, d] -> out (out_dtype)                         (layers/normalization.py:6-30) */
+WB_API int wb_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_dtype, int rows, int d,
+                 float eps, wb_stream stream);
+/* Linear: out = act(A W^T + bias) + residual; A [M,K] (lda), W [N,K], dtypes in_dtype, bias/residual fp32;
+ * act 0 none / 1 erf-GELU; backend 0 auto / 1 CUDA-core / 2 tcgen05       (layers/linear.py:38-139) */
+WB_API int wb_linear(const void* A, int64_t lda, const void* W, int64_t ldw, int in_dtype, const float* bias,
+              const float* residual, int64_t ldres, void* out, int64_t ldo, int out_dtype, int M, int N, int K, int act,
+              int backend, wb_stream stream);
+/* Encoder stem (conv1+GELU, conv2+GELU, +positions): mel fp32 [B,80,3000] -> x fp32 [B*1500, d]; uses the
+ * session's workspace and the model's packed conv weights             (models/whisper/model.py:96-102) */
+WB_API int wb_encoder_stem(wb_session* s, const float* mel, int batch, float* x_out, wb_stream stream);
+/* Encoder self-attention over fused qkv [B*S, 3*H*64] (q pre-scaled) -> out [B*S, H*64]; backend as above */
+WB_API int wb_encoder_attention(const void* qkv, void* out, int dtype, int batch, int seq, int heads, int backend, wb_stream stream);
+/* One-query attention over explicit contiguous K/V [B, H, T, 64] (WhisperDecoderAttention cached modes,
+ * model.py:240-304): q [B, H*64] pre-scaled, n_keys <= T */
+WB_API int wb_decode_attention(const void* q, const void* k, const void* v, void* out, int dtype, int batch, int heads,
+                        int n_keys, int64_t kv_batch_stride, int64_t kv_head_stride, wb_stream stream);
+/* masked argmax per row: logits fp32 [B, V]; mask (optional) uint8 [V], a token is skipped if mask & bits */
+WB_API int wb_argmax(const float* logits, int64_t ld, int batch, int vocab, const uint8_t* mask, int bits, int32_t* out,
+              wb_stream stream);
+WB_API int wb_cast(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, wb_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WHISPER_B200_H_ */

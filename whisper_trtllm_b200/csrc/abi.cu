@@ -1,0 +1,268 @@
+// extern "C" boundary of libwhisper_b200.so (declared in include/whisper_b200.h).
+// Exceptions never cross it: every entry point returns a wb_status and stores the message thread-locally,
+// the same discipline as the reference's plugin boundary (identityPlugin.cpp:190-203, InferPlugin.cpp:149-170).
+#include "../../include/whisper_b200.h"
+
+#include "wb_runtime.h"
+
+namespace {
+thread_local std::string g_last_error;
+
+template <typename F> int guarded(F&& f) {
+    try {
+        f();
+        return WB_OK;
+    } catch (const wb::Error& e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return WB_ERR_INTERNAL;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return WB_ERR_INTERNAL;
+    }
+}
+inline cudaStream_t S(wb_stream s) { return reinterpret_cast<cudaStream_t>(s); }
+inline wb::Model* M(wb_model* m) { return reinterpret_cast<wb::Model*>(m); }
+inline const wb::Model* M(const wb_model* m) { return reinterpret_cast<const wb::Model*>(m); }
+inline wb::Session* SS(wb_session* s) { return reinterpret_cast<wb::Session*>(s); }
+}  // namespace
+
+#define WB_NOT_NULL(p) WB_REQUIRE((p) != nullptr, #p " is null")
+
+namespace wb { void set_gemm_tc_block_n(int bn); }
+
+extern "C" {
+
+const char* wb_last_error(void) { return g_last_error.c_str(); }
+int wb_version(void) { return 100; }
+
+int wb_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    return guarded([&] {
+        int dev = 0;
+        WB_CHECK_CUDA(cudaGetDevice(&dev));
+        if (sm_count) WB_CHECK_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+        if (cc_major) WB_CHECK_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+        if (cc_minor) WB_CHECK_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    });
+}
+
+int wb_set_backend(int gemm_backend, int attn_backend) {
+    return guarded([&] {
+        WB_REQUIRE(gemm_backend >= 0 && gemm_backend <= 1 && attn_backend >= 0 && attn_backend <= 1, "backend must be 0 or 1");
+        wb::set_gemm_backend(gemm_backend);
+        wb::set_attn_backend(attn_backend);
+    });
+}
+
+long long wb_launch_count(void) { return wb::launch_counter().load(); }
+
+int wb_model_create(const wb_config* c, int dtype, wb_model** out) {
+    return guarded([&] {
+        WB_NOT_NULL(c);
+        WB_NOT_NULL(out);
+        wb::ModelConfig g;
+        g.d_model = c->d_model; g.n_heads = c->n_heads; g.enc_layers = c->encoder_layers; g.dec_layers = c->decoder_layers;
+        g.ffn = c->ffn_dim; g.vocab = c->vocab_size; g.n_mels = c->num_mel_bins; g.n_frames = c->n_frames;
+        g.n_ctx = c->max_source_positions; g.max_tgt = c->max_target_positions;
+        g.sot = c->decoder_start_token_id; g.eos = c->eos_token_id; g.pad = c->pad_token_id; g.max_length = c->max_length;
+        *out = reinterpret_cast<wb_model*>(new wb::Model(g, dtype));
+    });
+}
+int wb_model_destroy(wb_model* m) {
+    return guarded([&] { delete M(m); });
+}
+int wb_model_load_tensor(wb_model* m, const char* name, const float* data, int64_t numel) {
+    return guarded([&] {
+        WB_NOT_NULL(m);
+        WB_NOT_NULL(name);
+        M(m)->load_tensor(name, data, numel);
+    });
+}
+int wb_model_set_generation(wb_model* m, const int32_t* suppress, int n_suppress, const int32_t* begin_suppress, int n_begin,
+                            int begin_index, const int32_t* forced_pairs, int n_forced) {
+    return guarded([&] {
+        WB_NOT_NULL(m);
+        M(m)->set_generation(suppress, n_suppress, begin_suppress, n_begin, begin_index, forced_pairs, n_forced);
+    });
+}
+int wb_model_weight_bytes(const wb_model* m, size_t* bytes) {
+    return guarded([&] {
+        WB_NOT_NULL(m);
+        WB_NOT_NULL(bytes);
+        *bytes = M(m)->weight_bytes;
+    });
+}
+
+int wb_session_workspace_bytes(const wb_model* m, int max_batch, int enc_chunk, size_t* bytes) {
+    return guarded([&] {
+        WB_NOT_NULL(m);
+        WB_NOT_NULL(bytes);
+        WB_REQUIRE(max_batch > 0 && enc_chunk > 0 && enc_chunk <= max_batch, "need 0 < enc_chunk <= max_batch");
+        *bytes = wb::Session::workspace_bytes(M(m), max_batch, enc_chunk);
+    });
+}
+int wb_session_create(wb_model* m, int max_batch, int enc_chunk, void* workspace, size_t workspace_bytes, wb_session** out) {
+    return guarded([&] {
+        WB_NOT_NULL(out);
+        *out = reinterpret_cast<wb_session*>(new wb::Session(M(m), max_batch, enc_chunk, workspace, workspace_bytes));
+    });
+}
+int wb_session_destroy(wb_session* s) {
+    return guarded([&] { delete SS(s); });
+}
+
+int wb_encode(wb_session* s, const float* mel, int batch, float* enc_out_f32, wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(s);
+        SS(s)->encode(mel, batch, enc_out_f32, S(stream));
+    });
+}
+int wb_set_encoder_output(wb_session* s, const void* enc_states, int dtype, int batch, wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(s);
+        SS(s)->set_encoder_output(enc_states, dtype, batch, S(stream));
+    });
+}
+int wb_decode_begin(wb_session* s, int batch, wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(s);
+        SS(s)->decode_begin(batch, S(stream));
+    });
+}
+int wb_decode_step(wb_session* s, wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(s);
+        SS(s)->decode_step(S(stream));
+    });
+}
+int wb_decode_run(wb_session* s, int max_steps, int check_every, int* final_len, wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(s);
+        const int n = SS(s)->decode_run(max_steps, check_every, S(stream));
+        if (final_len) *final_len = n;
+    });
+}
+int wb_decode_tokens(wb_session* s, const int32_t** tokens_dev, int* row_stride) {
+    return guarded([&] {
+        WB_NOT_NULL(s);
+        WB_NOT_NULL(tokens_dev);
+        *tokens_dev = SS(s)->tokens;
+        if (row_stride) *row_stride = SS(s)->m->cfg.max_tgt;
+    });
+}
+int wb_decode_logits(wb_session* s, const float** logits_dev) {
+    return guarded([&] {
+        WB_NOT_NULL(s);
+        WB_NOT_NULL(logits_dev);
+        *logits_dev = SS(s)->logits;
+    });
+}
+int wb_decode_set_forced_tokens(wb_session* s, const int32_t* forced_dev) {
+    return guarded([&] {
+        WB_NOT_NULL(s);
+        SS(s)->forced_tokens = forced_dev;
+    });
+}
+int wb_decode_set_logits_dump(wb_session* s, float* dump_dev, int max_steps) {
+    return guarded([&] {
+        WB_NOT_NULL(s);
+        SS(s)->logits_dump = dump_dev;
+        SS(s)->logits_dump_steps = dump_dev ? max_steps : 0;
+    });
+}
+int wb_session_cross_kv(wb_session* s, int layer, const void** kv_dev, int64_t* kv_stride_elems) {
+    return guarded([&] {
+        WB_NOT_NULL(s);
+        WB_NOT_NULL(kv_dev);
+        wb::Session* ss = SS(s);
+        WB_REQUIRE(layer >= 0 && layer < ss->m->cfg.dec_layers, "layer out of range");
+        *kv_dev = (const uint8_t*)ss->cross + (size_t)layer * ss->cross_layer_elems() * wb::dtype_size(ss->m->dtype);
+        if (kv_stride_elems) *kv_stride_elems = (int64_t)(ss->cross_layer_elems() / 2);
+    });
+}
+int wb_session_self_kv(wb_session* s, int layer, const void** k_pages, const void** v_pages, const int32_t** page_table,
+                       int* pages_per_seq, int* page_tokens) {
+    return guarded([&] {
+        WB_NOT_NULL(s);
+        wb::Session* ss = SS(s);
+        WB_REQUIRE(layer >= 0 && layer < ss->m->cfg.dec_layers, "layer out of range");
+        const size_t off = (size_t)layer * ss->self_layer_elems() * wb::dtype_size(ss->m->dtype);
+        if (k_pages) *k_pages = (const uint8_t*)ss->self_k + off;
+        if (v_pages) *v_pages = (const uint8_t*)ss->self_v + off;
+        if (page_table) *page_table = ss->page_table;
+        if (pages_per_seq) *pages_per_seq = ss->pages_per_seq;
+        if (page_tokens) *page_tokens = wb::PAGE_TOKENS;
+    });
+}
+
+int wb_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_dtype, int rows, int d, float eps,
+                 wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(x); WB_NOT_NULL(gamma); WB_NOT_NULL(beta); WB_NOT_NULL(out);
+        wb::layernorm(x, gamma, beta, out, out_dtype, nullptr, rows, d, eps, nullptr, S(stream));
+    });
+}
+
+int wb_linear(const void* A, int64_t lda, const void* W, int64_t ldw, int in_dtype, const float* bias, const float* residual,
+              int64_t ldres, void* out, int64_t ldo, int out_dtype, int Mrows, int N, int K, int act, int backend,
+              wb_stream stream) {
+    return guarded([&] {
+        wb::GemmArgs a;
+        a.A = A; a.lda = lda; a.W = W; a.ldw = ldw; a.in_dtype = in_dtype; a.bias = bias; a.res = residual; a.ldres = ldres;
+        a.out = out; a.ldo = ldo; a.out_dtype = out_dtype; a.M = Mrows; a.N = N; a.K = K; a.act = act;
+        if (backend >= 100) {  // test hook: tcgen05 kernel with a fixed BLOCK_N (backend = 100 + BLOCK_N)
+            wb::set_gemm_tc_block_n(backend - 100);
+            try { wb::gemm_tc(a, S(stream)); } catch (...) { wb::set_gemm_tc_block_n(0); throw; }
+            wb::set_gemm_tc_block_n(0);
+        } else if (backend == 2) wb::gemm_tc(a, S(stream));
+        else if (backend == 1) wb::gemm_simt(a, S(stream));
+        else wb::gemm(a, S(stream));
+    });
+}
+
+int wb_encoder_stem(wb_session* s, const float* mel, int batch, float* x_out, wb_stream stream);
+
+int wb_encoder_attention(const void* qkv, void* out, int dtype, int batch, int seq, int heads, int backend, wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(qkv); WB_NOT_NULL(out);
+        if (backend == 1) wb::encoder_attention_simt(qkv, out, dtype, batch, seq, heads, S(stream));
+        else if (backend == 2) { WB_REQUIRE(dtype == wb::BF16, "tcgen05 attention is bf16 only"); wb::encoder_attention_tc(qkv, out, batch, seq, heads, S(stream)); }
+        else wb::encoder_attention(qkv, out, dtype, batch, seq, heads, S(stream));
+    });
+}
+
+int wb_decode_attention(const void* q, const void* k, const void* v, void* out, int dtype, int batch, int heads, int n_keys,
+                        int64_t kv_batch_stride, int64_t kv_head_stride, wb_stream stream) {
+    return guarded([&] {
+        wb::DecAttnArgs a;
+        a.dtype = dtype; a.q = q; a.q_stride = (long long)heads * 64; a.out = out; a.out_stride = (long long)heads * 64;
+        a.B = batch; a.H = heads; a.k = k; a.v = v; a.kv_bstride = kv_batch_stride; a.kv_hstride = kv_head_stride;
+        a.n_keys = n_keys;
+        wb::decode_attention(a, S(stream));
+    });
+}
+
+int wb_argmax(const float* logits, int64_t ld, int batch, int vocab, const uint8_t* mask, int bits, int32_t* out, wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(logits); WB_NOT_NULL(out);
+        wb::argmax_rows(logits, ld, batch, vocab, mask, bits, out, S(stream));
+    });
+}
+
+int wb_cast(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(in); WB_NOT_NULL(out);
+        wb::cast(in, in_dtype, out, out_dtype, n, S(stream));
+    });
+}
+
+int wb_encoder_stem(wb_session* s, const float* mel, int batch, float* x_out, wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(s); WB_NOT_NULL(mel); WB_NOT_NULL(x_out);
+        SS(s)->stem(mel, batch, x_out, S(stream));
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,180 @@
+// On-device greedy bookkeeping: decoder embedding, logits processors + argmax + EOS/pad handling + length
+// advance.  With these the token loop never returns to the host (the reference syncs twice per step and
+// runs three python logits processors, run.py:138-140,199-225).
+//
+// Oracle semantics reproduced (generation/utils.py:1485-1527, logits_process.py:1281-1328):
+//   scores[:, suppress] = -inf                      every step
+//   scores[:, begin_suppress] = -inf                when len(ids) == begin_index
+//   forced token                                    when len(ids) in force map (all -inf, token <- 0)
+//   tok = argmax (first maximal index); tok = tok*unfinished + pad*(1-unfinished); append;
+//   unfinished &= tok != eos; stop when no row is unfinished or len(ids) >= max_length.
+#include "wb_internal.h"
+
+namespace wb {
+
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(128) decoder_embed_kernel(const int* __restrict__ tokens, int tokens_stride,
+                                                            const StepState* __restrict__ state, const T* __restrict__ emb,
+                                                            const T* __restrict__ pos, float* __restrict__ x, int d) {
+    if (state->active == 0) return;
+    constexpr int VEC = Vec16<T>::N;
+    const int b = blockIdx.x;
+    const int p = state->cur_len - 1;  // position == past length (modeling_whisper.py:307-308, model.py:424)
+    const int tok = tokens[(size_t)b * tokens_stride + p];
+    const T* e = emb + (size_t)tok * d;
+    const T* pp = pos + (size_t)p * d;
+    for (int i = threadIdx.x * VEC; i < d; i += blockDim.x * VEC) {
+        float ef[VEC], pf[VEC];
+        ld16(e + i).unpack(ef);
+        ld16(pp + i).unpack(pf);
+#pragma unroll
+        for (int j = 0; j < VEC; j += 4)
+            *reinterpret_cast<float4*>(x + (size_t)b * d + i + j) =
+                make_float4(ef[j] + pf[j], ef[j + 1] + pf[j + 1], ef[j + 2] + pf[j + 2], ef[j + 3] + pf[j + 3]);
+    }
+}
+
+__device__ __forceinline__ void argmax_combine(float& v, int& i, float ov, int oi) {
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+
+// one block per row; returns the masked argmax in every thread of warp 0 (valid in thread 0)
+__device__ int block_masked_argmax(const float* __restrict__ row, int V, const unsigned char* __restrict__ mask,
+                                   int mask_bits) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    float best = -INFINITY;
+    int besti = 0x7fffffff;
+    const int nv = V >> 2;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        const float4 f = reinterpret_cast<const float4*>(row)[i];
+        float vals[4] = {f.x, f.y, f.z, f.w};
+        if (mask != nullptr) {
+            const uchar4 m = reinterpret_cast<const uchar4*>(mask)[i];
+            if (m.x & mask_bits) vals[0] = -INFINITY;
+            if (m.y & mask_bits) vals[1] = -INFINITY;
+            if (m.z & mask_bits) vals[2] = -INFINITY;
+            if (m.w & mask_bits) vals[3] = -INFINITY;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) argmax_combine(best, besti, vals[j], 4 * i + j);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        argmax_combine(best, besti, ov, oi);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sv[warp] = best; si[warp] = besti; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        best = lane < nw ? sv[lane] : -INFINITY;
+        besti = lane < nw ? si[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            argmax_combine(best, besti, ov, oi);
+        }
+    }
+    return besti;
+}
+
+__global__ void __launch_bounds__(1024) greedy_step_kernel(GreedyArgs a) {
+    StepState* st = a.state;
+    if (st->active == 0) return;
+    const int b = blockIdx.x;
+    const int n = st->cur_len;  // == input_ids.shape[-1] seen by the processors
+    int tok;
+    const int forced = a.force_map != nullptr ? a.force_map[n] : -1;
+    if (forced >= 0) {
+        tok = forced;
+    } else {
+        const int bits = 1 | (n == a.begin_index ? 2 : 0);
+        tok = block_masked_argmax(a.logits + (size_t)b * a.ld, a.V, a.vocab_mask, bits);
+    }
+    if (threadIdx.x == 0) {
+        const int unf = a.unfinished[b];
+        tok = unf ? tok : a.pad_id;
+        if (a.forced_tokens != nullptr) tok = a.forced_tokens[(size_t)b * a.tokens_stride + n];
+        a.tokens[(size_t)b * a.tokens_stride + n] = tok;
+        if (tok == a.eos_id) a.unfinished[b] = 0;
+        __threadfence();
+        const int prev = atomicAdd(&st->done_counter, 1);
+        if (prev == a.B - 1) {  // last row of this step: advance the shared length / stop flag
+            __threadfence();
+            int cnt = 0;
+            for (int i = 0; i < a.B; ++i) cnt += (*((volatile int*)&a.unfinished[i]) != 0);
+            const int new_len = n + 1;
+            st->n_unfinished = cnt;
+            st->done_counter = 0;
+            if (cnt == 0 || new_len >= a.max_length) {
+                st->final_len = new_len;
+                st->active = 0;
+            }
+            st->cur_len = new_len;
+        }
+    }
+}
+
+__global__ void greedy_init_kernel(int* tokens, int tokens_stride, int* unfinished, StepState* state, int B,
+                                   int start_token, int pad_id, int max_length) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * max_length) {
+        const int b = i / max_length, t = i - b * max_length;
+        tokens[(size_t)b * tokens_stride + t] = (t == 0) ? start_token : pad_id;
+    }
+    if (i < B) unfinished[i] = 1;
+    if (i == 0) {
+        state->cur_len = 1;
+        state->active = 1;
+        state->final_len = 0;
+        state->done_counter = 0;
+        state->n_unfinished = B;
+    }
+}
+
+__global__ void __launch_bounds__(1024) argmax_rows_kernel(const float* __restrict__ logits, long long ld, int V,
+                                                           const unsigned char* __restrict__ mask, int mask_bits,
+                                                           int* __restrict__ out) {
+    const int tok = block_masked_argmax(logits + (size_t)blockIdx.x * ld, V, mask, mask_bits);
+    if (threadIdx.x == 0) out[blockIdx.x] = tok;
+}
+
+}  // namespace
+
+void decoder_embed(const int* tokens, int tokens_stride, const StepState* state, const void* emb, const void* pos,
+                   int dtype, float* x, int B, int d, cudaStream_t stream) {
+    WB_REQUIRE(d % 8 == 0, "d_model must be a multiple of 8");
+    if (dtype == F32)
+        decoder_embed_kernel<float><<<B, 128, 0, stream>>>(tokens, tokens_stride, state, (const float*)emb, (const float*)pos, x, d);
+    else
+        decoder_embed_kernel<bf16><<<B, 128, 0, stream>>>(tokens, tokens_stride, state, (const bf16*)emb, (const bf16*)pos, x, d);
+    WB_CHECK_LAUNCH();
+}
+
+void greedy_step(const GreedyArgs& a, cudaStream_t stream) {
+    WB_REQUIRE(a.V % 4 == 0 && a.ld % 4 == 0, "vocab size / logits pitch must be multiples of 4");
+    greedy_step_kernel<<<a.B, 1024, 0, stream>>>(a);
+    WB_CHECK_LAUNCH();
+}
+
+void greedy_init(int* tokens, int tokens_stride, int* unfinished, StepState* state, int B, int start_token, int pad_id,
+                 int max_length, cudaStream_t stream) {
+    const int n = B * max_length;
+    greedy_init_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(tokens, tokens_stride, unfinished, state, B, start_token, pad_id, max_length);
+    WB_CHECK_LAUNCH();
+}
+
+void argmax_rows(const float* logits, long long ld, int B, int V, const unsigned char* vocab_mask, int mask_bits, int* out,
+                 cudaStream_t stream) {
+    WB_REQUIRE(V % 4 == 0 && ld % 4 == 0, "vocab size / logits pitch must be multiples of 4");
+    argmax_rows_kernel<<<B, 1024, 0, stream>>>(logits, ld, V, vocab_mask, mask_bits, out);
+    WB_CHECK_LAUNCH();
+}
+
+}  // namespace wb

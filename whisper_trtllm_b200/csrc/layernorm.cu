@@ -1,0 +1,83 @@
+// LayerNorm (eps 1e-5, fp32 statistics) over the fp32 residual stream.
+// Reference semantics: nn.LayerNorm in the oracle (modeling_whisper.py:608,613,675-686,940,1060);
+// TRT-LLM LayerNorm eps=1e-5 (layers/normalization.py:6-30).  HBM-bound: one warp per row, the whole
+// row lives in registers (d <= 1024 -> 8 float4 per lane), 16-byte coalesced loads and stores.
+#include "wb_internal.h"
+
+namespace wb {
+
+template <typename TOut>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, TOut* __restrict__ out,
+                                                        float* __restrict__ out2, int rows, int d, float eps,
+                                                        const int* __restrict__ active) {
+    if (active != nullptr && *active == 0) return;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int nvec = d >> 2;
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * d);
+    float4 v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nvec) {
+            v[i] = xr[idx];
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float mean = warp_sum(s) / (float)d;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nvec) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+            ss += (a * a + b * b) + (c * c + e * e);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)d + eps);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nvec) {
+            const float4 g = g4[idx], b = b4[idx];
+            float y[4];
+            y[0] = (v[i].x - mean) * rstd * g.x + b.x;
+            y[1] = (v[i].y - mean) * rstd * g.y + b.y;
+            y[2] = (v[i].z - mean) * rstd * g.z + b.z;
+            y[3] = (v[i].w - mean) * rstd * g.w + b.w;
+            TOut* o = out + (size_t)warp * d + idx * 4;
+            if constexpr (sizeof(TOut) == 4) {
+                *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+            } else {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]);
+                __nv_bfloat162 p1 = __floats2bfloat162_rn(y[2], y[3]);
+                uint2 u;
+                u.x = *reinterpret_cast<uint32_t*>(&p0);
+                u.y = *reinterpret_cast<uint32_t*>(&p1);
+                *reinterpret_cast<uint2*>(o) = u;
+            }
+            if (out2 != nullptr)
+                *reinterpret_cast<float4*>(out2 + (size_t)warp * d + idx * 4) = make_float4(y[0], y[1], y[2], y[3]);
+        }
+    }
+}
+
+void layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_dtype, float* out2,
+               int rows, int d, float eps, const int* active, cudaStream_t stream) {
+    WB_REQUIRE(d % 4 == 0 && d <= 1024, "layernorm supports d % 4 == 0, d <= 1024");
+    if (rows == 0) return;
+    const int warps_per_block = 8;
+    dim3 grid(ceil_div(rows, warps_per_block)), block(warps_per_block * 32);
+    if (out_dtype == F32)
+        layernorm_kernel<float><<<grid, block, 0, stream>>>(x, gamma, beta, (float*)out, out2, rows, d, eps, active);
+    else
+        layernorm_kernel<bf16><<<grid, block, 0, stream>>>(x, gamma, beta, (bf16*)out, out2, rows, d, eps, active);
+    WB_CHECK_LAUNCH();
+}
+
+}  // namespace wb

@@ -1,0 +1,502 @@
+// Native runtime: packed weights, encoder pass, cross-K/V projection, paged self-KV, on-device greedy loop.
+//
+// Weight-name mapping follows the reference's binders: build_encoder.py:71-91 (q/k/v fused into one `qkv`
+// weight with a ZERO K bias) and build_decoder.py:71-101; oracle key names per SURVEY.md Appendix B.
+// The q scale head_dim^-0.5 = 0.125 (modeling_whisper.py:472,572) is folded into the packed q weights
+// and bias: multiplying by a power of two commutes with every rounding step, so results are bit-identical
+// to scaling after the projection.
+#include "wb_runtime.h"
+
+#include <cstring>
+
+namespace wb {
+
+// ------------------------------------------------------------------------------------------------ Model
+void* Model::dalloc(size_t bytes) {
+    void* p = nullptr;
+    bytes = (bytes + 255) / 256 * 256;
+    WB_CHECK_CUDA(cudaMalloc(&p, bytes));
+    WB_CHECK_CUDA(cudaMemset(p, 0, bytes));
+    allocs.push_back(p);
+    weight_bytes += bytes;
+    return p;
+}
+
+Model::Model(const ModelConfig& c, int dt) : cfg(c), dtype(dt) {
+    WB_REQUIRE(dt == F32 || dt == BF16, "dtype must be 0 (fp32) or 1 (bf16)");
+    WB_REQUIRE(c.d_model > 0 && c.n_heads > 0 && c.d_model == c.n_heads * 64, "head_dim must be 64");
+    WB_REQUIRE(c.d_model % 64 == 0 && c.d_model <= 1024, "d_model must be a multiple of 64, <= 1024");
+    WB_REQUIRE(c.ffn % 64 == 0 && c.vocab % 8 == 0, "ffn % 64 == 0 and vocab % 8 == 0 required");
+    WB_REQUIRE(c.n_frames == 2 * c.n_ctx && c.n_frames + 8 <= H1_ROWS && c.n_ctx <= CONV2_MPERIOD, "unsupported audio window");
+    WB_REQUIRE(3 * c.n_mels <= CONV1_KPAD, "too many mel bins");
+    WB_REQUIRE(c.max_length >= 2 && c.max_length <= c.max_tgt && c.max_tgt % PAGE_TOKENS == 0, "bad max_length / max_target_positions");
+    const size_t es = dtype_size(dtype);
+    const int d = c.d_model, F = c.ffn;
+    auto lin = [&](Linear& l, int n, int k) {
+        l.n = n; l.k = k;
+        l.w = dalloc((size_t)n * k * es);
+        l.b = (float*)dalloc((size_t)n * 4);
+    };
+    auto ln = [&](LNorm& l) {
+        l.g = (float*)dalloc((size_t)d * 4);
+        l.b = (float*)dalloc((size_t)d * 4);
+    };
+    lin(conv1, d, CONV1_KPAD);
+    lin(conv2, d, 3 * d);
+    enc_pos = (float*)dalloc((size_t)c.n_ctx * d * 4);
+    enc.resize(c.enc_layers);
+    for (auto& L : enc) { ln(L.ln1); lin(L.qkv, 3 * d, d); lin(L.out, d, d); ln(L.ln2); lin(L.fc1, F, d); lin(L.fc2, d, F); }
+    ln(enc_ln);
+    emb = dalloc((size_t)c.vocab * d * es);
+    dec_pos = dalloc((size_t)c.max_tgt * d * es);
+    dec.resize(c.dec_layers);
+    for (auto& L : dec) {
+        ln(L.ln1); lin(L.qkv, 3 * d, d); lin(L.out, d, d);
+        ln(L.ln2); lin(L.cq, d, d); lin(L.ckv, 2 * d, d); lin(L.cout, d, d);
+        ln(L.ln3); lin(L.fc1, F, d); lin(L.fc2, d, F);
+    }
+    ln(dec_ln);
+    vocab_mask = (unsigned char*)dalloc((size_t)c.vocab);
+    force_map = (int*)dalloc((size_t)(c.max_tgt + 1) * 4);
+    std::vector<int> fm(c.max_tgt + 1, -1);
+    WB_CHECK_CUDA(cudaMemcpy(force_map, fm.data(), fm.size() * 4, cudaMemcpyHostToDevice));
+}
+
+Model::~Model() {
+    for (void* p : allocs) cudaFree(p);
+}
+
+int Model::expected_tensors() const { return 5 + cfg.enc_layers * 15 + 2 + 2 + cfg.dec_layers * 24 + 2; }
+
+void Model::check_complete() const {
+    if (loaded != expected_tensors())
+        throw Error(-4, "model is missing weights: loaded " + std::to_string(loaded) + " of " + std::to_string(expected_tensors()) + " tensors");
+}
+
+namespace {
+// copy `numel` host floats (optionally scaled) into dst (compute dtype) at element offset `off`
+void upload(int dtype, void* dst, size_t off, const float* host, size_t numel, float scale = 1.0f) {
+    std::vector<float> scaled;
+    if (scale != 1.0f) {
+        scaled.resize(numel);
+        for (size_t i = 0; i < numel; ++i) scaled[i] = host[i] * scale;
+        host = scaled.data();
+    }
+    if (dtype == F32) {
+        WB_CHECK_CUDA(cudaMemcpy((float*)dst + off, host, numel * 4, cudaMemcpyHostToDevice));
+    } else {
+        float* tmp = nullptr;
+        WB_CHECK_CUDA(cudaMalloc(&tmp, numel * 4));
+        cudaError_t e = cudaMemcpy(tmp, host, numel * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            try {
+                cast(tmp, F32, (bf16*)dst + off, BF16, (long long)numel, 0);
+                e = cudaStreamSynchronize(0);
+            } catch (...) { cudaFree(tmp); throw; }
+        }
+        cudaFree(tmp);
+        WB_CHECK_CUDA(e);
+    }
+}
+void upload_f32(float* dst, size_t off, const float* host, size_t numel, float scale = 1.0f) { upload(F32, dst, off, host, numel, scale); }
+
+bool starts_with(const std::string& s, const std::string& p) { return s.compare(0, p.size(), p) == 0; }
+}  // namespace
+
+void Model::load_tensor(const std::string& name, const float* host, long long numel) {
+    WB_REQUIRE(host != nullptr && numel > 0, "empty tensor " + name);
+    const int d = cfg.d_model, F = cfg.ffn;
+    const float qscale = 0.125f;
+    auto expect = [&](long long n) {
+        if (numel != n) throw Error(-1, "tensor " + name + ": expected " + std::to_string(n) + " elements, got " + std::to_string(numel));
+    };
+    auto load_ln = [&](LNorm& l, const std::string& leaf) {
+        expect(d);
+        upload_f32(leaf == "weight" ? l.g : l.b, 0, host, d);
+    };
+    auto load_lin = [&](Linear& l, const std::string& leaf, int row0, int rows, float scale) {
+        if (leaf == "weight") { expect((long long)rows * l.k); upload(dtype, l.w, (size_t)row0 * l.k, host, (size_t)rows * l.k, scale); }
+        else { expect(rows); upload_f32(l.b, row0, host, rows, scale); }
+    };
+    // attention projections of one block: fused [q*0.125 | k | v] rows (K has no bias: its slice stays zero)
+    auto load_attn = [&](const std::string& proj, const std::string& leaf, Linear& qkv_or_q, Linear* kv, Linear& outp) {
+        if (proj == "q_proj") load_lin(qkv_or_q, leaf, 0, d, qscale);
+        else if (proj == "k_proj") { if (kv) load_lin(*kv, leaf, 0, d, 1.f); else load_lin(qkv_or_q, leaf, d, d, 1.f); }
+        else if (proj == "v_proj") { if (kv) load_lin(*kv, leaf, d, d, 1.f); else load_lin(qkv_or_q, leaf, 2 * d, d, 1.f); }
+        else if (proj == "out_proj") load_lin(outp, leaf, 0, d, 1.f);
+        else throw Error(-1, "unknown attention tensor " + name);
+    };
+
+    if (name == "proj_out.weight") return;  // tied to embed_tokens (modeling_whisper.py:1335); not counted
+    const size_t dot = name.rfind('.');
+    WB_REQUIRE(dot != std::string::npos, "bad tensor name " + name);
+    const std::string leaf = name.substr(dot + 1);
+    const std::string stem = name.substr(0, dot);
+
+    if (stem == "model.encoder.conv1") {
+        if (leaf == "bias") { expect(d); upload_f32(conv1.b, 0, host, d); }
+        else {  // [d, n_mels, 3] -> [d, KPAD] with k = tap * n_mels + c
+            expect((long long)d * cfg.n_mels * 3);
+            std::vector<float> w((size_t)d * CONV1_KPAD, 0.f);
+            for (int n = 0; n < d; ++n)
+                for (int c = 0; c < cfg.n_mels; ++c)
+                    for (int t = 0; t < 3; ++t) w[(size_t)n * CONV1_KPAD + t * cfg.n_mels + c] = host[((size_t)n * cfg.n_mels + c) * 3 + t];
+            upload(dtype, conv1.w, 0, w.data(), w.size());
+        }
+    } else if (stem == "model.encoder.conv2") {
+        if (leaf == "bias") { expect(d); upload_f32(conv2.b, 0, host, d); }
+        else {  // [d, d, 3] -> [d, 3d] with k = tap * d + c
+            expect((long long)d * d * 3);
+            std::vector<float> w((size_t)d * 3 * d);
+            for (int n = 0; n < d; ++n)
+                for (int c = 0; c < d; ++c)
+                    for (int t = 0; t < 3; ++t) w[(size_t)n * 3 * d + (size_t)t * d + c] = host[((size_t)n * d + c) * 3 + t];
+            upload(dtype, conv2.w, 0, w.data(), w.size());
+        }
+    } else if (stem == "model.encoder.embed_positions") {
+        expect((long long)cfg.n_ctx * d);
+        upload_f32(enc_pos, 0, host, (size_t)cfg.n_ctx * d);
+    } else if (stem == "model.encoder.layer_norm") {
+        load_ln(enc_ln, leaf);
+    } else if (stem == "model.decoder.layer_norm") {
+        load_ln(dec_ln, leaf);
+    } else if (stem == "model.decoder.embed_tokens") {
+        expect((long long)cfg.vocab * d);
+        upload(dtype, emb, 0, host, (size_t)cfg.vocab * d);
+    } else if (stem == "model.decoder.embed_positions") {
+        expect((long long)cfg.max_tgt * d);
+        upload(dtype, dec_pos, 0, host, (size_t)cfg.max_tgt * d);
+    } else if (starts_with(stem, "model.encoder.layers.") || starts_with(stem, "model.decoder.layers.")) {
+        const bool is_enc = stem[6] == 'e';
+        const size_t p0 = std::strlen("model.encoder.layers.");
+        const size_t p1 = stem.find('.', p0);
+        WB_REQUIRE(p1 != std::string::npos, "bad layer tensor name " + name);
+        const int li = std::stoi(stem.substr(p0, p1 - p0));
+        const std::string rest = stem.substr(p1 + 1);
+        WB_REQUIRE(li >= 0 && li < (is_enc ? cfg.enc_layers : cfg.dec_layers), "layer index out of range in " + name);
+        if (is_enc) {
+            EncLayer& L = enc[li];
+            if (rest == "self_attn_layer_norm") load_ln(L.ln1, leaf);
+            else if (rest == "final_layer_norm") load_ln(L.ln2, leaf);
+            else if (rest == "fc1") load_lin(L.fc1, leaf, 0, F, 1.f);
+            else if (rest == "fc2") load_lin(L.fc2, leaf, 0, d, 1.f);
+            else if (starts_with(rest, "self_attn.")) load_attn(rest.substr(10), leaf, L.qkv, nullptr, L.out);
+            else throw Error(-1, "unknown tensor " + name);
+        } else {
+            DecLayer& L = dec[li];
+            if (rest == "self_attn_layer_norm") load_ln(L.ln1, leaf);
+            else if (rest == "encoder_attn_layer_norm") load_ln(L.ln2, leaf);
+            else if (rest == "final_layer_norm") load_ln(L.ln3, leaf);
+            else if (rest == "fc1") load_lin(L.fc1, leaf, 0, F, 1.f);
+            else if (rest == "fc2") load_lin(L.fc2, leaf, 0, d, 1.f);
+            else if (starts_with(rest, "self_attn.")) load_attn(rest.substr(10), leaf, L.qkv, nullptr, L.out);
+            else if (starts_with(rest, "encoder_attn.")) load_attn(rest.substr(13), leaf, L.cq, &L.ckv, L.cout);
+            else throw Error(-1, "unknown tensor " + name);
+        }
+    } else {
+        throw Error(-1, "unknown tensor " + name);
+    }
+    ++loaded;
+}
+
+void Model::set_generation(const int* suppress, int n_suppress, const int* begin_suppress, int n_begin, int begin_index,
+                           const int* forced_pairs, int n_forced) {
+    std::vector<unsigned char> mask(cfg.vocab, 0);
+    for (int i = 0; i < n_suppress; ++i) {
+        WB_REQUIRE(suppress[i] >= 0 && suppress[i] < cfg.vocab, "suppress token out of range");
+        mask[suppress[i]] |= 1;
+    }
+    for (int i = 0; i < n_begin; ++i) {
+        WB_REQUIRE(begin_suppress[i] >= 0 && begin_suppress[i] < cfg.vocab, "begin-suppress token out of range");
+        mask[begin_suppress[i]] |= 2;
+    }
+    WB_CHECK_CUDA(cudaMemcpy(vocab_mask, mask.data(), mask.size(), cudaMemcpyHostToDevice));
+    std::vector<int> fm(cfg.max_tgt + 1, -1);
+    for (int i = 0; i < n_forced; ++i) {
+        const int idx = forced_pairs[2 * i], tok = forced_pairs[2 * i + 1];
+        WB_REQUIRE(idx >= 0 && idx <= cfg.max_tgt && tok >= 0 && tok < cfg.vocab, "forced decoder id out of range");
+        fm[idx] = tok;
+    }
+    WB_CHECK_CUDA(cudaMemcpy(force_map, fm.data(), fm.size() * 4, cudaMemcpyHostToDevice));
+    cfg.begin_index = begin_index;
+}
+
+// ------------------------------------------------------------------------------------------------ Session
+namespace {
+struct Carver {
+    uint8_t* base; size_t off = 0, cap;
+    Carver(void* p, size_t c) : base((uint8_t*)p), cap(c) {}
+    template <typename P> void take(P*& field, size_t bytes) {
+        off = (off + 1023) / 1024 * 1024;
+        field = base ? reinterpret_cast<P*>(base + off) : nullptr;
+        off += bytes;
+        if (base && off > cap) throw Error(-1, "workspace too small: need at least " + std::to_string(off) + " bytes");
+    }
+};
+
+// single source of truth for the workspace layout (base == nullptr -> sizing pass)
+size_t layout(Buffers& b, const Model* m, int max_batch, int enc_chunk, void* base, size_t cap) {
+    const ModelConfig& g = m->cfg;
+    const size_t es = dtype_size(m->dtype), d = g.d_model, Bc = enc_chunk, B = max_batch;
+    const size_t Mc = Bc * g.n_ctx, L = g.dec_layers, H = g.n_heads;
+    const size_t pages = B * (g.max_tgt / PAGE_TOKENS);
+    Carver c(base, cap);
+    c.take(b.a1, Bc * g.n_frames * CONV1_KPAD * es);
+    c.take(b.h1p, (Bc * H1_ROWS + 8) * d * es);
+    c.take(b.x, Mc * d * 4);
+    c.take(b.ln, Mc * d * es);
+    c.take(b.qkv, Mc * 3 * d * es);
+    c.take(b.att, Mc * d * es);
+    c.take(b.ffn, Mc * g.ffn * es);
+    c.take(b.enc, B * g.n_ctx * d * es);
+    c.take(b.cross, L * 2 * B * H * g.n_ctx * 64 * es);
+    c.take(b.self_k, L * pages * H * PAGE_TOKENS * 64 * es);
+    c.take(b.self_v, L * pages * H * PAGE_TOKENS * 64 * es);
+    c.take(b.page_table, pages * 4);
+    c.take(b.dx, B * d * 4);
+    c.take(b.dln, B * d * es);
+    c.take(b.dqkv, B * 3 * d * es);
+    c.take(b.datt, B * d * es);
+    c.take(b.dq, B * d * es);
+    c.take(b.dffn, B * g.ffn * es);
+    c.take(b.logits, B * (size_t)g.vocab * 4);
+    c.take(b.tokens, B * g.max_tgt * 4);
+    c.take(b.unfinished, B * 4);
+    c.take(b.state, sizeof(StepState));
+    return c.off + 1024;
+}
+}  // namespace
+
+size_t Session::workspace_bytes(const Model* m, int max_batch, int enc_chunk) {
+    Buffers b;
+    return layout(b, m, max_batch, enc_chunk, nullptr, 0);
+}
+
+Session::Session(Model* model, int mb, int ec, void* workspace, size_t workspace_bytes) : m(model), max_batch(mb), enc_chunk(ec) {
+    WB_REQUIRE(model != nullptr && workspace != nullptr, "null model / workspace");
+    WB_REQUIRE(mb > 0 && ec > 0 && ec <= mb, "need 0 < enc_chunk <= max_batch");
+    WB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+    model->check_complete();
+    // align the carve base to 1024 so every buffer is TMA-friendly
+    uint8_t* base = (uint8_t*)workspace;
+    const size_t skew = (1024 - (reinterpret_cast<uintptr_t>(base) & 1023)) & 1023;
+    WB_REQUIRE(workspace_bytes > skew, "workspace too small");
+    layout(*this, model, mb, ec, base + skew, workspace_bytes - skew);
+    pages_per_seq = model->cfg.max_tgt / PAGE_TOKENS;
+    num_pages = mb * pages_per_seq;
+    // page allocator: every row owns its pages up front (identity map); the kernels only see the table
+    std::vector<int> pt((size_t)num_pages);
+    for (int i = 0; i < num_pages; ++i) pt[i] = i;
+    WB_CHECK_CUDA(cudaMemcpy(page_table, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice));
+    WB_CHECK_CUDA(cudaMemset(h1p, 0, ((size_t)ec * H1_ROWS + 8) * model->cfg.d_model * dtype_size(model->dtype)));
+    WB_CHECK_CUDA(cudaMemset(state, 0, sizeof(StepState)));
+    WB_CHECK_CUDA(cudaMallocHost(&host_state, sizeof(StepState)));
+    std::memset(host_state, 0, sizeof(StepState));
+    WB_CHECK_CUDA(cudaEventCreateWithFlags(&check_event, cudaEventDisableTiming));
+}
+
+Session::~Session() {
+    if (host_state) cudaFreeHost(host_state);
+    if (check_event) cudaEventDestroy(check_event);
+}
+
+size_t Session::cross_layer_elems() const { return (size_t)2 * max_batch * m->cfg.n_heads * m->cfg.n_ctx * 64; }
+size_t Session::self_layer_elems() const { return (size_t)num_pages * m->cfg.n_heads * PAGE_TOKENS * 64; }
+
+namespace {
+inline void* eoff(void* p, size_t elems, int dtype) { return (uint8_t*)p + elems * dtype_size(dtype); }
+
+GemmArgs linear_args(const Model* m, const void* A, long long lda, const Linear& l, void* out, long long ldo, int out_dtype, int M) {
+    GemmArgs g;
+    g.A = A; g.lda = lda; g.W = l.w; g.ldw = l.k; g.in_dtype = m->dtype; g.bias = l.b;
+    g.out = out; g.ldo = ldo; g.out_dtype = out_dtype; g.M = M; g.N = l.n; g.K = l.k;
+    return g;
+}
+}  // namespace
+
+// cross-attention K/V for utterances [b0, b0+bc): one GEMM per decoder layer, scattered head-major
+static void project_cross_kv(Session* s, int b0, int bc, cudaStream_t st) {
+    const Model* m = s->m;
+    const ModelConfig& g = m->cfg;
+    const int d = g.d_model;
+    for (int l = 0; l < g.dec_layers; ++l) {
+        GemmArgs a = linear_args(m, eoff(s->enc, (size_t)b0 * g.n_ctx * d, m->dtype), d, m->dec[l].ckv,
+                                 eoff(s->cross, (size_t)l * s->cross_layer_elems(), m->dtype), 0, m->dtype, bc * g.n_ctx);
+        a.m_period_in = g.n_ctx; a.m_valid = g.n_ctx; a.m_period_out = g.n_ctx;
+        a.out_mode = 1; a.hs_heads = g.n_heads; a.hs_batch = s->max_batch; a.hs_b0 = b0;
+        gemm(a, st);
+    }
+}
+
+// conv1 (+GELU) as a GEMM over the im2col'd mel; conv2 (+GELU, +positions) as a GEMM over sliding windows of
+// the zero-padded, time-major conv1 output.  Result: fp32 residual stream x [bc * n_ctx, d].
+void Session::stem_chunk(const float* mel, int bc, cudaStream_t st) {
+    const ModelConfig& g = m->cfg;
+    const int d = g.d_model, dt = m->dtype;
+    im2col_conv1(mel, a1, dt, bc, g.n_mels, g.n_frames, CONV1_KPAD, st);
+    {
+        GemmArgs a = linear_args(m, a1, CONV1_KPAD, m->conv1, h1p, d, dt, bc * g.n_frames);
+        a.act = 1;
+        a.m_period_in = g.n_frames; a.m_valid = g.n_frames; a.m_period_out = H1_ROWS; a.m_out_offset = 1;
+        gemm(a, st);
+    }
+    {
+        GemmArgs a = linear_args(m, h1p, 2 * d, m->conv2, x, d, F32, bc * CONV2_MPERIOD);
+        a.act = 1;
+        a.res = m->enc_pos; a.ldres = d; a.res_periodic = 1;
+        a.m_period_in = CONV2_MPERIOD; a.m_valid = g.n_ctx; a.m_period_out = g.n_ctx;
+        gemm(a, st);
+    }
+}
+
+void Session::stem(const float* mel, int B, float* x_out, cudaStream_t st) {
+    WB_REQUIRE(B > 0 && B <= enc_chunk, "stem batch must be <= enc_chunk");
+    stem_chunk(mel, B, st);
+    WB_CHECK_CUDA(cudaMemcpyAsync(x_out, x, (size_t)B * m->cfg.n_ctx * m->cfg.d_model * 4, cudaMemcpyDeviceToDevice, st));
+}
+
+void Session::encode(const float* mel, int B, float* enc_out_f32, cudaStream_t st) {
+    WB_REQUIRE(mel != nullptr && B > 0 && B <= max_batch, "bad encode batch");
+    const ModelConfig& g = m->cfg;
+    const int d = g.d_model, dt = m->dtype;
+    for (int b0 = 0; b0 < B; b0 += enc_chunk) {
+        const int bc = std::min(enc_chunk, B - b0);
+        const int M = bc * g.n_ctx;
+        stem_chunk(mel + (size_t)b0 * g.n_mels * g.n_frames, bc, st);
+        // ---- transformer layers (pre-LN), fp32 residual stream in x
+        for (int l = 0; l < g.enc_layers; ++l) {
+            const EncLayer& L = m->enc[l];
+            layernorm(x, L.ln1.g, L.ln1.b, ln, dt, nullptr, M, d, 1e-5f, nullptr, st);
+            gemm(linear_args(m, ln, d, L.qkv, qkv, 3 * d, dt, M), st);
+            encoder_attention(qkv, att, dt, bc, g.n_ctx, g.n_heads, st);
+            {
+                GemmArgs a = linear_args(m, att, d, L.out, x, d, F32, M);
+                a.res = x; a.ldres = d;
+                gemm(a, st);
+            }
+            layernorm(x, L.ln2.g, L.ln2.b, ln, dt, nullptr, M, d, 1e-5f, nullptr, st);
+            {
+                GemmArgs a = linear_args(m, ln, d, L.fc1, ffn, g.ffn, dt, M);
+                a.act = 1;
+                gemm(a, st);
+            }
+            {
+                GemmArgs a = linear_args(m, ffn, g.ffn, L.fc2, x, d, F32, M);
+                a.res = x; a.ldres = d;
+                gemm(a, st);
+            }
+        }
+        layernorm(x, m->enc_ln.g, m->enc_ln.b, eoff(enc, (size_t)b0 * g.n_ctx * d, dt), dt,
+                  enc_out_f32 ? enc_out_f32 + (size_t)b0 * g.n_ctx * d : nullptr, M, d, 1e-5f, nullptr, st);
+        project_cross_kv(this, b0, bc, st);
+    }
+}
+
+void Session::set_encoder_output(const void* enc_states, int dtype, int B, cudaStream_t st) {
+    WB_REQUIRE(enc_states != nullptr && B > 0 && B <= max_batch, "bad encoder states");
+    const ModelConfig& g = m->cfg;
+    cast(enc_states, dtype, enc, m->dtype, (long long)B * g.n_ctx * g.d_model, st);
+    for (int b0 = 0; b0 < B; b0 += enc_chunk) project_cross_kv(this, b0, std::min(enc_chunk, B - b0), st);
+}
+
+void Session::decode_begin(int B, cudaStream_t st) {
+    WB_REQUIRE(B > 0 && B <= max_batch, "bad decode batch");
+    const ModelConfig& g = m->cfg;
+    batch = B;
+    steps_enqueued = 0;
+    greedy_init(tokens, g.max_tgt, unfinished, state, B, g.sot, g.pad, g.max_tgt, st);
+}
+
+void Session::decode_step(cudaStream_t st) {
+    WB_REQUIRE(batch > 0, "decode_begin was not called");
+    const ModelConfig& g = m->cfg;
+    const int d = g.d_model, dt = m->dtype, B = batch;
+    const int* active = &state->active;
+    auto lin = [&](const void* A, long long lda, const Linear& l, void* out, long long ldo, int odt, int act, const float* res) {
+        GemmArgs a = linear_args(m, A, lda, l, out, ldo, odt, B);
+        a.act = act; a.res = res; a.ldres = d; a.active = active;
+        gemm(a, st);
+    };
+    decoder_embed(tokens, g.max_tgt, state, m->emb, m->dec_pos, dt, dx, B, d, st);
+    for (int l = 0; l < g.dec_layers; ++l) {
+        const DecLayer& L = m->dec[l];
+        // --- self attention: fused q|k|v projection, in-place paged append, one-query attention
+        layernorm(dx, L.ln1.g, L.ln1.b, dln, dt, nullptr, B, d, 1e-5f, active, st);
+        lin(dln, d, L.qkv, dqkv, 3 * d, dt, 0, nullptr);
+        {
+            DecAttnArgs a;
+            a.dtype = dt; a.q = dqkv; a.q_stride = 3 * d; a.out = datt; a.out_stride = d; a.B = B; a.H = g.n_heads;
+            a.state = state;
+            a.k_new = eoff(dqkv, d, dt); a.v_new = eoff(dqkv, 2 * d, dt); a.new_stride = 3 * d;
+            a.k_pages = eoff(self_k, (size_t)l * self_layer_elems(), dt);
+            a.v_pages = eoff(self_v, (size_t)l * self_layer_elems(), dt);
+            a.page_table = page_table; a.pages_per_seq = pages_per_seq; a.page_tokens = PAGE_TOKENS;
+            decode_attention(a, st);
+        }
+        lin(datt, d, L.out, dx, d, F32, 0, dx);
+        // --- cross attention over the K/V projected once per utterance
+        layernorm(dx, L.ln2.g, L.ln2.b, dln, dt, nullptr, B, d, 1e-5f, active, st);
+        lin(dln, d, L.cq, dq, d, dt, 0, nullptr);
+        {
+            DecAttnArgs a;
+            a.dtype = dt; a.q = dq; a.q_stride = d; a.out = datt; a.out_stride = d; a.B = B; a.H = g.n_heads;
+            a.state = nullptr; a.n_keys = g.n_ctx;
+            const size_t per_kv = (size_t)max_batch * g.n_heads * g.n_ctx * 64;
+            a.k = eoff(cross, (size_t)l * cross_layer_elems(), dt);
+            a.v = eoff(cross, (size_t)l * cross_layer_elems() + per_kv, dt);
+            a.kv_bstride = (long long)g.n_heads * g.n_ctx * 64; a.kv_hstride = (long long)g.n_ctx * 64;
+            decode_attention(a, st);
+        }
+        lin(datt, d, L.cout, dx, d, F32, 0, dx);
+        // --- MLP
+        layernorm(dx, L.ln3.g, L.ln3.b, dln, dt, nullptr, B, d, 1e-5f, active, st);
+        lin(dln, d, L.fc1, dffn, g.ffn, dt, 1, nullptr);
+        lin(dffn, g.ffn, L.fc2, dx, d, F32, 0, dx);
+    }
+    layernorm(dx, m->dec_ln.g, m->dec_ln.b, dln, dt, nullptr, B, d, 1e-5f, active, st);
+    {
+        // LM head: proj_out shares storage with embed_tokens (modeling_whisper.py:1335,1433), no bias
+        GemmArgs a;
+        a.A = dln; a.lda = d; a.W = m->emb; a.ldw = d; a.in_dtype = dt;
+        a.out = logits; a.ldo = g.vocab; a.out_dtype = F32; a.M = B; a.N = g.vocab; a.K = d; a.active = active;
+        gemm(a, st);
+    }
+    if (logits_dump != nullptr && steps_enqueued < logits_dump_steps)
+        WB_CHECK_CUDA(cudaMemcpyAsync(logits_dump + (size_t)steps_enqueued * B * g.vocab, logits, (size_t)B * g.vocab * 4,
+                                      cudaMemcpyDeviceToDevice, st));
+    {
+        GreedyArgs a;
+        a.logits = logits; a.ld = g.vocab; a.B = B; a.V = g.vocab;
+        a.vocab_mask = m->vocab_mask; a.begin_index = g.begin_index; a.force_map = m->force_map;
+        a.pad_id = g.pad; a.eos_id = g.eos; a.max_length = g.max_length;
+        a.tokens = tokens; a.tokens_stride = g.max_tgt; a.unfinished = unfinished; a.state = state;
+        a.forced_tokens = forced_tokens;
+        greedy_step(a, st);
+    }
+    ++steps_enqueued;
+}
+
+int Session::decode_run(int max_steps, int check_every, cudaStream_t st) {
+    const ModelConfig& g = m->cfg;
+    if (max_steps <= 0 || max_steps > g.max_length - 1) max_steps = g.max_length - 1;
+    if (check_every <= 0) check_every = 32;
+    bool pending = false, stopped = false;
+    for (int i = 0; i < max_steps && !stopped; ++i) {
+        decode_step(st);
+        if ((i + 1) % check_every == 0 && i + 1 < max_steps) {
+            // look at the PREVIOUS snapshot (long finished while a window of steps is still queued), then take a new one
+            if (pending) {
+                WB_CHECK_CUDA(cudaEventSynchronize(check_event));
+                if (host_state->active == 0) stopped = true;
+            }
+            WB_CHECK_CUDA(cudaMemcpyAsync(host_state, state, sizeof(StepState), cudaMemcpyDeviceToHost, st));
+            WB_CHECK_CUDA(cudaEventRecord(check_event, st));
+            pending = true;
+        }
+    }
+    WB_CHECK_CUDA(cudaMemcpyAsync(host_state, state, sizeof(StepState), cudaMemcpyDeviceToHost, st));
+    WB_CHECK_CUDA(cudaStreamSynchronize(st));
+    return host_state->active ? host_state->cur_len : host_state->final_len;
+}
+
+}  // namespace wb

@@ -1,0 +1,155 @@
+// Shared device/host helpers for the sm_100a Whisper kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+namespace wb {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: kernels launchers throw, the C-ABI boundary (abi.cu) catches and returns codes
+// ---------------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define WB_CHECK_CUDA(expr)                                                                      \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            throw ::wb::Error(-2, std::string(#expr) + " failed: " + cudaGetErrorString(_e) +    \
+                                      " (" __FILE__ ":" + std::to_string(__LINE__) + ")");       \
+    } while (0)
+
+#define WB_REQUIRE(cond, msg)                                                                    \
+    do {                                                                                         \
+        if (!(cond))                                                                             \
+            throw ::wb::Error(-1, std::string("invalid argument: ") + (msg) + " [" #cond "] (" + \
+                                      __FILE__ ":" + std::to_string(__LINE__) + ")");            \
+    } while (0)
+
+// every kernel launch of this library goes through WB_CHECK_LAUNCH, which also counts it (bench `gpu_launches`)
+inline std::atomic<long long>& launch_counter() {
+    static std::atomic<long long> c{0};
+    return c;
+}
+#define WB_CHECK_LAUNCH()                                                \
+    do {                                                                 \
+        ::wb::launch_counter().fetch_add(1, std::memory_order_relaxed);  \
+        WB_CHECK_CUDA(cudaGetLastError());                               \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// dtypes
+// ---------------------------------------------------------------------------------------------
+enum DType : int { F32 = 0, BF16 = 1 };
+using bf16 = __nv_bfloat16;
+
+template <typename T> struct DTypeOf;
+template <> struct DTypeOf<float> { static constexpr DType value = F32; };
+template <> struct DTypeOf<bf16> { static constexpr DType value = BF16; };
+
+inline size_t dtype_size(int dt) { return dt == F32 ? 4 : 2; }
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 16-byte vector of T: 4 floats or 8 bf16
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+    static constexpr int N = 4;
+    float4 raw;
+    __device__ __forceinline__ void unpack(float* f) const { f[0] = raw.x; f[1] = raw.y; f[2] = raw.z; f[3] = raw.w; }
+    __device__ __forceinline__ void pack(const float* f) { raw = make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <> struct Vec16<bf16> {
+    static constexpr int N = 8;
+    uint4 raw;
+    __device__ __forceinline__ void unpack(float* f) const {
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // bf16 -> f32 is a 16-bit shift
+            f[2 * i] = __uint_as_float(w[i] << 16);
+            f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    __device__ __forceinline__ void pack(const float* f) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&p);
+        }
+        raw = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+template <typename T> __device__ __forceinline__ Vec16<T> ld16(const T* p) {
+    Vec16<T> v;
+    v.raw = *reinterpret_cast<const decltype(v.raw)*>(p);
+    return v;
+}
+// streaming (read-once) 16-byte load: bypass L1 allocation
+template <typename T> __device__ __forceinline__ Vec16<T> ld16_stream(const T* p) {
+    Vec16<T> v;
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    v.raw = *reinterpret_cast<decltype(v.raw)*>(&r);
+    return v;
+}
+template <typename T> __device__ __forceinline__ void st16(T* p, const Vec16<T>& v) {
+    *reinterpret_cast<decltype(v.raw)*>(p) = v.raw;
+}
+
+// ---------------------------------------------------------------------------------------------
+// math
+// ---------------------------------------------------------------------------------------------
+// exact-erf GELU, the oracle's activation (transformers/activations.py:214 -> nn.functional.gelu)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// erf to ~1.5e-7 abs (Abramowitz-Stegun 7.1.26), cheap enough to hide under the MMA in bf16 epilogues
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = 1.0f - p * t * __expf(-z * z);  // erf(|x|/sqrt2)
+    return 0.5f * x + 0.5f * fabsf(x) * e;          // 0.5x(1+sign(x)erf) = 0.5x + 0.5|x|erf(|x|/sqrt2)
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Decode-loop kernels read the current length and the "still running" flag from device memory so
+// that the whole greedy loop can be enqueued (or graph-replayed) without a host round trip.
+struct StepState {
+    int cur_len;       // tokens already in ids (>= 1); position of the token being fed = cur_len - 1
+    int active;        // 1 while the loop runs; 0 once every row finished or max_length was reached
+    int final_len;     // length of ids when the loop stopped
+    int done_counter;  // last-block detection in the greedy kernel
+    int n_unfinished;  // rows not yet at EOS
+    int pad[3];
+};
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace wb

@@ -1,0 +1,99 @@
+// Model / session objects behind the C-ABI (include/whisper_b200.h).  Native runtime: weight packing,
+// encoder pass, cross-K/V projection, the on-device greedy loop.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "wb_internal.h"
+
+namespace wb {
+
+struct ModelConfig {
+    int d_model = 0, n_heads = 0, enc_layers = 0, dec_layers = 0, ffn = 0, vocab = 0;
+    int n_mels = 80, n_frames = 3000, n_ctx = 1500, max_tgt = 448;
+    int sot = 50257, eos = 50256, pad = 50256, max_length = 448, begin_index = 2;
+};
+
+struct Linear { void* w = nullptr; float* b = nullptr; int n = 0, k = 0; };
+struct LNorm { float* g = nullptr; float* b = nullptr; };
+struct EncLayer { LNorm ln1, ln2; Linear qkv, out, fc1, fc2; };
+struct DecLayer { LNorm ln1, ln2, ln3; Linear qkv, out, cq, ckv, cout, fc1, fc2; };
+
+constexpr int CONV1_KPAD = 256;   // 3 * 80 = 240 zero-padded to a multiple of the 64-wide K block
+constexpr int H1_ROWS = 3008;     // rows per utterance of the padded conv1 output (1 zero row + 3000 + 7 zero rows)
+constexpr int CONV2_MPERIOD = 1504;
+constexpr int PAGE_TOKENS = 64;
+
+struct Model {
+    ModelConfig cfg;
+    int dtype = F32;
+    Linear conv1, conv2;
+    float* enc_pos = nullptr;
+    std::vector<EncLayer> enc;
+    LNorm enc_ln;
+    void* emb = nullptr;
+    void* dec_pos = nullptr;
+    std::vector<DecLayer> dec;
+    LNorm dec_ln;
+    unsigned char* vocab_mask = nullptr;
+    int* force_map = nullptr;
+    std::vector<void*> allocs;
+    size_t weight_bytes = 0;
+    long long loaded = 0;
+
+    Model(const ModelConfig& c, int dt);
+    ~Model();
+    void* dalloc(size_t bytes);
+    // HF state_dict key -> packed device weights (fp32 host data)
+    void load_tensor(const std::string& name, const float* host, long long numel);
+    void set_generation(const int* suppress, int n_suppress, const int* begin_suppress, int n_begin, int begin_index,
+                        const int* forced_pairs, int n_forced);
+    void check_complete() const;
+    int expected_tensors() const;
+};
+
+// device buffers carved out of the caller-provided workspace
+struct Buffers {
+    // encoder workspace (sized for enc_chunk utterances)
+    void* a1 = nullptr; void* h1p = nullptr; float* x = nullptr; void* ln = nullptr; void* qkv = nullptr;
+    void* att = nullptr; void* ffn = nullptr;
+    void* enc = nullptr;        // [max_batch * n_ctx, d] encoder output in the compute dtype
+    // caches
+    void* cross = nullptr;      // [L][2][max_batch][H][n_ctx][64]
+    void* self_k = nullptr;     // [L][num_pages][H][PAGE_TOKENS][64]
+    void* self_v = nullptr;
+    int* page_table = nullptr;  // [max_batch][pages_per_seq]
+    // decode activations
+    float* dx = nullptr; void* dln = nullptr; void* dqkv = nullptr; void* datt = nullptr; void* dq = nullptr;
+    void* dffn = nullptr; float* logits = nullptr;
+    int* tokens = nullptr; int* unfinished = nullptr; StepState* state = nullptr;
+};
+
+struct Session : Buffers {
+    Model* m;
+    int max_batch, enc_chunk;
+    int pages_per_seq = 0, num_pages = 0;
+    const int* forced_tokens = nullptr;  // teacher forcing (tests): [B, max_length]
+    float* logits_dump = nullptr; int logits_dump_steps = 0;
+    int batch = 0;
+    int steps_enqueued = 0;
+    StepState* host_state = nullptr;  // pinned
+    cudaEvent_t check_event = nullptr;
+    bool h1p_zeroed = false;
+
+    Session(Model* model, int max_batch, int enc_chunk, void* workspace, size_t workspace_bytes);
+    ~Session();
+    static size_t workspace_bytes(const Model* m, int max_batch, int enc_chunk);
+
+    void stem_chunk(const float* mel, int bc, cudaStream_t s);
+    void stem(const float* mel, int B, float* x_out, cudaStream_t s);
+    void encode(const float* mel, int B, float* enc_out_f32, cudaStream_t s);   // also projects cross K/V
+    void set_encoder_output(const void* enc_states, int dtype, int B, cudaStream_t s);  // external encoder states
+    void decode_begin(int B, cudaStream_t s);
+    void decode_step(cudaStream_t s);
+    int decode_run(int max_steps, int check_every, cudaStream_t s);  // returns final length (syncs)
+    size_t cross_layer_elems() const;
+    size_t self_layer_elems() const;
+};
+
+}  // namespace wb

@@ -1,0 +1,219 @@
+"""WhisperEngine — packed weights + a session of libwhisper_b200 (the native runtime).
+
+Takes the place of the reference's two serialized TensorRT engines plus ``config.pkl``
+(examples/whisper/build_encoder.py:30-109, build_decoder.py:30-119, run.py:250-256): weights come
+straight from an HF ``state_dict`` (same keys the reference's binders read) and are packed once on the
+device; nothing is traced or compiled.  PyTorch is used only to own device memory and streams.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import _abi
+from ._abi import byref, c_int, c_int32, c_int64, c_size_t, c_void_p, ptr, stream_handle
+
+_DTYPES = {"float32": _abi.F32, "fp32": _abi.F32, "bfloat16": _abi.BF16, "bf16": _abi.BF16,
+           torch.float32: _abi.F32, torch.bfloat16: _abi.BF16}
+_TORCH_DTYPE = {_abi.F32: torch.float32, _abi.BF16: torch.bfloat16}
+
+
+def begin_index_of(config: Dict, input_ids_seq_length: int = 1) -> int:
+    """begin_index of SuppressTokensAtBeginLogitsProcessor exactly as run.py:155-158 computes it."""
+    b = input_ids_seq_length
+    if config.get("forced_bos_token_id") is not None:
+        b += 1
+    return b + config["forced_decoder_ids"][-1][0]
+
+
+class WhisperEngine:
+    def __init__(self, config: Dict, state_dict: Dict[str, torch.Tensor], dtype="float32", max_batch: int = 1,
+                 enc_chunk: Optional[int] = None, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise _abi.WhisperB200Error(-101, "a CUDA device is required (no CPU fallback)")
+        self.lib = _abi.load()
+        self.config = dict(config)
+        self.dtype_code = _DTYPES[dtype]
+        self.torch_dtype = _TORCH_DTYPE[self.dtype_code]
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.max_batch = int(max_batch)
+        self.enc_chunk = int(min(enc_chunk or 32, max_batch))
+        c = config
+        assert c["encoder_attention_heads"] == c["decoder_attention_heads"] and c["encoder_ffn_dim"] == c["decoder_ffn_dim"]
+        self._cfg = _abi.wb_config(
+            d_model=c["d_model"], n_heads=c["encoder_attention_heads"], encoder_layers=c["encoder_layers"],
+            decoder_layers=c["decoder_layers"], ffn_dim=c["encoder_ffn_dim"], vocab_size=c["vocab_size"],
+            num_mel_bins=c["num_mel_bins"], n_frames=2 * c["max_source_positions"],
+            max_source_positions=c["max_source_positions"], max_target_positions=c["max_target_positions"],
+            decoder_start_token_id=c["decoder_start_token_id"], eos_token_id=c["eos_token_id"],
+            pad_token_id=c["pad_token_id"], max_length=c["max_length"])
+        self._model = c_void_p()
+        self._session = c_void_p()
+        with torch.cuda.device(self.device):
+            _abi.call("wb_model_create", byref(self._cfg), self.dtype_code, byref(self._model))
+            self._load_state_dict(state_dict)
+            self._set_generation()
+            nbytes = c_size_t()
+            _abi.call("wb_session_workspace_bytes", self._model, self.max_batch, self.enc_chunk, byref(nbytes))
+            self.workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+            _abi.call("wb_session_create", self._model, self.max_batch, self.enc_chunk, ptr(self.workspace),
+                      c_size_t(nbytes.value), byref(self._session))
+        self.d_model = c["d_model"]
+        self.n_ctx = c["max_source_positions"]
+        self.vocab = c["vocab_size"]
+        self.max_tgt = c["max_target_positions"]
+        self._keepalive = []
+
+    # ------------------------------------------------------------------ weights
+    def _load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        """HF state_dict -> packed device weights (mapping of build_encoder.py:71-91 / build_decoder.py:71-101,
+        done natively in csrc/runtime.cu Model::load_tensor)."""
+        for name, t in sd.items():
+            if name == "proj_out.weight":
+                emb = sd.get("model.decoder.embed_tokens.weight")
+                if emb is not None and t.data_ptr() != emb.data_ptr() and not torch.equal(t, emb):
+                    raise ValueError("proj_out.weight is not tied to embed_tokens (modeling_whisper.py:1335)")
+                continue
+            h = t.detach().to(device="cpu", dtype=torch.float32).contiguous()
+            _abi.call("wb_model_load_tensor", self._model, name.encode(), c_void_p(h.data_ptr()), c_int64(h.numel()))
+
+    def _set_generation(self):
+        c = self.config
+        sup = (c_int32 * len(c["suppress_tokens"]))(*c["suppress_tokens"])
+        beg = (c_int32 * len(c["begin_suppress_tokens"]))(*c["begin_suppress_tokens"])
+        flat = [int(v) for pair in c["forced_decoder_ids"] for v in pair]
+        forced = (c_int32 * len(flat))(*flat)
+        _abi.call("wb_model_set_generation", self._model, sup, len(c["suppress_tokens"]), beg,
+                  len(c["begin_suppress_tokens"]), begin_index_of(c), forced, len(c["forced_decoder_ids"]))
+
+    def weight_bytes(self) -> int:
+        n = c_size_t()
+        _abi.call("wb_model_weight_bytes", self._model, byref(n))
+        return n.value
+
+    # ------------------------------------------------------------------ encoder
+    def encode(self, mel: torch.Tensor, return_hidden: bool = True, stream=None) -> Optional[torch.Tensor]:
+        """mel fp32 [B, 80, 3000] on the device -> hidden_states fp32 [B, 1500, d]; fills the cross K/V caches."""
+        assert mel.is_cuda and mel.dtype == torch.float32 and mel.is_contiguous(), "mel must be a contiguous fp32 CUDA tensor"
+        B = mel.shape[0]
+        out = torch.empty(B, self.n_ctx, self.d_model, dtype=torch.float32, device=mel.device) if return_hidden else None
+        _abi.call("wb_encode", self._session, ptr(mel), B, ptr(out), stream_handle(stream))
+        return out
+
+    def set_encoder_output(self, enc: torch.Tensor, stream=None):
+        assert enc.is_cuda and enc.is_contiguous() and enc.dtype in (torch.float32, torch.bfloat16)
+        _abi.call("wb_set_encoder_output", self._session, ptr(enc), _DTYPES[enc.dtype], enc.shape[0], stream_handle(stream))
+
+    # ------------------------------------------------------------------ greedy decode
+    def decode_begin(self, batch: int, stream=None):
+        _abi.call("wb_decode_begin", self._session, batch, stream_handle(stream))
+
+    def decode_step(self, stream=None):
+        _abi.call("wb_decode_step", self._session, stream_handle(stream))
+
+    def decode_run(self, max_steps: int = 0, check_every: int = 32, stream=None) -> int:
+        n = c_int()
+        _abi.call("wb_decode_run", self._session, max_steps, check_every, byref(n), stream_handle(stream))
+        return n.value
+
+    def _view(self, address: int, shape, dtype) -> torch.Tensor:
+        """Zero-copy torch view of session-owned device memory (lives inside self.workspace)."""
+        off = address - self.workspace.data_ptr()
+        n = 1
+        for s in shape:
+            n *= s
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        assert 0 <= off and off + nbytes <= self.workspace.numel()
+        return self.workspace[off:off + nbytes].view(dtype).view(*shape)
+
+    def tokens(self) -> torch.Tensor:
+        """ids int32 [max_batch, max_target_positions] (view into the session)."""
+        p, stride = c_void_p(), c_int()
+        _abi.call("wb_decode_tokens", self._session, byref(p), byref(stride))
+        return self._view(p.value, (self.max_batch, stride.value), torch.int32)
+
+    def logits(self) -> torch.Tensor:
+        p = c_void_p()
+        _abi.call("wb_decode_logits", self._session, byref(p))
+        return self._view(p.value, (self.max_batch, self.vocab), torch.float32)
+
+    def cross_kv(self, layer: int) -> torch.Tensor:
+        """[2, max_batch, H, 1500, 64] view of the cross-attention cache of one decoder layer."""
+        p, stride = c_void_p(), c_int64()
+        _abi.call("wb_session_cross_kv", self._session, layer, byref(p), byref(stride))
+        H = self.config["decoder_attention_heads"]
+        return self._view(p.value, (2, self.max_batch, H, self.n_ctx, 64), self.torch_dtype)
+
+    def self_kv(self, layer: int, batch: int, length: int):
+        """Gather the paged self-attention cache of one layer into dense [B, H, length, 64] K and V."""
+        kp, vp, pt, pps, ptok = c_void_p(), c_void_p(), c_void_p(), c_int(), c_int()
+        _abi.call("wb_session_self_kv", self._session, layer, byref(kp), byref(vp), byref(pt), byref(pps), byref(ptok))
+        H = self.config["decoder_attention_heads"]
+        num_pages = self.max_batch * pps.value
+        k = self._view(kp.value, (num_pages, H, ptok.value, 64), self.torch_dtype)
+        v = self._view(vp.value, (num_pages, H, ptok.value, 64), self.torch_dtype)
+        table = self._view(pt.value, (self.max_batch, pps.value), torch.int32)[:batch].long()
+        def dense(pages):
+            g = pages[table]                                  # [B, pps, H, tok, 64]
+            g = g.permute(0, 2, 1, 3, 4).reshape(batch, H, pps.value * ptok.value, 64)
+            return g[:, :, :length].contiguous()
+        return dense(k), dense(v)
+
+    @torch.no_grad()
+    def generate(self, mel: torch.Tensor, max_new_tokens: Optional[int] = None, forced_tokens: Optional[torch.Tensor] = None,
+                 dump_logits_steps: int = 0, check_every: int = 32, stream=None):
+        """Encoder + on-device greedy loop.  Returns ids int32 [B, L] (L as the oracle's loop would stop),
+        plus per-step raw logits [steps, B, V] when ``dump_logits_steps`` > 0."""
+        B = mel.shape[0]
+        self.encode(mel, return_hidden=False, stream=stream)
+        return self.greedy(B, max_new_tokens, forced_tokens, dump_logits_steps, check_every, stream)
+
+    @torch.no_grad()
+    def greedy(self, B: int, max_new_tokens=None, forced_tokens=None, dump_logits_steps: int = 0, check_every: int = 32,
+               stream=None):
+        dump = None
+        if forced_tokens is not None:
+            ft = torch.full((B, self.max_tgt), self.config["pad_token_id"], dtype=torch.int32, device=self.device)
+            ft[:, :forced_tokens.shape[1]] = forced_tokens.to(device=self.device, dtype=torch.int32)
+            self._keepalive = [ft]
+            _abi.call("wb_decode_set_forced_tokens", self._session, ptr(ft))
+        else:
+            _abi.call("wb_decode_set_forced_tokens", self._session, None)
+        if dump_logits_steps > 0:
+            dump = torch.empty(dump_logits_steps, B, self.vocab, dtype=torch.float32, device=self.device)
+        _abi.call("wb_decode_set_logits_dump", self._session, ptr(dump), dump_logits_steps)
+        self.decode_begin(B, stream)
+        steps = 0 if max_new_tokens is None else int(max_new_tokens)
+        final_len = self.decode_run(steps, check_every, stream)
+        ids = self.tokens()[:B, :final_len].clone()
+        _abi.call("wb_decode_set_logits_dump", self._session, None, 0)
+        _abi.call("wb_decode_set_forced_tokens", self._session, None)
+        if dump is not None:
+            return ids, dump[:final_len - 1]
+        return ids
+
+    @torch.no_grad()
+    def transcribe_host(self, mel_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
+        """End-to-end call with HOST buffers: H2D copy of the log-mel, encoder, greedy loop, D2H copy of the ids."""
+        B = mel_host.shape[0]
+        mel = mel_host.to(self.device, non_blocking=True)
+        ids = self.generate(mel, stream=stream)
+        if out_host is None:
+            return ids.cpu()
+        out_host[:B, :ids.shape[1]].copy_(ids, non_blocking=False)
+        return out_host[:B, :ids.shape[1]]
+
+    def close(self):
+        if self._session:
+            _abi.call("wb_session_destroy", self._session)
+            self._session = c_void_p()
+        if self._model:
+            _abi.call("wb_model_destroy", self._model)
+            self._model = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
