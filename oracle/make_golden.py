@@ -30,7 +30,7 @@ CASES = {
     "micro": ("micro", 3, 0, 1234, 448, [0, 1, 2, 3, 7, 31, 100, 446]),
     "tiny": ("tiny.en", 2, 0, 1234, 448, [0, 1, 2, 3, 7, 31, 100, 446]),
     "tiny_b1": ("tiny.en", 1, 0, 77, 448, [0, 1, 2, 5, 446]),          # BASELINE.json configs[0]
-    "base_b16": ("base.en", 16, 0, 1234, 448, [0, 1, 2, 9, 200, 446]),  # BASELINE.json configs[1]
+    "base_b16": ("base.en", 16, 0, 6, 448, [0, 1, 2, 9, 200, 446]),  # BASELINE.json configs[1]
     "small": ("small.en", 2, 0, 1234, 33, [0, 1, 2, 9, 31]),
     "medium": ("medium.en", 2, 0, 1234, 25, [0, 1, 2, 9, 23]),
 }

@@ -1,0 +1,142 @@
+"""Kernel-level parity (-m gpu): every CUDA operator, called through the C-ABI, against the same op in plain
+fp32 PyTorch (the arithmetic the oracle is made of).  Mirrors the reference's one-file-per-op
+style (tests/functional/test_layer_norm.py, test_gelu.py, test_matmul.py ...)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _gen(seed):
+    return torch.Generator(device="cpu").manual_seed(seed)
+
+
+@pytest.mark.parametrize("rows,d", [(1, 384), (7, 128), (300, 512), (1500, 768), (4097, 1024)])
+@pytest.mark.parametrize("odt", [torch.float32, torch.bfloat16])
+def test_layernorm(rows, d, odt):
+    g = _gen(rows + d)
+    x = (torch.randn(rows, d, generator=g) * 3 + 0.5).to(DEV)
+    w = (1 + 0.1 * torch.randn(d, generator=g)).to(DEV)
+    b = (0.1 * torch.randn(d, generator=g)).to(DEV)
+    ref = F.layer_norm(x, (d,), w, b, 1e-5)
+    out = G.layernorm(x, w, b, odt)
+    tol = 2e-6 if odt == torch.float32 else 4e-3
+    assert G.rel_err(out, ref) < tol
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 384, 384), (16, 512, 2048), (100, 1152, 384), (130, 51864, 128), (1500, 1536, 384), (3000, 384, 256)])
+@pytest.mark.parametrize("act,res", [(0, False), (1, False), (0, True)])
+def test_linear_fp32_cuda_core(M, N, K, act, res):
+    g = _gen(M + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = (0.1 * torch.randn(N, generator=g)).to(DEV)
+    R = torch.randn(M, N, generator=g).to(DEV) if res else None
+    ref = F.linear(A, W, bias)
+    if act:
+        ref = F.gelu(ref)
+    if res:
+        ref = ref + R
+    out = G.linear(A, W, bias, R, act, torch.float32, backend=1)
+    assert G.rel_err(out, ref) < 1e-5   # fp32 FFMA accumulation; differences are summation order only
+
+
+@pytest.mark.parametrize("bn", [0, 32, 64, 128, 256])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 1024, 1024), (1500, 1152, 384), (77, 512, 2048), (300, 51864, 384), (3001, 384, 256)])
+def test_linear_bf16_tcgen05(M, N, K, bn):
+    """tcgen05/TMEM/TMA GEMM vs fp32 torch on the SAME bf16-rounded operands (so only accumulation differs)."""
+    g = _gen(M * 3 + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).to(torch.bfloat16)
+    bias = (0.1 * torch.randn(N, generator=g)).to(DEV)
+    ref = F.linear(A.float(), W.float(), bias)
+    out = G.linear(A, W, bias, None, 0, torch.float32, backend=2 if bn == 0 else 100 + bn)
+    assert G.rel_err(out, ref) < 2e-5
+    out16 = G.linear(A, W, bias, None, 0, torch.bfloat16, backend=2 if bn == 0 else 100 + bn)
+    assert G.rel_err(out16, ref) < 6e-3
+
+
+def test_linear_bf16_tcgen05_epilogues():
+    g = _gen(5)
+    M, N, K = 700, 1536, 384
+    A = torch.randn(M, K, generator=g).to(DEV).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).to(torch.bfloat16)
+    bias = (0.1 * torch.randn(N, generator=g)).to(DEV)
+    R = torch.randn(M, N, generator=g).to(DEV)
+    lin = F.linear(A.float(), W.float(), bias)
+    assert G.rel_err(G.linear(A, W, bias, None, 1, torch.float32, backend=2), F.gelu(lin)) < 1e-5   # erf GELU
+    assert G.rel_err(G.linear(A, W, bias, R, 0, torch.float32, backend=2), lin + R) < 1e-5
+    # in-place residual (out aliases the residual): the encoder's x += out_proj(...)
+    x = R.clone()
+    from whisper_trtllm_b200 import _abi
+    _abi.call("wb_linear", G.ptr(A), K, G.ptr(W), K, _abi.BF16, G.ptr(bias), G.ptr(x), N, G.ptr(x), N, _abi.F32, M, N, K, 0, 2,
+              G.stream_handle())
+    assert G.rel_err(x, lin + R) < 1e-5
+
+
+def test_linear_bf16_cuda_core_matches_tcgen05():
+    g = _gen(9)
+    M, N, K = 257, 768, 768
+    A = torch.randn(M, K, generator=g).to(DEV).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).to(torch.bfloat16)
+    a = G.linear(A, W, None, None, 0, torch.float32, backend=1)
+    b = G.linear(A, W, None, None, 0, torch.float32, backend=2)
+    assert G.rel_err(a, b) < 2e-5
+
+
+def _attn_ref(qkv, B, S, H):
+    d = H * 64
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    w = torch.softmax(q @ k.transpose(-1, -2), dim=-1)
+    return (w @ v).permute(0, 2, 1, 3).reshape(B * S, d)
+
+
+@pytest.mark.parametrize("B,S,H", [(1, 64, 2), (2, 200, 6), (1, 1500, 8)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_encoder_attention_cuda_core(B, S, H, dt):
+    g = _gen(B + S + H)
+    qkv = torch.randn(B * S, 3 * H * 64, generator=g).to(DEV)
+    qkv[:, :H * 64] *= 0.125 * 3
+    qkv = qkv.to(dt)
+    ref = _attn_ref(qkv, B, S, H)
+    out = G.encoder_attention(qkv, B, S, H, backend=1)
+    assert G.rel_err(out, ref) < (2e-6 if dt == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize("B,H,T,n", [(1, 6, 448, 1), (3, 8, 448, 77), (2, 16, 1500, 1500), (5, 2, 1500, 1499)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_decode_attention(B, H, T, n, dt):
+    g = _gen(B + H + T + n)
+    q = (torch.randn(B, H * 64, generator=g) * 0.3).to(DEV).to(dt)
+    k = torch.randn(B, H, T, 64, generator=g).to(DEV).to(dt)
+    v = torch.randn(B, H, T, 64, generator=g).to(DEV).to(dt)
+    w = torch.softmax(torch.einsum("bhd,bhtd->bht", q.float().view(B, H, 64), k.float()[:, :, :n]), dim=-1)
+    ref = torch.einsum("bht,bhtd->bhd", w, v.float()[:, :, :n]).reshape(B, H * 64)
+    out = G.decode_attention(q, k, v, n)
+    assert G.rel_err(out, ref) < (2e-6 if dt == torch.float32 else 6e-3)
+
+
+def test_masked_argmax_first_max_and_masks():
+    V = 51864
+    g = _gen(1)
+    x = torch.randn(4, V, generator=g).to(DEV)
+    x[0, 100] = 50.0
+    x[0, 7] = 60.0            # masked below
+    x[1, 5000] = 42.0
+    x[1, 40000] = 42.0        # tie -> first index wins (torch.argmax semantics)
+    x[2, V - 1] = 99.0
+    mask = torch.zeros(V, dtype=torch.uint8, device=DEV)
+    mask[7] = 1
+    mask[V - 1] = 2
+    out = G.argmax(x, mask, 1)
+    xm = x.clone()
+    xm[:, 7] = -float("inf")
+    assert out.tolist() == torch.argmax(xm, -1).tolist()
+    assert out[1].item() == 5000 and out[0].item() == 100 and out[2].item() == V - 1
+    out2 = G.argmax(x, mask, 3)
+    xm[:, V - 1] = -float("inf")
+    assert out2.tolist() == torch.argmax(xm, -1).tolist()
