@@ -102,6 +102,13 @@ WB_API int wb_session_cross_kv(wb_session* s, int layer, const void** kv_dev, in
 WB_API int wb_session_self_kv(wb_session* s, int layer, const void** k_pages, const void** v_pages, const int32_t** page_table,
                        int* pages_per_seq, int* page_tokens);
 
+/* live timing for the bench roofline: CUDA events are recorded on the launching stream around every launch of
+ * one kernel class inside the real loop.  classes: 1 cross-attention, 2 self-attention, 3 decode GEMMs,
+ * 4 LM head, 5 encoder GEMMs, 6 encoder attention, 8 greedy/argmax, 9 conv stem, 10 cross-K/V projection; 0 = off.
+ * wb_session_profile_read synchronises, returns the summed device time and the launch count, and resets. */
+WB_API int wb_session_profile(wb_session* s, int kernel_class);
+WB_API int wb_session_profile_read(wb_session* s, double* total_ms, long long* launches);
+
 /* ---- operators (module-level drop-ins and kernel tests) ---------------------------------------- */
 /* LayerNorm eps: x fp32 [rows, d] -> out (out_dtype)                         (layers/normalization.py:6-30) */
 WB_API int wb_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_dtype, int rows, int d,

@@ -55,6 +55,8 @@ SIGNATURES = {
     "wb_decode_set_logits_dump": (c_int, [c_void_p, c_void_p, c_int]),
     "wb_session_cross_kv": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_int64)]),
     "wb_session_self_kv": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_int)]),
+    "wb_session_profile": (c_int, [c_void_p, c_int]),
+    "wb_session_profile_read": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_longlong)]),
     "wb_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "wb_linear": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                           c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -197,6 +197,21 @@ int wb_session_self_kv(wb_session* s, int layer, const void** k_pages, const voi
     });
 }
 
+int wb_session_profile(wb_session* s, int kernel_class) {
+    return guarded([&] {
+        WB_NOT_NULL(s);
+        WB_REQUIRE(kernel_class >= 0 && kernel_class <= 10, "unknown kernel class");
+        SS(s)->prof_class = kernel_class;
+        SS(s)->prof_used = 0;
+    });
+}
+int wb_session_profile_read(wb_session* s, double* total_ms, long long* launches) {
+    return guarded([&] {
+        WB_NOT_NULL(s);
+        SS(s)->prof_read(total_ms, launches);
+    });
+}
+
 int wb_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_dtype, int rows, int d, float eps,
                  wb_stream stream) {
     return guarded([&] {

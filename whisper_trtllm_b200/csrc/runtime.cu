@@ -298,7 +298,45 @@ Session::Session(Model* model, int mb, int ec, void* workspace, size_t workspace
 Session::~Session() {
     if (host_state) cudaFreeHost(host_state);
     if (check_event) cudaEventDestroy(check_event);
+    for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
 }
+
+void Session::prof_begin(int cls, cudaStream_t st) {
+    if (cls != prof_class) return;
+    if (prof_used + 2 > prof_events.size()) {
+        for (int i = 0; i < 2; ++i) {
+            cudaEvent_t e;
+            WB_CHECK_CUDA(cudaEventCreate(&e));
+            prof_events.push_back(e);
+        }
+    }
+    WB_CHECK_CUDA(cudaEventRecord(prof_events[prof_used], st));
+}
+void Session::prof_end(int cls, cudaStream_t st) {
+    if (cls != prof_class) return;
+    WB_CHECK_CUDA(cudaEventRecord(prof_events[prof_used + 1], st));
+    prof_used += 2;
+}
+void Session::prof_read(double* total_ms, long long* launches) {
+    double total = 0;
+    for (size_t i = 0; i + 1 < prof_used; i += 2) {
+        WB_CHECK_CUDA(cudaEventSynchronize(prof_events[i + 1]));
+        float ms = 0;
+        WB_CHECK_CUDA(cudaEventElapsedTime(&ms, prof_events[i], prof_events[i + 1]));
+        total += ms;
+    }
+    if (total_ms) *total_ms = total;
+    if (launches) *launches = (long long)(prof_used / 2);
+    prof_used = 0;
+}
+
+namespace {
+struct ProfScope {
+    Session* s; int cls; cudaStream_t st;
+    ProfScope(Session* s_, int c, cudaStream_t t) : s(s_), cls(c), st(t) { s->prof_begin(cls, st); }
+    ~ProfScope() noexcept(false) { s->prof_end(cls, st); }
+};
+}  // namespace
 
 size_t Session::cross_layer_elems() const { return (size_t)2 * max_batch * m->cfg.n_heads * m->cfg.n_ctx * 64; }
 size_t Session::self_layer_elems() const { return (size_t)num_pages * m->cfg.n_heads * PAGE_TOKENS * 64; }
@@ -362,27 +400,30 @@ void Session::encode(const float* mel, int B, float* enc_out_f32, cudaStream_t s
     for (int b0 = 0; b0 < B; b0 += enc_chunk) {
         const int bc = std::min(enc_chunk, B - b0);
         const int M = bc * g.n_ctx;
-        stem_chunk(mel + (size_t)b0 * g.n_mels * g.n_frames, bc, st);
+        { ProfScope ps(this, PROF_STEM, st); stem_chunk(mel + (size_t)b0 * g.n_mels * g.n_frames, bc, st); }
         // ---- transformer layers (pre-LN), fp32 residual stream in x
         for (int l = 0; l < g.enc_layers; ++l) {
             const EncLayer& L = m->enc[l];
             layernorm(x, L.ln1.g, L.ln1.b, ln, dt, nullptr, M, d, 1e-5f, nullptr, st);
-            gemm(linear_args(m, ln, d, L.qkv, qkv, 3 * d, dt, M), st);
-            encoder_attention(qkv, att, dt, bc, g.n_ctx, g.n_heads, st);
+            { ProfScope ps(this, PROF_ENC_GEMM, st); gemm(linear_args(m, ln, d, L.qkv, qkv, 3 * d, dt, M), st); }
+            { ProfScope ps(this, PROF_ENC_ATTN, st); encoder_attention(qkv, att, dt, bc, g.n_ctx, g.n_heads, st); }
             {
                 GemmArgs a = linear_args(m, att, d, L.out, x, d, F32, M);
                 a.res = x; a.ldres = d;
+                ProfScope ps(this, PROF_ENC_GEMM, st);
                 gemm(a, st);
             }
             layernorm(x, L.ln2.g, L.ln2.b, ln, dt, nullptr, M, d, 1e-5f, nullptr, st);
             {
                 GemmArgs a = linear_args(m, ln, d, L.fc1, ffn, g.ffn, dt, M);
                 a.act = 1;
+                ProfScope ps(this, PROF_ENC_GEMM, st);
                 gemm(a, st);
             }
             {
                 GemmArgs a = linear_args(m, ffn, g.ffn, L.fc2, x, d, F32, M);
                 a.res = x; a.ldres = d;
+                ProfScope ps(this, PROF_ENC_GEMM, st);
                 gemm(a, st);
             }
         }
@@ -415,6 +456,7 @@ void Session::decode_step(cudaStream_t st) {
     auto lin = [&](const void* A, long long lda, const Linear& l, void* out, long long ldo, int odt, int act, const float* res) {
         GemmArgs a = linear_args(m, A, lda, l, out, ldo, odt, B);
         a.act = act; a.res = res; a.ldres = d; a.active = active;
+        ProfScope ps(this, PROF_DEC_GEMM, st);
         gemm(a, st);
     };
     decoder_embed(tokens, g.max_tgt, state, m->emb, m->dec_pos, dt, dx, B, d, st);
@@ -431,6 +473,7 @@ void Session::decode_step(cudaStream_t st) {
             a.k_pages = eoff(self_k, (size_t)l * self_layer_elems(), dt);
             a.v_pages = eoff(self_v, (size_t)l * self_layer_elems(), dt);
             a.page_table = page_table; a.pages_per_seq = pages_per_seq; a.page_tokens = PAGE_TOKENS;
+            ProfScope ps(this, PROF_SELF_ATTN, st);
             decode_attention(a, st);
         }
         lin(datt, d, L.out, dx, d, F32, 0, dx);
@@ -445,6 +488,7 @@ void Session::decode_step(cudaStream_t st) {
             a.k = eoff(cross, (size_t)l * cross_layer_elems(), dt);
             a.v = eoff(cross, (size_t)l * cross_layer_elems() + per_kv, dt);
             a.kv_bstride = (long long)g.n_heads * g.n_ctx * 64; a.kv_hstride = (long long)g.n_ctx * 64;
+            ProfScope ps(this, PROF_CROSS_ATTN, st);
             decode_attention(a, st);
         }
         lin(datt, d, L.cout, dx, d, F32, 0, dx);
@@ -459,6 +503,7 @@ void Session::decode_step(cudaStream_t st) {
         GemmArgs a;
         a.A = dln; a.lda = d; a.W = m->emb; a.ldw = d; a.in_dtype = dt;
         a.out = logits; a.ldo = g.vocab; a.out_dtype = F32; a.M = B; a.N = g.vocab; a.K = d; a.active = active;
+        ProfScope ps(this, PROF_LM_HEAD, st);
         gemm(a, st);
     }
     if (logits_dump != nullptr && steps_enqueued < logits_dump_steps)
@@ -471,6 +516,7 @@ void Session::decode_step(cudaStream_t st) {
         a.pad_id = g.pad; a.eos_id = g.eos; a.max_length = g.max_length;
         a.tokens = tokens; a.tokens_stride = g.max_tgt; a.unfinished = unfinished; a.state = state;
         a.forced_tokens = forced_tokens;
+        ProfScope ps(this, PROF_GREEDY, st);
         greedy_step(a, st);
     }
     ++steps_enqueued;

@@ -23,6 +23,9 @@ constexpr int CONV1_KPAD = 256;   // 3 * 80 = 240 zero-padded to a multiple of t
 constexpr int H1_ROWS = 3008;     // rows per utterance of the padded conv1 output (1 zero row + 3000 + 7 zero rows)
 constexpr int CONV2_MPERIOD = 1504;
 constexpr int PAGE_TOKENS = 64;
+// kernel classes for wb_session_profile
+enum ProfClass { PROF_NONE = 0, PROF_CROSS_ATTN = 1, PROF_SELF_ATTN = 2, PROF_DEC_GEMM = 3, PROF_LM_HEAD = 4,
+                 PROF_ENC_GEMM = 5, PROF_ENC_ATTN = 6, PROF_LAYERNORM = 7, PROF_GREEDY = 8, PROF_STEM = 9, PROF_CROSS_KV = 10 };
 
 struct Model {
     ModelConfig cfg;
@@ -80,6 +83,14 @@ struct Session : Buffers {
     StepState* host_state = nullptr;  // pinned
     cudaEvent_t check_event = nullptr;
     bool h1p_zeroed = false;
+    // live per-kernel-class timing (bench roofline): CUDA events recorded on the launching stream around every
+    // launch of the selected class inside the real loop
+    int prof_class = 0;
+    std::vector<cudaEvent_t> prof_events;  // pairs
+    size_t prof_used = 0;
+    void prof_begin(int cls, cudaStream_t s);
+    void prof_end(int cls, cudaStream_t s);
+    void prof_read(double* total_ms, long long* launches);  // synchronises, then resets
 
     Session(Model* model, int max_batch, int enc_chunk, void* workspace, size_t workspace_bytes);
     ~Session();

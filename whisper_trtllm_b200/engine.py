@@ -204,6 +204,24 @@ class WhisperEngine:
         out_host[:B, :ids.shape[1]].copy_(ids, non_blocking=False)
         return out_host[:B, :ids.shape[1]]
 
+    # ------------------------------------------------------------------ live kernel timing (bench roofline)
+    PROF_CLASSES = {"cross_attn": 1, "self_attn": 2, "dec_gemm": 3, "lm_head": 4, "enc_gemm": 5, "enc_attn": 6,
+                    "greedy": 8, "stem": 9, "cross_kv": 10}
+
+    def profile(self, kernel_class: Optional[str]):
+        """Record CUDA events around every launch of one kernel class inside the real loop (None = off)."""
+        _abi.call("wb_session_profile", self._session, 0 if kernel_class is None else self.PROF_CLASSES[kernel_class])
+
+    def profile_read(self):
+        """-> (summed device milliseconds, launches) since profile() was armed; synchronises."""
+        import ctypes
+        ms, n = ctypes.c_double(), ctypes.c_longlong()
+        _abi.call("wb_session_profile_read", self._session, byref(ms), byref(n))
+        return ms.value, n.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.wb_launch_count())
+
     def close(self):
         if self._session:
             _abi.call("wb_session_destroy", self._session)
