@@ -107,6 +107,22 @@ def test_encoder_attention_cuda_core(B, S, H, dt):
     assert G.rel_err(out, ref) < (2e-6 if dt == torch.float32 else 6e-3)
 
 
+@pytest.mark.parametrize("B,S,H", [(1, 64, 1), (1, 128, 2), (2, 200, 6), (3, 1500, 8), (2, 1500, 16)])
+def test_encoder_attention_tcgen05(B, S, H):
+    """tcgen05 flash kernel (bf16 in, fp32 softmax/accumulate) vs fp32 torch on the same bf16 inputs.
+    B > 1 with S % 64 != 0 exercises the tail mask (the last key tile reaches into the next utterance)."""
+    g = _gen(B * 7 + S + H)
+    qkv = torch.randn(B * S, 3 * H * 64, generator=g).to(DEV)
+    qkv[:, :H * 64] *= 0.125 * 3
+    qkv = qkv.to(torch.bfloat16)
+    ref = _attn_ref(qkv, B, S, H)
+    out = G.encoder_attention(qkv, B, S, H, backend=2)
+    assert torch.isfinite(out.float()).all()
+    assert G.rel_err(out, ref) < 8e-3          # P is rounded to bf16 before the P V product
+    simt = G.encoder_attention(qkv, B, S, H, backend=1)
+    assert G.rel_err(out, simt) < 8e-3
+
+
 @pytest.mark.parametrize("B,H,T,n", [(1, 6, 448, 1), (3, 8, 448, 77), (2, 16, 1500, 1500), (5, 2, 1500, 1499)])
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 def test_decode_attention(B, H, T, n, dt):
