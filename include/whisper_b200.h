@@ -130,6 +130,24 @@ WB_API int wb_decode_attention(const void* q, const void* k, const void* v, void
 /* masked argmax per row: logits fp32 [B, V]; mask (optional) uint8 [V], a token is skipped if mask & bits */
 WB_API int wb_argmax(const float* logits, int64_t ld, int batch, int vocab, const uint8_t* mask, int bits, int32_t* out,
               wb_stream stream);
+/* Decoder embedding with an explicit position (WhisperDecoder.forward, model.py:423-425: position row =
+ * shape(past_self_cache_mask,0)-1): x[b*T+t, :] = embed_tokens[ids[b,t], :] + embed_positions[position0+t, :], fp32 out */
+WB_API int wb_embed(const int32_t* ids, int64_t ids_stride, int batch, int n_tokens, int position0, const void* embed_tokens,
+             const void* embed_positions, int dtype, int d_model, int vocab_size, float* x_out, wb_stream stream);
+/* Dense cache growth of the engine contract (model.py:276-281 slice+concat; oracle torch.cat modeling_whisper.py:494-495):
+ * out [B,H,cache_len+1,64] = concat(past[:, :, :cache_len] (strided), current [B, H*64] (row stride)) */
+WB_API int wb_kv_append(const void* past, int64_t past_batch_stride, int64_t past_head_stride, int cache_len, const void* current,
+                 int64_t current_batch_stride, void* out, int dtype, int batch, int heads, wb_stream stream);
+/* Linear + transpose_for_scores (model.py:254-259): A [B*S, K] x W[H*64, K]^T (+bias) -> out [B, H, S, 64] */
+WB_API int wb_linear_split_heads(const void* A, int64_t lda, const void* W, int64_t ldw, int in_dtype, const float* bias, void* out,
+                          int out_dtype, int batch, int seq, int heads, int K, wb_stream stream);
+/* Stateless encoder stem (WhisperEncoder.forward, model.py:94-102): conv1+GELU, conv2(stride 2)+GELU, +positions.
+ * w1_packed [d, 256] with k = tap*num_mel_bins + c (zero padded), w2_packed [d, 3d] with k = tap*d + c, compute dtype;
+ * biases / positions fp32; x_out fp32 [B*n_frames/2, d]; caller-provided workspace */
+WB_API int wb_conv_stem_workspace_bytes(int batch, int d_model, int n_frames, int dtype, size_t* bytes);
+WB_API int wb_conv_stem(const float* mel, int batch, const void* w1_packed, const float* b1, const void* w2_packed, const float* b2,
+                 const float* positions, int dtype, int d_model, int num_mel_bins, int n_frames, void* workspace,
+                 size_t workspace_bytes, float* x_out, wb_stream stream);
 WB_API int wb_cast(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, wb_stream stream);
 
 #ifdef __cplusplus

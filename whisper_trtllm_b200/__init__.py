@@ -3,8 +3,18 @@ EdVince/whisper-trtllm (WhisperEncoder / WhisperDecoder / WhisperDecoderAttentio
 
 Python here is host plumbing only; all arithmetic runs in hand-written CUDA kernels reached through the
 C-ABI of ``libwhisper_b200.so`` (include/whisper_b200.h).  There is no CPU or library fallback.
+
+    whisper_trtllm_b200.models.WhisperEncoder / WhisperDecoder / WhisperDecoderAttention / WhisperDecoderLayer
+                                  module-level drop-ins of tensorrt_llm.models (model.py)
+    whisper_trtllm_b200.runtime.Session / TensorInfo          drop-ins of tensorrt_llm.runtime (session.py)
+    whisper_trtllm_b200.run      runner classes + greedy_search / get_logits_processor / get_stopping_criteria (run.py)
+    whisper_trtllm_b200.WhisperEngine   the native runtime (packed weights, paged KV, on-device greedy loop)
+    whisper_trtllm_b200.dp       data-parallel sharding by utterance + the final token gather
 """
 from ._abi import BF16, F32, WhisperB200Error  # noqa: F401
 from .engine import WhisperEngine, begin_index_of  # noqa: F401
+from . import model as models  # noqa: F401  (tensorrt_llm.models.WhisperEncoder -> whisper_trtllm_b200.models.WhisperEncoder)
+from . import session as runtime  # noqa: F401  (tensorrt_llm.runtime.Session / TensorInfo)
+from . import layers, run, dp  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -273,6 +273,67 @@ int wb_cast(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, w
     });
 }
 
+int wb_embed(const int32_t* ids, int64_t ids_stride, int batch, int n_tokens, int position0, const void* embed_tokens,
+             const void* embed_positions, int dtype, int d_model, int vocab_size, float* x_out, wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(ids); WB_NOT_NULL(embed_tokens); WB_NOT_NULL(embed_positions); WB_NOT_NULL(x_out);
+        wb::embed_tokens(ids, ids_stride, batch, n_tokens, position0, embed_tokens, embed_positions, dtype, x_out, d_model,
+                         vocab_size, S(stream));
+    });
+}
+
+int wb_kv_append(const void* past, int64_t past_batch_stride, int64_t past_head_stride, int cache_len, const void* current,
+                 int64_t current_batch_stride, void* out, int dtype, int batch, int heads, wb_stream stream) {
+    return guarded([&] {
+        wb::kv_append(past, past_batch_stride, past_head_stride, current, current_batch_stride, out, dtype, batch, heads,
+                      cache_len, S(stream));
+    });
+}
+
+int wb_linear_split_heads(const void* A, int64_t lda, const void* W, int64_t ldw, int in_dtype, const float* bias, void* out,
+                          int out_dtype, int batch, int seq, int heads, int K, wb_stream stream) {
+    return guarded([&] {
+        WB_REQUIRE(batch > 0 && seq > 0 && heads > 0, "bad split-heads shape");
+        wb::GemmArgs a;
+        a.A = A; a.lda = lda; a.W = W; a.ldw = ldw; a.in_dtype = in_dtype; a.bias = bias;
+        a.out = out; a.ldo = 0; a.out_dtype = out_dtype; a.M = batch * seq; a.N = heads * 64; a.K = K;
+        a.m_period_in = seq; a.m_valid = seq; a.m_period_out = seq;
+        a.out_mode = 1; a.hs_heads = heads; a.hs_batch = batch; a.hs_b0 = 0;
+        wb::gemm(a, S(stream));
+    });
+}
+
+int wb_conv_stem_workspace_bytes(int batch, int d_model, int n_frames, int dtype, size_t* bytes) {
+    return guarded([&] {
+        WB_NOT_NULL(bytes);
+        WB_REQUIRE(batch > 0 && d_model > 0 && n_frames > 0, "bad stem shape");
+        *bytes = wb::conv_stem_a1_bytes(batch, n_frames, dtype) + wb::conv_stem_h1p_bytes(batch, d_model, dtype) + 4096;
+    });
+}
+
+int wb_conv_stem(const float* mel, int batch, const void* w1_packed, const float* b1, const void* w2_packed, const float* b2,
+                 const float* positions, int dtype, int d_model, int num_mel_bins, int n_frames, void* workspace,
+                 size_t workspace_bytes, float* x_out, wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(mel); WB_NOT_NULL(w1_packed); WB_NOT_NULL(b1); WB_NOT_NULL(w2_packed); WB_NOT_NULL(b2);
+        WB_NOT_NULL(positions); WB_NOT_NULL(workspace); WB_NOT_NULL(x_out);
+        WB_REQUIRE(batch > 0 && d_model % 64 == 0 && 3 * num_mel_bins <= wb::CONV1_KPAD, "bad stem shape");
+        WB_REQUIRE(n_frames % 2 == 0 && n_frames + 8 <= wb::H1_ROWS && n_frames / 2 <= wb::CONV2_MPERIOD, "unsupported audio window");
+        const size_t a1b = (wb::conv_stem_a1_bytes(batch, n_frames, dtype) + 1023) / 1024 * 1024;
+        const size_t h1b = wb::conv_stem_h1p_bytes(batch, d_model, dtype);
+        uint8_t* base = (uint8_t*)workspace;
+        const size_t skew = (1024 - (reinterpret_cast<uintptr_t>(base) & 1023)) & 1023;
+        WB_REQUIRE(workspace_bytes >= skew + a1b + h1b, "stem workspace too small (see wb_conv_stem_workspace_bytes)");
+        void* a1 = base + skew;
+        void* h1p = base + skew + a1b;
+        WB_CHECK_CUDA(cudaMemsetAsync(h1p, 0, h1b, S(stream)));
+        wb::StemWeights w;
+        w.w1 = w1_packed; w.b1 = b1; w.w2 = w2_packed; w.b2 = b2; w.pos = positions;
+        w.dtype = dtype; w.d = d_model; w.n_mels = num_mel_bins; w.n_frames = n_frames;
+        wb::conv_stem(w, mel, batch, a1, h1p, x_out, S(stream));
+    });
+}
+
 int wb_encoder_stem(wb_session* s, const float* mel, int batch, float* x_out, wb_stream stream) {
     return guarded([&] {
         WB_NOT_NULL(s); WB_NOT_NULL(mel); WB_NOT_NULL(x_out);

@@ -36,6 +36,45 @@ __global__ void __launch_bounds__(128) decoder_embed_kernel(const int* __restric
     }
 }
 
+// stateless embedding (module-level drop-in): x[b*T + t, :] = E[ids[b, t], :] + P[pos0 + t, :]
+template <typename T>
+__global__ void __launch_bounds__(128) embed_kernel(const int* __restrict__ ids, long long ids_stride, int Tn, int pos0,
+                                                    const T* __restrict__ emb, const T* __restrict__ pos, float* __restrict__ x,
+                                                    int d, int vocab) {
+    constexpr int VEC = Vec16<T>::N;
+    const int row = blockIdx.x;
+    const int b = row / Tn, t = row - b * Tn;
+    int tok = ids[(size_t)b * ids_stride + t];
+    tok = min(max(tok, 0), vocab - 1);
+    const T* e = emb + (size_t)tok * d;
+    const T* pp = pos + (size_t)(pos0 + t) * d;
+    for (int i = threadIdx.x * VEC; i < d; i += blockDim.x * VEC) {
+        float ef[VEC], pf[VEC];
+        ld16(e + i).unpack(ef);
+        ld16(pp + i).unpack(pf);
+#pragma unroll
+        for (int j = 0; j < VEC; j += 4)
+            *reinterpret_cast<float4*>(x + (size_t)row * d + i + j) =
+                make_float4(ef[j] + pf[j], ef[j + 1] + pf[j + 1], ef[j + 2] + pf[j + 2], ef[j + 3] + pf[j + 3]);
+    }
+}
+
+// dense KV "concat" of the reference contract (model.py:276-281): out[b,h,0:n) = past[b,h,0:n), out[b,h,n] = new[b,h]
+template <typename T>
+__global__ void __launch_bounds__(256) kv_append_kernel(const T* __restrict__ past, long long past_bs, long long past_hs,
+                                                        const T* __restrict__ cur, long long cur_bs, T* __restrict__ out,
+                                                        int H, int n) {
+    constexpr int VEC = Vec16<T>::N;
+    constexpr int CPR = 64 / VEC;  // 16-byte chunks per row
+    const int h = blockIdx.x, b = blockIdx.y;
+    T* o = out + ((size_t)b * H + h) * (size_t)(n + 1) * 64;
+    const T* p = past + (size_t)b * past_bs + (size_t)h * past_hs;
+    const int total = n * CPR;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) st16(o + (size_t)i * VEC, ld16(p + (size_t)i * VEC));
+    if (threadIdx.x < CPR)
+        st16(o + (size_t)n * 64 + threadIdx.x * VEC, ld16(cur + (size_t)b * cur_bs + h * 64 + threadIdx.x * VEC));
+}
+
 __device__ __forceinline__ void argmax_combine(float& v, int& i, float ov, int oi) {
     if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
 }
@@ -154,6 +193,28 @@ void decoder_embed(const int* tokens, int tokens_stride, const StepState* state,
         decoder_embed_kernel<float><<<B, 128, 0, stream>>>(tokens, tokens_stride, state, (const float*)emb, (const float*)pos, x, d);
     else
         decoder_embed_kernel<bf16><<<B, 128, 0, stream>>>(tokens, tokens_stride, state, (const bf16*)emb, (const bf16*)pos, x, d);
+    WB_CHECK_LAUNCH();
+}
+
+void embed_tokens(const int* ids, long long ids_stride, int B, int T, int pos0, const void* emb, const void* pos, int dtype,
+                  float* x, int d, int vocab, cudaStream_t stream) {
+    WB_REQUIRE(d % 8 == 0 && B > 0 && T > 0 && pos0 >= 0, "bad embed arguments");
+    if (dtype == F32)
+        embed_kernel<float><<<B * T, 128, 0, stream>>>(ids, ids_stride, T, pos0, (const float*)emb, (const float*)pos, x, d, vocab);
+    else
+        embed_kernel<bf16><<<B * T, 128, 0, stream>>>(ids, ids_stride, T, pos0, (const bf16*)emb, (const bf16*)pos, x, d, vocab);
+    WB_CHECK_LAUNCH();
+}
+
+void kv_append(const void* past, long long past_bs, long long past_hs, const void* cur, long long cur_bs, void* out, int dtype,
+               int B, int H, int n, cudaStream_t stream) {
+    WB_REQUIRE(cur && out && B > 0 && H > 0 && n >= 0 && (n == 0 || past), "bad kv_append arguments");
+    WB_REQUIRE(past_bs % 8 == 0 && past_hs % 8 == 0 && cur_bs % 8 == 0, "kv_append strides must be multiples of 8 elements");
+    dim3 grid(H, B);
+    if (dtype == F32)
+        kv_append_kernel<float><<<grid, 256, 0, stream>>>((const float*)past, past_bs, past_hs, (const float*)cur, cur_bs, (float*)out, H, n);
+    else
+        kv_append_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)past, past_bs, past_hs, (const bf16*)cur, cur_bs, (bf16*)out, H, n);
     WB_CHECK_LAUNCH();
 }
 

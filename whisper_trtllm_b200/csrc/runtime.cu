@@ -368,23 +368,38 @@ static void project_cross_kv(Session* s, int b0, int bc, cudaStream_t st) {
 
 // conv1 (+GELU) as a GEMM over the im2col'd mel; conv2 (+GELU, +positions) as a GEMM over sliding windows of
 // the zero-padded, time-major conv1 output.  Result: fp32 residual stream x [bc * n_ctx, d].
+// Stateless: used by the session (packed model weights) and by wb_conv_stem (module-level WhisperEncoder).
+void conv_stem(const StemWeights& w, const float* mel, int bc, void* a1, void* h1p, float* x, cudaStream_t st) {
+    const int d = w.d, dt = w.dtype, n_ctx = w.n_frames / 2;
+    im2col_conv1(mel, a1, dt, bc, w.n_mels, w.n_frames, CONV1_KPAD, st);
+    {
+        GemmArgs a;
+        a.A = a1; a.lda = CONV1_KPAD; a.W = w.w1; a.ldw = CONV1_KPAD; a.in_dtype = dt; a.bias = w.b1;
+        a.out = h1p; a.ldo = d; a.out_dtype = dt; a.M = bc * w.n_frames; a.N = d; a.K = CONV1_KPAD;
+        a.act = 1;
+        a.m_period_in = w.n_frames; a.m_valid = w.n_frames; a.m_period_out = H1_ROWS; a.m_out_offset = 1;
+        gemm(a, st);
+    }
+    {
+        GemmArgs a;
+        a.A = h1p; a.lda = 2 * d; a.W = w.w2; a.ldw = 3 * d; a.in_dtype = dt; a.bias = w.b2;
+        a.out = x; a.ldo = d; a.out_dtype = F32; a.M = bc * CONV2_MPERIOD; a.N = d; a.K = 3 * d;
+        a.act = 1;
+        a.res = w.pos; a.ldres = d; a.res_periodic = 1;
+        a.m_period_in = CONV2_MPERIOD; a.m_valid = n_ctx; a.m_period_out = n_ctx;
+        gemm(a, st);
+    }
+}
+
+size_t conv_stem_a1_bytes(int bc, int n_frames, int dtype) { return (size_t)bc * n_frames * CONV1_KPAD * dtype_size(dtype); }
+size_t conv_stem_h1p_bytes(int bc, int d, int dtype) { return ((size_t)bc * H1_ROWS + 8) * d * dtype_size(dtype); }
+
 void Session::stem_chunk(const float* mel, int bc, cudaStream_t st) {
     const ModelConfig& g = m->cfg;
-    const int d = g.d_model, dt = m->dtype;
-    im2col_conv1(mel, a1, dt, bc, g.n_mels, g.n_frames, CONV1_KPAD, st);
-    {
-        GemmArgs a = linear_args(m, a1, CONV1_KPAD, m->conv1, h1p, d, dt, bc * g.n_frames);
-        a.act = 1;
-        a.m_period_in = g.n_frames; a.m_valid = g.n_frames; a.m_period_out = H1_ROWS; a.m_out_offset = 1;
-        gemm(a, st);
-    }
-    {
-        GemmArgs a = linear_args(m, h1p, 2 * d, m->conv2, x, d, F32, bc * CONV2_MPERIOD);
-        a.act = 1;
-        a.res = m->enc_pos; a.ldres = d; a.res_periodic = 1;
-        a.m_period_in = CONV2_MPERIOD; a.m_valid = g.n_ctx; a.m_period_out = g.n_ctx;
-        gemm(a, st);
-    }
+    StemWeights w;
+    w.w1 = m->conv1.w; w.b1 = m->conv1.b; w.w2 = m->conv2.w; w.b2 = m->conv2.b; w.pos = m->enc_pos;
+    w.dtype = m->dtype; w.d = g.d_model; w.n_mels = g.n_mels; w.n_frames = g.n_frames;
+    conv_stem(w, mel, bc, a1, h1p, x, st);
 }
 
 void Session::stem(const float* mel, int B, float* x_out, cudaStream_t st) {

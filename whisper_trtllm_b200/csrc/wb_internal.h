@@ -79,6 +79,12 @@ void decode_attention(const DecAttnArgs& a, cudaStream_t stream);
 void decoder_embed(const int* tokens, int tokens_stride, const StepState* state, const void* emb, const void* pos,
                    int dtype, float* x, int B, int d, cudaStream_t stream);
 
+// stateless variants for the module-level drop-ins (explicit position / dense caches)
+void embed_tokens(const int* ids, long long ids_stride, int B, int T, int pos0, const void* emb, const void* pos, int dtype,
+                  float* x, int d, int vocab, cudaStream_t stream);
+void kv_append(const void* past, long long past_bs, long long past_hs, const void* cur, long long cur_bs, void* out, int dtype,
+               int B, int H, int n, cudaStream_t stream);
+
 // Logits processors + argmax + EOS/pad bookkeeping + length advance, entirely on device.
 struct GreedyArgs {
     const float* logits = nullptr; long long ld = 0;   // [B, V] fp32

@@ -27,6 +27,17 @@ constexpr int PAGE_TOKENS = 64;
 enum ProfClass { PROF_NONE = 0, PROF_CROSS_ATTN = 1, PROF_SELF_ATTN = 2, PROF_DEC_GEMM = 3, PROF_LM_HEAD = 4,
                  PROF_ENC_GEMM = 5, PROF_ENC_ATTN = 6, PROF_LAYERNORM = 7, PROF_GREEDY = 8, PROF_STEM = 9, PROF_CROSS_KV = 10 };
 
+// packed conv-stem weights: w1 [d, CONV1_KPAD] (k = tap * n_mels + c), w2 [d, 3d] (k = tap * d + c), compute dtype
+struct StemWeights {
+    const void* w1 = nullptr; const float* b1 = nullptr; const void* w2 = nullptr; const float* b2 = nullptr;
+    const float* pos = nullptr;  // [n_frames / 2, d] fp32
+    int dtype = F32, d = 0, n_mels = 80, n_frames = 3000;
+};
+// a1: im2col buffer, h1p: zero-initialised padded conv1 output (rows 0 and 3001.. of every utterance stay zero)
+void conv_stem(const StemWeights& w, const float* mel, int bc, void* a1, void* h1p, float* x, cudaStream_t st);
+size_t conv_stem_a1_bytes(int bc, int n_frames, int dtype);
+size_t conv_stem_h1p_bytes(int bc, int d, int dtype);
+
 struct Model {
     ModelConfig cfg;
     int dtype = F32;

@@ -80,12 +80,21 @@ class WhisperEngine:
 
     def _set_generation(self):
         c = self.config
-        sup = (c_int32 * len(c["suppress_tokens"]))(*c["suppress_tokens"])
-        beg = (c_int32 * len(c["begin_suppress_tokens"]))(*c["begin_suppress_tokens"])
-        flat = [int(v) for pair in c["forced_decoder_ids"] for v in pair]
+        self.set_generation(c["suppress_tokens"], c["begin_suppress_tokens"], begin_index_of(c), c["forced_decoder_ids"])
+
+    def set_generation(self, suppress_tokens, begin_suppress_tokens, begin_index: int, forced_decoder_ids):
+        """The three logits processors of run.py:150-162 as data: suppress list, begin-suppress list + begin_index,
+        forced (generation index, token) pairs.  Cheap (two small H2D copies); skipped when nothing changed."""
+        key = (tuple(suppress_tokens), tuple(begin_suppress_tokens), int(begin_index), tuple(tuple(p) for p in forced_decoder_ids))
+        if getattr(self, "_generation_key", None) == key:
+            return
+        sup = (c_int32 * len(key[0]))(*key[0])
+        beg = (c_int32 * len(key[1]))(*key[1])
+        flat = [int(v) for pair in key[3] for v in pair]
         forced = (c_int32 * len(flat))(*flat)
-        _abi.call("wb_model_set_generation", self._model, sup, len(c["suppress_tokens"]), beg,
-                  len(c["begin_suppress_tokens"]), begin_index_of(c), forced, len(c["forced_decoder_ids"]))
+        torch.cuda.current_stream().synchronize()   # the tables may still be read by queued steps
+        _abi.call("wb_model_set_generation", self._model, sup, len(key[0]), beg, len(key[1]), int(begin_index), forced, len(key[3]))
+        self._generation_key = key
 
     def weight_bytes(self) -> int:
         n = c_size_t()
