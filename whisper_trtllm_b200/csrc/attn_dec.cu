@@ -8,132 +8,178 @@
 //    (modeling_whisper.py:494-495) and TRT-LLM's slice + concat (model.py:276-281).
 //  Oracle semantics (modeling_whisper.py:468-526): no mask, q pre-scaled (folded into the q weights), fp32 softmax.
 //
-// HBM-bound streaming kernel: every key row (128 B in bf16) is read by 8 consecutive lanes with one
-// 16-byte load each, so a warp instruction covers 4 complete rows = 512 contiguous bytes.
+// HBM-bound streaming kernel, single pass (flash-decoding style online softmax):
+//   - persistent grid: a few CTAs per SM walk the (utterance, head) items round-robin, so the tail of the last
+//     wave costs 1/28 of the launch instead of half a wave;
+//   - every key row (128 B in bf16) is read by 8 consecutive lanes with one 16-byte load each, so a warp
+//     instruction covers 4 complete rows = 512 contiguous bytes; K and V rows of UNROLL iterations are all in
+//     flight before the first use (16-byte L1-bypassing loads);
+//   - each 8-lane group keeps its own running (max, sum, acc[8]) and the groups/warps are merged once per item.
 #include "wb_internal.h"
 
 namespace wb {
 
 namespace {
-constexpr int DH = 64, THREADS = 256, WARPS = THREADS / 32;
+constexpr int DH = 64, THREADS = 256, WARPS = THREADS / 32, UNROLL = 4;
 
-template <typename T>
+template <typename T> __device__ __forceinline__ float softmax_exp(float x);
+template <> __device__ __forceinline__ float softmax_exp<float>(float x) { return expf(x); }      // exactness path
+template <> __device__ __forceinline__ float softmax_exp<bf16>(float x) { return __expf(x); }     // speed path
+
+template <typename T, bool kPaged>
 __global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
     constexpr int VEC = Vec16<T>::N;       // elements per 16-byte load: 8 (bf16) / 4 (fp32)
     constexpr int LPK = DH / VEC;          // lanes per key row: 8 / 16
     constexpr int KPW = 32 / LPK;          // key rows per warp instruction: 4 / 2
     constexpr int KPB = KPW * WARPS;       // key rows per block iteration
-    extern __shared__ float sc[];          // [n] scores, then probabilities
-    __shared__ float red[WARPS];
-    __shared__ float ored[WARPS][DH];
+    __shared__ float part_m[2][WARPS], part_l[2][WARPS];
+    __shared__ float part_o[2][WARPS][DH];
 
     int n = a.n_keys;
     if (a.state != nullptr) {
         if (a.state->active == 0) return;
         n = a.state->cur_len;
     }
-    const int h = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int sub = lane % LPK, grp = lane / LPK;
-    const bool paged = a.k_pages != nullptr;
+    const int n_items = a.B * a.H;
+    int parity = 0;
 
-    float qf[VEC];
-    ld16(reinterpret_cast<const T*>(a.q) + (size_t)b * a.q_stride + h * DH + sub * VEC).unpack(qf);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, parity ^= 1) {
+        const int b = item / a.H, h = item - b * a.H;
+        float qf[VEC];
+        ld16(reinterpret_cast<const T*>(a.q) + (size_t)b * a.q_stride + h * DH + sub * VEC).unpack(qf);
 
-    const T* kbase = nullptr;
-    const T* vbase = nullptr;
-    const int* pt = nullptr;
-    if (paged) {
-        pt = a.page_table + (size_t)b * a.pages_per_seq;
-        if (a.k_new != nullptr && warp == 0 && grp == 0) {  // in-place append at slot n-1
-            const int s = n - 1;
-            const size_t off = (((size_t)pt[s / a.page_tokens] * a.H + h) * a.page_tokens + (s % a.page_tokens)) * DH + sub * VEC;
-            const size_t src = (size_t)b * a.new_stride + h * DH + sub * VEC;
-            st16(reinterpret_cast<T*>(a.k_pages) + off, ld16(reinterpret_cast<const T*>(a.k_new) + src));
-            st16(reinterpret_cast<T*>(a.v_pages) + off, ld16(reinterpret_cast<const T*>(a.v_new) + src));
+        const T* kbase = nullptr;
+        const T* vbase = nullptr;
+        const int* pt = nullptr;
+        if constexpr (kPaged) {
+            pt = a.page_table + (size_t)b * a.pages_per_seq;
+            if (a.k_new != nullptr) {
+                if (warp == 0 && grp == 0) {  // in-place append at slot n-1
+                    const int s = n - 1;
+                    const size_t off = (((size_t)pt[s / a.page_tokens] * a.H + h) * a.page_tokens + (s % a.page_tokens)) * DH + sub * VEC;
+                    const size_t src = (size_t)b * a.new_stride + h * DH + sub * VEC;
+                    st16(reinterpret_cast<T*>(a.k_pages) + off, ld16(reinterpret_cast<const T*>(a.k_new) + src));
+                    st16(reinterpret_cast<T*>(a.v_pages) + off, ld16(reinterpret_cast<const T*>(a.v_new) + src));
+                }
+                __syncthreads();  // the appended row is read below by other warps of this block
+            }
+        } else {
+            const size_t o = (size_t)b * a.kv_bstride + (size_t)h * a.kv_hstride;
+            kbase = reinterpret_cast<const T*>(a.k) + o;
+            vbase = reinterpret_cast<const T*>(a.v) + o;
         }
-        __syncthreads();  // the appended row is read below by other warps of this block
-    } else {
-        const size_t o = (size_t)b * a.kv_bstride + (size_t)h * a.kv_hstride;
-        kbase = reinterpret_cast<const T*>(a.k) + o;
-        vbase = reinterpret_cast<const T*>(a.v) + o;
-    }
-    auto row_ptr = [&](const T* contiguous, const void* pages, int s) -> const T* {
-        if (!paged) return contiguous + (size_t)s * DH + sub * VEC;
-        return reinterpret_cast<const T*>(pages) +
-               (((size_t)pt[s / a.page_tokens] * a.H + h) * a.page_tokens + (s % a.page_tokens)) * DH + sub * VEC;
-    };
+        auto row_off = [&](int s) -> size_t {
+            if constexpr (kPaged)
+                return (((size_t)pt[s / a.page_tokens] * a.H + h) * a.page_tokens + (s % a.page_tokens)) * DH + sub * VEC;
+            else
+                return (size_t)s * DH + sub * VEC;
+        };
 
-    // ---- phase 1: scores ----
-    float lmax = -INFINITY;
-#pragma unroll 4
-    for (int s0 = warp * KPW; s0 < n; s0 += KPB) {
-        const int s = s0 + grp;
-        const bool valid = s < n;
-        float kf[VEC];
-        (paged ? ld16(row_ptr(kbase, a.k_pages, valid ? s : n - 1))
-               : ld16_stream(row_ptr(kbase, a.k_pages, valid ? s : n - 1))).unpack(kf);
-        float dot = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;
+        float acc[VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) dot = fmaf(qf[i], kf[i], dot);
-#pragma unroll
-        for (int o = LPK / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        if (valid && sub == 0) sc[s] = dot;
-        if (valid) lmax = fmaxf(lmax, dot);
-    }
-    lmax = warp_max(lmax);
-    if (lane == 0) red[warp] = lmax;
-    __syncthreads();
-    float gmax = red[0];
-#pragma unroll
-    for (int w = 1; w < WARPS; ++w) gmax = fmaxf(gmax, red[w]);
-    __syncthreads();  // red is reused below
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
 
-    // ---- phase 2: exp + sum ----
-    float lsum = 0.f;
-    for (int s = tid; s < n; s += THREADS) {
-        const float p = expf(sc[s] - gmax);
-        sc[s] = p;
-        lsum += p;
-    }
-    lsum = warp_sum(lsum);
-    if (lane == 0) red[warp] = lsum;
-    __syncthreads();
-    float gsum = 0.f;
+        for (int s0 = warp * KPW + grp; s0 < n; s0 += KPB * UNROLL) {
+            Vec16<T> kr[UNROLL], vr[UNROLL];
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) gsum += red[w];
+            for (int u = 0; u < UNROLL; ++u) {          // all loads first: 2 * UNROLL 16-byte requests in flight per lane
+                const int s = min(s0 + u * KPB, n - 1);
+                const size_t off = row_off(s);
+                if constexpr (kPaged) {
+                    kr[u] = ld16(reinterpret_cast<const T*>(a.k_pages) + off);
+                    vr[u] = ld16(reinterpret_cast<const T*>(a.v_pages) + off);
+                } else {
+                    kr[u] = ld16_stream(kbase + off);
+                    vr[u] = ld16_stream(vbase + off);
+                }
+            }
+            float sc[UNROLL];
+            float mb = -INFINITY;
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                float kf[VEC];
+                kr[u].unpack(kf);
+                float dot = 0.f;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) dot = fmaf(qf[i], kf[i], dot);
+#pragma unroll
+                for (int o = LPK / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                sc[u] = (s0 + u * KPB < n) ? dot : -INFINITY;
+                mb = fmaxf(mb, sc[u]);
+            }
+            const float m_new = fmaxf(m_run, mb);       // finite: the first row of every batch is valid
+            const float scale = softmax_exp<T>(m_run - m_new);   // exp(-inf) = 0 on the first batch
+            l_run *= scale;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] *= scale;
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const float p = softmax_exp<T>(sc[u] - m_new);   // 0 for the masked tail rows
+                l_run += p;
+                float vf[VEC];
+                vr[u].unpack(vf);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
+            }
+            m_run = m_new;
+        }
 
-    // ---- phase 3: out = P V ----
-    float of[VEC];
+        // ---- merge the key groups of the warp (lanes with equal sub), then the warps
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) of[i] = 0.f;
-#pragma unroll 4
-    for (int s0 = warp * KPW; s0 < n; s0 += KPB) {
-        const int s = s0 + grp;
-        const bool valid = s < n;
-        float vf[VEC];
-        (paged ? ld16(row_ptr(vbase, a.v_pages, valid ? s : n - 1))
-               : ld16_stream(row_ptr(vbase, a.v_pages, valid ? s : n - 1))).unpack(vf);
-        const float p = valid ? sc[s] : 0.f;
+        for (int o = LPK; o < 32; o <<= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, m_run, o);
+            const float ol = __shfl_xor_sync(0xffffffffu, l_run, o);
+            const float mm = fmaxf(m_run, om);
+            const float s1 = (m_run == -INFINITY) ? 0.f : softmax_exp<T>(m_run - mm);
+            const float s2 = (om == -INFINITY) ? 0.f : softmax_exp<T>(om - mm);
+            l_run = l_run * s1 + ol * s2;
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) of[i] = fmaf(p, vf[i], of[i]);
+            for (int i = 0; i < VEC; ++i) {
+                const float oa = __shfl_xor_sync(0xffffffffu, acc[i], o);
+                acc[i] = acc[i] * s1 + oa * s2;
+            }
+            m_run = mm;
+        }
+        if (grp == 0) {
+            if (sub == 0) { part_m[parity][warp] = m_run; part_l[parity][warp] = l_run; }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) part_o[parity][warp][sub * VEC + i] = acc[i];
+        }
+        __syncthreads();   // partials are double buffered by item parity: one barrier per item is enough
+        if (tid < DH) {
+            float mm = part_m[parity][0];
+#pragma unroll
+            for (int w = 1; w < WARPS; ++w) mm = fmaxf(mm, part_m[parity][w]);
+            float l = 0.f, o = 0.f;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const float pm = part_m[parity][w];
+                const float s = (pm == -INFINITY) ? 0.f : softmax_exp<T>(pm - mm);
+                l = fmaf(part_l[parity][w], s, l);
+                o = fmaf(part_o[parity][w][tid], s, o);
+            }
+            reinterpret_cast<T*>(a.out)[(size_t)b * a.out_stride + h * DH + tid] = from_f32<T>(o / l);
+        }
     }
-    // reduce over the key groups of the warp (lanes with equal sub), then over warps
-#pragma unroll
-    for (int i = 0; i < VEC; ++i)
-#pragma unroll
-        for (int o = LPK; o < 32; o <<= 1) of[i] += __shfl_xor_sync(0xffffffffu, of[i], o);
-    if (grp == 0) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) ored[warp][sub * VEC + i] = of[i];
+}
+
+template <typename T, bool kPaged>
+void launch(const DecAttnArgs& a, cudaStream_t stream) {
+    static int blocks_per_sm = 0, sms = 0;
+    if (blocks_per_sm == 0) {
+        int dev = 0;
+        WB_CHECK_CUDA(cudaGetDevice(&dev));
+        WB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        WB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, decode_attn_kernel<T, kPaged>, THREADS, 0));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
-    __syncthreads();
-    if (tid < DH) {
-        float v = 0.f;
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) v += ored[w][tid];
-        reinterpret_cast<T*>(a.out)[(size_t)b * a.out_stride + h * DH + tid] = from_f32<T>(v / gsum);
-    }
+    const int items = a.B * a.H;
+    const int grid = std::min(items, sms * blocks_per_sm);
+    decode_attn_kernel<T, kPaged><<<grid, THREADS, 0, stream>>>(a);
+    WB_CHECK_LAUNCH();
 }
 }  // namespace
 
@@ -142,13 +188,12 @@ void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
     const bool paged = a.k_pages != nullptr;
     WB_REQUIRE(paged || (a.k && a.v), "missing K/V");
     WB_REQUIRE(!paged || (a.page_table && a.v_pages && a.pages_per_seq > 0 && a.page_tokens > 0), "bad paged cache");
-    const int max_keys = paged ? a.pages_per_seq * a.page_tokens : a.n_keys;
-    WB_REQUIRE(max_keys > 0 && max_keys <= 8192, "key count out of range");
-    dim3 grid(a.H, a.B), block(THREADS);
-    const size_t smem = (size_t)max_keys * sizeof(float);
-    if (a.dtype == F32) decode_attn_kernel<float><<<grid, block, smem, stream>>>(a);
-    else decode_attn_kernel<bf16><<<grid, block, smem, stream>>>(a);
-    WB_CHECK_LAUNCH();
+    WB_REQUIRE(paged ? a.state != nullptr : a.n_keys > 0, "key count must be positive");
+    if (a.dtype == F32) {
+        if (paged) launch<float, true>(a, stream); else launch<float, false>(a, stream);
+    } else {
+        if (paged) launch<bf16, true>(a, stream); else launch<bf16, false>(a, stream);
+    }
 }
 
 }  // namespace wb
