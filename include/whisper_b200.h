@@ -55,6 +55,8 @@ WB_API int wb_version(void);
 WB_API int wb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* debug/bench switches: gemm 0 = tcgen05 for bf16 (default), 1 = CUDA-core; attention likewise */
 WB_API int wb_set_backend(int gemm_backend, int attn_backend);
+/* programmatic dependent launch between the kernels of a decode step (default 1 = on); 0 = plain stream order */
+WB_API int wb_set_pdl(int enabled);
 /* number of kernels this library launched so far on this thread's device (bench `gpu_launches`) */
 WB_API long long wb_launch_count(void);
 
@@ -118,6 +120,16 @@ WB_API int wb_layernorm(const float* x, const float* gamma, const float* beta, v
 WB_API int wb_linear(const void* A, int64_t lda, const void* W, int64_t ldw, int in_dtype, const float* bias,
               const float* residual, int64_t ldres, void* out, int64_t ldo, int out_dtype, int M, int N, int K, int act,
               int backend, wb_stream stream);
+/* Skinny (decode-step) Linear as split-K with DEFERRED reduction: split s accumulates k in [s*K/S, (s+1)*K/S) and stores its raw
+ * fp32 product at parts + s*split_stride ([M, N] row-major); no bias / activation.  k_splits 0 = let the library choose
+ * (<= max_k_splits; the choice is returned in *chosen_splits).  The consumer adds bias + slabs in a fixed order:
+ * wb_layernorm_preadd (residual GEMMs: RowLinear `dense` / fc2, layers/linear.py:98-139) or the cross-attention q load. */
+WB_API int wb_linear_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, int in_dtype, float* parts, int64_t split_stride,
+                     int M, int N, int K, int k_splits, int max_k_splits, int* chosen_splits, wb_stream stream);
+/* x[r,:] += add_bias + sum_s parts[s*part_stride + r*d + :] (in place), then out[r,:] = LayerNorm(x[r,:])
+ * (the residual add + pre-LN of WhisperDecoderLayer.forward, model.py:336-361, fused into one pass) */
+WB_API int wb_layernorm_preadd(float* x, const float* parts, int n_parts, int64_t part_stride, const float* add_bias, const float* gamma,
+                        const float* beta, void* out, int out_dtype, int rows, int d, float eps, wb_stream stream);
 /* Encoder stem (conv1+GELU, conv2+GELU, +positions): mel fp32 [B,80,3000] -> x fp32 [B*1500, d]; uses the
  * session's workspace and the model's packed conv weights             (models/whisper/model.py:96-102) */
 WB_API int wb_encoder_stem(wb_session* s, const float* mel, int batch, float* x_out, wb_stream stream);

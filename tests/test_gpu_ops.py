@@ -156,3 +156,60 @@ def test_masked_argmax_first_max_and_masks():
     out2 = G.argmax(x, mask, 3)
     xm[:, V - 1] = -float("inf")
     assert out2.tolist() == torch.argmax(xm, -1).tolist()
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(256, 1024, 1024, 0), (256, 1024, 4096, 0), (256, 1024, 1024, 4), (64, 384, 1536, 2), (31, 512, 512, 8)])
+def test_linear_splitk_deferred_reduction_and_layernorm_preadd(M, N, K, splits):
+    """split-K tcgen05 GEMM -> raw fp32 slabs; the consumer (LayerNorm pre-add) adds bias + slabs + residual in a fixed order."""
+    import ctypes
+    from whisper_trtllm_b200 import _abi
+    g = _gen(M + N + K + splits)
+    A = torch.randn(M, K, generator=g).to(DEV).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).to(torch.bfloat16)
+    bias = (0.1 * torch.randn(N, generator=g)).to(DEV)
+    x = torch.randn(M, N, generator=g).to(DEV)
+    gamma = (1 + 0.1 * torch.randn(N, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(N, generator=g)).to(DEV)
+    parts = torch.full((8, M, N), float("nan"), device=DEV)
+    chosen = ctypes.c_int(0)
+    _abi.call("wb_linear_splitk", G.ptr(A), K, G.ptr(W), K, _abi.BF16, G.ptr(parts), M * N, M, N, K, splits, 8, ctypes.byref(chosen),
+              G.stream_handle())
+    S = chosen.value
+    assert 1 <= S <= 8 and (splits == 0 or S == splits)
+    ref = F.linear(A.float(), W.float())
+    assert G.rel_err(parts[:S].sum(0), ref) < 2e-5
+    if S < 8:
+        assert torch.isnan(parts[S:]).all()          # slabs beyond the chosen count are untouched
+    # consumer: x += bias + sum(slabs); out = LN(x)
+    x2 = x.clone()
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    _abi.call("wb_layernorm_preadd", G.ptr(x2), G.ptr(parts), S, M * N, G.ptr(bias), G.ptr(gamma), G.ptr(beta), G.ptr(out), _abi.BF16,
+              M, N, 1e-5, G.stream_handle())
+    want_x = x + bias + ref
+    assert G.rel_err(x2, want_x) < 2e-5
+    assert G.rel_err(out, F.layer_norm(want_x, (N,), gamma, beta, 1e-5)) < 6e-3
+    # determinism: same slabs, same order -> bit-identical
+    x3 = x.clone()
+    _abi.call("wb_layernorm_preadd", G.ptr(x3), G.ptr(parts), S, M * N, G.ptr(bias), G.ptr(gamma), G.ptr(beta), G.ptr(out), _abi.BF16,
+              M, N, 1e-5, G.stream_handle())
+    assert torch.equal(x2, x3)
+
+
+def test_pdl_switch_gives_identical_results():
+    """Programmatic dependent launch only changes WHEN a kernel's prologue runs, never its result."""
+    from whisper_trtllm_b200 import _abi
+    g = _gen(77)
+    x = torch.randn(256, 1024, generator=g).to(DEV)
+    w = (1 + 0.1 * torch.randn(1024, generator=g)).to(DEV)
+    b = (0.1 * torch.randn(1024, generator=g)).to(DEV)
+    W = (torch.randn(1024, 1024, generator=g) / 32).to(DEV).to(torch.bfloat16)
+    outs = []
+    for flag in (0, 1):
+        _abi.call("wb_set_pdl", flag)
+        h = x
+        for _ in range(6):       # a chain of dependent kernels: LN -> GEMM(+residual) -> LN -> ...
+            ln = G.layernorm(h, w, b, torch.bfloat16)
+            h = G.linear(ln, W, b, h, 0, torch.float32, backend=2)
+        outs.append(h.clone())
+    _abi.call("wb_set_pdl", 1)
+    assert torch.equal(outs[0], outs[1]) and torch.isfinite(outs[0]).all()

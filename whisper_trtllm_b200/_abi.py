@@ -35,6 +35,7 @@ SIGNATURES = {
     "wb_version": (c_int, []),
     "wb_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "wb_set_backend": (c_int, [c_int, c_int]),
+    "wb_set_pdl": (c_int, [c_int]),
     "wb_launch_count": (c_longlong, []),
     "wb_model_create": (c_int, [POINTER(wb_config), c_int, POINTER(c_void_p)]),
     "wb_model_destroy": (c_int, [c_void_p]),
@@ -60,6 +61,10 @@ SIGNATURES = {
     "wb_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "wb_linear": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                           c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "wb_linear_splitk": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
+                                 POINTER(c_int), c_void_p]),
+    "wb_layernorm_preadd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                    c_float, c_void_p]),
     "wb_encoder_stem": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "wb_encoder_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "wb_decode_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int64, c_void_p]),

@@ -56,6 +56,11 @@ int wb_set_backend(int gemm_backend, int attn_backend) {
     });
 }
 
+int wb_set_pdl(int enabled) {
+    wb::pdl_enabled() = enabled != 0;
+    return WB_OK;
+}
+
 long long wb_launch_count(void) { return wb::launch_counter().load(); }
 
 int wb_model_create(const wb_config* c, int dtype, wb_model** out) {
@@ -238,6 +243,32 @@ int wb_linear(const void* A, int64_t lda, const void* W, int64_t ldw, int in_dty
 }
 
 int wb_encoder_stem(wb_session* s, const float* mel, int batch, float* x_out, wb_stream stream);
+
+int wb_linear_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, int in_dtype, float* parts, int64_t split_stride,
+                     int Mrows, int N, int K, int k_splits, int max_k_splits, int* chosen_splits, wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(parts);
+        wb::GemmArgs a;
+        a.A = A; a.lda = lda; a.W = W; a.ldw = ldw; a.in_dtype = in_dtype;
+        a.out = parts; a.ldo = N; a.out_dtype = wb::F32; a.M = Mrows; a.N = N; a.K = K;
+        a.k_splits = k_splits; a.max_k_splits = max_k_splits; a.split_stride = split_stride;
+        int chosen = 1;
+        a.chosen_splits = &chosen;
+        WB_REQUIRE(split_stride >= (int64_t)Mrows * N || (k_splits == 1), "split_stride must cover one [M, N] slab");
+        wb::gemm(a, S(stream));
+        if (chosen_splits) *chosen_splits = chosen;
+    });
+}
+
+int wb_layernorm_preadd(float* x, const float* parts, int n_parts, int64_t part_stride, const float* add_bias, const float* gamma,
+                        const float* beta, void* out, int out_dtype, int rows, int d, float eps, wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(x); WB_NOT_NULL(gamma); WB_NOT_NULL(beta); WB_NOT_NULL(out);
+        wb::LnPreAdd pre;
+        pre.parts = parts; pre.n_parts = n_parts; pre.part_stride = part_stride; pre.bias = add_bias;
+        wb::layernorm_preadd(x, pre, gamma, beta, out, out_dtype, rows, d, eps, nullptr, S(stream));
+    });
+}
 
 int wb_encoder_attention(const void* qkv, void* out, int dtype, int batch, int seq, int heads, int backend, wb_stream stream) {
     return guarded([&] {

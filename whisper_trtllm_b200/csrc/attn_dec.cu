@@ -35,7 +35,10 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
     __shared__ float part_m[2][WARPS], part_l[2][WARPS];
     __shared__ float part_o[2][WARPS][DH];
 
+    pdl_wait();
+    pdl_trigger();
     int n = a.n_keys;
+    if (a.active != nullptr && *a.active == 0) return;
     if (a.state != nullptr) {
         if (a.state->active == 0) return;
         n = a.state->cur_len;
@@ -48,7 +51,20 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, parity ^= 1) {
         const int b = item / a.H, h = item - b * a.H;
         float qf[VEC];
-        ld16(reinterpret_cast<const T*>(a.q) + (size_t)b * a.q_stride + h * DH + sub * VEC).unpack(qf);
+        if (a.q_parts != nullptr) {   // q = bias + sum of the split-K partial slabs of the q projection (fp32, fixed order)
+            const int c0 = h * DH + sub * VEC;
+#pragma unroll
+            for (int i = 0; i < VEC; i += 4) {
+                float4 t = a.q_bias != nullptr ? *reinterpret_cast<const float4*>(a.q_bias + c0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int p = 0; p < a.q_n_parts; ++p) {
+                    const float4 u = *reinterpret_cast<const float4*>(a.q_parts + (size_t)p * a.q_part_stride + (size_t)b * a.H * DH + c0 + i);
+                    t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                }
+                qf[i] = t.x; qf[i + 1] = t.y; qf[i + 2] = t.z; qf[i + 3] = t.w;
+            }
+        } else {
+            ld16(reinterpret_cast<const T*>(a.q) + (size_t)b * a.q_stride + h * DH + sub * VEC).unpack(qf);
+        }
 
         const T* kbase = nullptr;
         const T* vbase = nullptr;
@@ -82,7 +98,9 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
 
-        for (int s0 = warp * KPW + grp; s0 < n; s0 += KPB * UNROLL) {
+        // warp-uniform trip count (the shuffles below need all 32 lanes): groups whose rows fall past n are masked
+        for (int sb = warp * KPW; sb < n; sb += KPB * UNROLL) {
+            const int s0 = sb + grp;
             Vec16<T> kr[UNROLL], vr[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {          // all loads first: 2 * UNROLL 16-byte requests in flight per lane
@@ -110,14 +128,15 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
                 sc[u] = (s0 + u * KPB < n) ? dot : -INFINITY;
                 mb = fmaxf(mb, sc[u]);
             }
-            const float m_new = fmaxf(m_run, mb);       // finite: the first row of every batch is valid
-            const float scale = softmax_exp<T>(m_run - m_new);   // exp(-inf) = 0 on the first batch
+            const float m_new = fmaxf(m_run, mb);
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;   // this group has not seen a valid row yet: every p below is 0
+            const float scale = softmax_exp<T>(m_run - m_use);        // exp(-inf) = 0 while l_run / acc are still 0
             l_run *= scale;
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[i] *= scale;
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                const float p = softmax_exp<T>(sc[u] - m_new);   // 0 for the masked tail rows
+                const float p = softmax_exp<T>(sc[u] - m_use);        // 0 for the masked rows
                 l_run += p;
                 float vf[VEC];
                 vr[u].unpack(vf);
@@ -178,13 +197,12 @@ void launch(const DecAttnArgs& a, cudaStream_t stream) {
     }
     const int items = a.B * a.H;
     const int grid = std::min(items, sms * blocks_per_sm);
-    decode_attn_kernel<T, kPaged><<<grid, THREADS, 0, stream>>>(a);
-    WB_CHECK_LAUNCH();
+    launch_kernel(decode_attn_kernel<T, kPaged>, dim3(grid), dim3(THREADS), 0, stream, true, a);
 }
 }  // namespace
 
 void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
-    WB_REQUIRE(a.q && a.out && a.B > 0 && a.H > 0, "bad decode attention arguments");
+    WB_REQUIRE((a.q || a.q_parts) && a.out && a.B > 0 && a.H > 0, "bad decode attention arguments");
     const bool paged = a.k_pages != nullptr;
     WB_REQUIRE(paged || (a.k && a.v), "missing K/V");
     WB_REQUIRE(!paged || (a.page_table && a.v_pages && a.pages_per_seq > 0 && a.page_tokens > 0), "bad paged cache");

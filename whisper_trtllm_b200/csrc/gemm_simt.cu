@@ -25,6 +25,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A, long long lda, const T* __restrict__ W,
                                                         long long ldw, int K, EpiParams ep,
                                                         const int* __restrict__ active) {
+    pdl_wait();
+    pdl_trigger();
     if (active != nullptr && *active == 0) return;
     __shared__ __align__(16) float As[2][BK][BM + PAD];
     __shared__ __align__(16) float Bs[2][BK][BN + PAD];
@@ -88,10 +90,9 @@ void gemm_simt(const GemmArgs& a, cudaStream_t stream) {
     dim3 grid(ceil_div(a.N, BN), ceil_div(a.M, BM)), block(256);
     WB_REQUIRE(grid.y <= 65535, "M too large for the SIMT GEMM grid");
     if (a.in_dtype == F32)
-        gemm_simt_kernel<float><<<grid, block, 0, stream>>>((const float*)a.A, a.lda, (const float*)a.W, a.ldw, a.K, ep, a.active);
+        launch_kernel(gemm_simt_kernel<float>, grid, block, 0, stream, true, (const float*)a.A, a.lda, (const float*)a.W, a.ldw, a.K, ep, a.active);
     else
-        gemm_simt_kernel<bf16><<<grid, block, 0, stream>>>((const bf16*)a.A, a.lda, (const bf16*)a.W, a.ldw, a.K, ep, a.active);
-    WB_CHECK_LAUNCH();
+        launch_kernel(gemm_simt_kernel<bf16>, grid, block, 0, stream, true, (const bf16*)a.A, a.lda, (const bf16*)a.W, a.ldw, a.K, ep, a.active);
 }
 
 }  // namespace wb

@@ -5,7 +5,9 @@
 //   warp 1   MMA issuer     one elected lane issues tcgen05.mma (UMMA 128 x BN x 16), tcgen05.commit frees slots
 //   warp 2   TMEM allocator 2 x BN fp32 accumulator columns (double buffered so the epilogue of tile i
 //                            overlaps the main loop of tile i+1)
-//   warps 4-7 epilogue      tcgen05.ld (lane quarter = warp % 4) -> bias / erf-GELU / fp32 residual -> store
+//   warps 4-11 epilogue     tcgen05.ld (lane quarter = warp % 4, column half = (warp - 4) / 4) -> 32x32 transpose through
+//                            XOR-swizzled smem -> bias / erf-GELU / fp32 residual -> row-contiguous 128-byte stores
+//                            (4 rows per warp instruction instead of 32 scattered 16-byte pieces)
 //
 // Replaces the TensorRT-chosen fp32 tactics behind the reference's ColumnLinear/RowLinear/Conv2d layers
 // (tensorrt_llm/layers/linear.py:38-139, models/whisper/model.py:77-79) and the oracle's F.linear/conv1d.
@@ -21,36 +23,39 @@ namespace {
 
 constexpr int BM = 128, BK = 64;
 constexpr uint32_t A_BYTES = BM * BK * 2;
+constexpr int EPI_WARPS = 8, NUM_THREADS = (4 + EPI_WARPS) * 32;
 
 template <int BN> struct TcCfg {
     static constexpr uint32_t B_BYTES = BN * BK * 2;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
     static constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {32,64,128,256}
-    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+    static constexpr uint32_t STAGING_BYTES = EPI_WARPS * 32 * 32 * 4;  // one 32x32 fp32 transpose tile per epilogue warp
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int K,
-               int num_m_tiles, int num_n_tiles, EpiParams ep, const int* __restrict__ active) {
+               int num_m_tiles, int num_n_tiles, int k_splits, long long split_stride, EpiParams ep,
+               const int* __restrict__ active) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
-    if (active != nullptr && *active == 0) return;
 
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte aligned bases
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = num_m_tiles * num_n_tiles;
-    const int nk = K / BK;
+    const int num_tiles = num_m_tiles * num_n_tiles * k_splits;   // work item = (m tile, n tile, k split)
+    const int nk = K / BK / k_splits;                             // k blocks per work item
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
@@ -63,7 +68,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tmem_full_bar[s], 1);
-            ptx::mbar_init(&tmem_empty_bar[s], 4);  // one arrive per epilogue warp
+            ptx::mbar_init(&tmem_empty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
         }
         ptx::fence_barrier_init();
     }
@@ -73,19 +78,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp == 0) {
+    // PDL: everything above overlapped the previous kernel's tail; from here on we touch its outputs
+    pdl_wait();
+    pdl_trigger();
+    const bool run = (active == nullptr) || (*active != 0);   // decode loop already stopped: skip the work, keep the teardown
+
+    if (!run) {
+        // nothing
+    } else if (warp == 0) {
         // ===================== TMA producer =====================
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / num_n_tiles, n_blk = tile - m_blk * num_n_tiles;
+            const int mn = tile / k_splits, ks = tile - mn * k_splits;
+            const int m_blk = mn / num_n_tiles, n_blk = mn - m_blk * num_n_tiles;
             for (int kb = 0; kb < nk; ++kb) {
                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (lane == 0) {
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     ptx::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-                    ptx::tma_load_2d(sa + A_BYTES, &tmW, &full_bar[stage], kb * BK, n_blk * BN);
+                    ptx::tma_load_2d(sa, &tmA, &full_bar[stage], (ks * nk + kb) * BK, m_blk * BM);
+                    ptx::tma_load_2d(sa + A_BYTES, &tmW, &full_bar[stage], (ks * nk + kb) * BK, n_blk * BN);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -122,23 +135,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int q = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+        const int q = warp & 3;             // the TMEM lane quarter this warp may read
+        const int half = (warp - 4) >> 2;   // which half of the tile's 32-column slabs this warp owns
+        constexpr int SLABS = BN / 32;
+        constexpr int SLABS_PER_WARP = (SLABS + 1) / 2;
+        float4* st4 = reinterpret_cast<float4*>(staging + (warp - 4) * 32 * 32);   // [32 rows][8 chunks of 16 B], chunk ^= row & 7
+        const int rrow = lane >> 3, rchunk = lane & 7;                             // read-back mapping: 4 rows x 128 B per instruction
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / num_n_tiles, n_blk = tile - m_blk * num_n_tiles;
+            const int mn = tile / k_splits, ks = tile - mn * k_splits;
+            const int m_blk = mn / num_n_tiles, n_blk = mn - m_blk * num_n_tiles;
+            EpiParams ept = ep;
+            ept.out = reinterpret_cast<float*>(ep.out) + ks * split_stride;   // split-K: raw fp32 partial slab (offset 0 otherwise)
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tcgen05_fence_after();
-            const EpiRow r = epi_row(ep, m_blk * BM + q * 32 + lane);
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+            const int row0 = m_blk * BM + q * 32;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int ci = 0; ci < SLABS_PER_WARP; ++ci) {
+                const int c = half * SLABS_PER_WARP + ci;
+                if (c >= SLABS) break;
                 uint32_t v[32];
                 ptx::tmem_ld_32x32(t_row + c * 32, v);
                 ptx::tmem_ld_wait();
-                const int n0 = n_blk * BN + c * 32;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) epi_store<8, true>(ep, r, n0 + g * 8, reinterpret_cast<float*>(v) + g * 8);
+                for (int j = 0; j < 8; ++j)   // thread = row `lane`: conflict-free 16-byte stores (8 lanes hit 8 distinct chunks)
+                    st4[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                __syncwarp();
+                const int n0 = n_blk * BN + c * 32 + rchunk * 4;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = i * 4 + rrow;
+                    const float4 f = st4[rr * 8 + (rchunk ^ (rr & 7))];
+                    float o[4] = {f.x, f.y, f.z, f.w};
+                    epi_store<4, true>(ept, epi_row(ept, row0 + rr), n0, o);
+                }
+                __syncwarp();   // staging tile is rewritten by the next slab
             }
             ptx::tcgen05_fence_before();
             __syncwarp();
@@ -236,7 +270,7 @@ bool gemm_tc_supported(const GemmArgs& a) {
 }
 
 template <int BN>
-static void launch_tc(const GemmArgs& a, cudaStream_t stream) {
+static void launch_tc(const GemmArgs& a, int k_splits, cudaStream_t stream) {
     using Cfg = TcCfg<BN>;
     static bool configured = false;
     if (!configured) {
@@ -246,32 +280,62 @@ static void launch_tc(const GemmArgs& a, cudaStream_t stream) {
     const CUtensorMap tmA = make_tmap_bf16_2d(a.A, a.lda, a.M, a.K, BM);
     const CUtensorMap tmW = make_tmap_bf16_2d(a.W, a.ldw, a.N, a.K, BN);
     const int mt = ceil_div(a.M, BM), nt = ceil_div(a.N, BN);
-    const int grid = std::min(mt * nt, sm_count());
+    const int grid = std::min(mt * nt * k_splits, sm_count());
     EpiParams ep = make_epi(a);
-    gemm_tc_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmW, a.K, mt, nt, ep, a.active);
-    WB_CHECK_LAUNCH();
+    launch_kernel(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES, stream, true, tmA, tmW, a.K, mt, nt, k_splits,
+                  a.split_stride, ep, a.active);
 }
 
 static int g_force_bn = 0;
 void set_gemm_tc_block_n(int bn) { g_force_bn = bn; }
 
+// Tile width / split-K choice.  Large M (encoder): the widest tile that still gives every SM a tile.  Skinny M (decode,
+// one or two M tiles): the kernel is bound by how fast one SM can pull operand bytes (~40 B/clk/SM measured: 64 CTAs
+// x 320 KB took ~8 us), so minimise bytes per CTA = (BM + BN) * K/S * 2 over the configurations that keep <= one wave,
+// charging split-K for the partial slabs its consumer has to re-read (~M*N*4*S bytes each way through L2).
+static void pick_config(const GemmArgs& a, int max_splits, int& bn_out, int& splits_out) {
+    const int sms = sm_count();
+    const int mt = ceil_div(a.M, BM);
+    const int nkb = a.K / BK;
+    if (mt > 2) {
+        int bn = 256;
+        while (bn > 32 && mt * ceil_div(a.N, bn) < sms) bn >>= 1;
+        bn_out = bn; splits_out = 1;
+        return;
+    }
+    double best = 1e30;
+    bn_out = 32; splits_out = 1;
+    for (int bn : {32, 64, 128, 256}) {
+        for (int s = 1; s <= max_splits; s *= 2) {
+            if (nkb % s != 0) continue;
+            const long long ctas = (long long)mt * ceil_div(a.N, bn) * s;
+            const double waves = (double)((ctas + sms - 1) / sms);
+            const double ingest = (double)(BM + bn) * (a.K / s) * 2.0;                  // bytes one CTA pulls per work item
+            const double partial = s > 1 ? (double)a.M * a.N * 4.0 * s * 2.0 / 6000.0 : 0.0;   // clk, chip-wide L2 rate
+            const double t = waves * (ingest / 40.0 + 1500.0) + partial;                // clk; 1500 = pipeline fill + epilogue
+            if (t < best) { best = t; bn_out = bn; splits_out = s; }
+        }
+    }
+}
+
 void gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     validate_gemm_common(a);
     WB_REQUIRE(gemm_tc_supported(a), "shape/alignment not supported by the tcgen05 GEMM");
-    // pick the widest tile that still yields about one tile per SM
-    const int mt = ceil_div(a.M, BM);
-    int bn = 256;
-    if (g_force_bn) {
-        bn = g_force_bn;
-    } else {
-        const int sms = sm_count();
-        while (bn > 32 && mt * ceil_div(a.N, bn) < sms) bn >>= 1;
-    }
+    int bn = 256, splits = 1;
+    const bool auto_split = a.k_splits == 0;
+    pick_config(a, auto_split ? std::max(1, a.max_k_splits) : 1, bn, splits);
+    if (!auto_split) splits = a.k_splits;
+    if (g_force_bn) bn = g_force_bn;
+    WB_REQUIRE(splits >= 1 && (a.K / BK) % splits == 0, "k_splits must divide K / 64");
+    if (splits > 1 || auto_split)
+        WB_REQUIRE(a.out_dtype == F32 && a.bias == nullptr && a.res == nullptr && a.act == 0 && a.out_mode == 0 && a.out2 == nullptr,
+                   "split-K stores raw fp32 partials: bias / activation / residual belong to the consumer");
+    if (a.chosen_splits) *a.chosen_splits = splits;
     switch (bn) {
-        case 256: launch_tc<256>(a, stream); break;
-        case 128: launch_tc<128>(a, stream); break;
-        case 64: launch_tc<64>(a, stream); break;
-        case 32: launch_tc<32>(a, stream); break;
+        case 256: launch_tc<256>(a, splits, stream); break;
+        case 128: launch_tc<128>(a, splits, stream); break;
+        case 64: launch_tc<64>(a, splits, stream); break;
+        case 32: launch_tc<32>(a, splits, stream); break;
         default: WB_REQUIRE(false, "unsupported BLOCK_N");
     }
 }
@@ -281,8 +345,12 @@ void set_gemm_backend(int backend) { g_gemm_backend = backend; }
 int get_gemm_backend() { return g_gemm_backend; }
 
 void gemm(const GemmArgs& a, cudaStream_t stream) {
-    if (g_gemm_backend == 0 && gemm_tc_supported(a)) gemm_tc(a, stream);
-    else gemm_simt(a, stream);
+    if (g_gemm_backend == 0 && gemm_tc_supported(a)) {
+        gemm_tc(a, stream);
+    } else {
+        if (a.chosen_splits) *a.chosen_splits = 1;   // the CUDA-core kernel never splits: one "partial" slab = the whole product
+        gemm_simt(a, stream);
+    }
 }
 
 }  // namespace wb

@@ -18,6 +18,8 @@ template <typename T>
 __global__ void __launch_bounds__(128) decoder_embed_kernel(const int* __restrict__ tokens, int tokens_stride,
                                                             const StepState* __restrict__ state, const T* __restrict__ emb,
                                                             const T* __restrict__ pos, float* __restrict__ x, int d) {
+    pdl_wait();
+    pdl_trigger();
     if (state->active == 0) return;
     constexpr int VEC = Vec16<T>::N;
     const int b = blockIdx.x;
@@ -124,6 +126,8 @@ __device__ int block_masked_argmax(const float* __restrict__ row, int V, const u
 }
 
 __global__ void __launch_bounds__(1024) greedy_step_kernel(GreedyArgs a) {
+    pdl_wait();
+    pdl_trigger();
     StepState* st = a.state;
     if (st->active == 0) return;
     const int b = blockIdx.x;
@@ -190,10 +194,9 @@ void decoder_embed(const int* tokens, int tokens_stride, const StepState* state,
                    int dtype, float* x, int B, int d, cudaStream_t stream) {
     WB_REQUIRE(d % 8 == 0, "d_model must be a multiple of 8");
     if (dtype == F32)
-        decoder_embed_kernel<float><<<B, 128, 0, stream>>>(tokens, tokens_stride, state, (const float*)emb, (const float*)pos, x, d);
+        launch_kernel(decoder_embed_kernel<float>, dim3(B), dim3(128), 0, stream, true, tokens, tokens_stride, state, (const float*)emb, (const float*)pos, x, d);
     else
-        decoder_embed_kernel<bf16><<<B, 128, 0, stream>>>(tokens, tokens_stride, state, (const bf16*)emb, (const bf16*)pos, x, d);
-    WB_CHECK_LAUNCH();
+        launch_kernel(decoder_embed_kernel<bf16>, dim3(B), dim3(128), 0, stream, true, tokens, tokens_stride, state, (const bf16*)emb, (const bf16*)pos, x, d);
 }
 
 void embed_tokens(const int* ids, long long ids_stride, int B, int T, int pos0, const void* emb, const void* pos, int dtype,
@@ -220,8 +223,7 @@ void kv_append(const void* past, long long past_bs, long long past_hs, const voi
 
 void greedy_step(const GreedyArgs& a, cudaStream_t stream) {
     WB_REQUIRE(a.V % 4 == 0 && a.ld % 4 == 0, "vocab size / logits pitch must be multiples of 4");
-    greedy_step_kernel<<<a.B, 1024, 0, stream>>>(a);
-    WB_CHECK_LAUNCH();
+    launch_kernel(greedy_step_kernel, dim3(a.B), dim3(1024), 0, stream, true, a);
 }
 
 void greedy_init(int* tokens, int tokens_stride, int* unfinished, StepState* state, int B, int start_token, int pad_id,

@@ -6,17 +6,21 @@
 
 namespace wb {
 
-template <typename TOut>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+// kPreAdd: x[r,:] += bias + sum_s parts[s][r,:] first (consumer side of a split-K GEMM, fixed summation order),
+// the updated residual row is written back in place.
+template <typename TOut, bool kPreAdd>
+__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, LnPreAdd pre, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, TOut* __restrict__ out,
                                                         float* __restrict__ out2, int rows, int d, float eps,
                                                         const int* __restrict__ active) {
+    pdl_wait();
+    pdl_trigger();
     if (active != nullptr && *active == 0) return;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
     const int nvec = d >> 2;
-    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * d);
+    float4* xr = reinterpret_cast<float4*>(x + (size_t)warp * d);
     float4 v[8];
     float s = 0.f;
 #pragma unroll
@@ -24,6 +28,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         const int idx = lane + 32 * i;
         if (idx < nvec) {
             v[i] = xr[idx];
+            if constexpr (kPreAdd) {
+                float4 t = pre.bias != nullptr ? reinterpret_cast<const float4*>(pre.bias)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int p = 0; p < pre.n_parts; ++p) {
+                    const float4 q = reinterpret_cast<const float4*>(pre.parts + (size_t)p * pre.part_stride + (size_t)warp * d)[idx];
+                    t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
+                }
+                v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
+                xr[idx] = v[i];
+            }
             s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         }
     }
@@ -71,13 +84,27 @@ void layernorm(const float* x, const float* gamma, const float* beta, void* out,
                int rows, int d, float eps, const int* active, cudaStream_t stream) {
     WB_REQUIRE(d % 4 == 0 && d <= 1024, "layernorm supports d % 4 == 0, d <= 1024");
     if (rows == 0) return;
-    const int warps_per_block = 8;
+    const int warps_per_block = rows <= 2048 ? 4 : 8;   // few rows (decode): spread them over more SMs
+    dim3 grid(ceil_div(rows, warps_per_block)), block(warps_per_block * 32);
+    LnPreAdd none;
+    float* xm = const_cast<float*>(x);   // never written without kPreAdd
+    if (out_dtype == F32)
+        launch_kernel(layernorm_kernel<float, false>, grid, block, 0, stream, true, xm, none, gamma, beta, (float*)out, out2, rows, d, eps, active);
+    else
+        launch_kernel(layernorm_kernel<bf16, false>, grid, block, 0, stream, true, xm, none, gamma, beta, (bf16*)out, out2, rows, d, eps, active);
+}
+
+void layernorm_preadd(float* x, const LnPreAdd& pre, const float* gamma, const float* beta, void* out, int out_dtype,
+                      int rows, int d, float eps, const int* active, cudaStream_t stream) {
+    WB_REQUIRE(d % 4 == 0 && d <= 1024, "layernorm supports d % 4 == 0, d <= 1024");
+    WB_REQUIRE(pre.n_parts >= 0 && (pre.n_parts == 0 || pre.parts != nullptr) && pre.part_stride % 4 == 0, "bad pre-add slabs");
+    if (rows == 0) return;
+    const int warps_per_block = 4;   // decode: few rows, spread them over more SMs
     dim3 grid(ceil_div(rows, warps_per_block)), block(warps_per_block * 32);
     if (out_dtype == F32)
-        layernorm_kernel<float><<<grid, block, 0, stream>>>(x, gamma, beta, (float*)out, out2, rows, d, eps, active);
+        launch_kernel(layernorm_kernel<float, true>, grid, block, 0, stream, true, x, pre, gamma, beta, (float*)out, (float*)nullptr, rows, d, eps, active);
     else
-        layernorm_kernel<bf16><<<grid, block, 0, stream>>>(x, gamma, beta, (bf16*)out, out2, rows, d, eps, active);
-    WB_CHECK_LAUNCH();
+        launch_kernel(layernorm_kernel<bf16, true>, grid, block, 0, stream, true, x, pre, gamma, beta, (bf16*)out, (float*)nullptr, rows, d, eps, active);
 }
 
 }  // namespace wb

@@ -254,6 +254,7 @@ size_t layout(Buffers& b, const Model* m, int max_batch, int enc_chunk, void* ba
     c.take(b.self_v, L * pages * H * PAGE_TOKENS * 64 * es);
     c.take(b.page_table, pages * 4);
     c.take(b.dx, B * d * 4);
+    c.take(b.dpart, (size_t)MAX_K_SPLITS * B * d * 4);
     c.take(b.dln, B * d * es);
     c.take(b.dqkv, B * 3 * d * es);
     c.take(b.datt, B * d * es);
@@ -362,6 +363,7 @@ static void project_cross_kv(Session* s, int b0, int bc, cudaStream_t st) {
                                  eoff(s->cross, (size_t)l * s->cross_layer_elems(), m->dtype), 0, m->dtype, bc * g.n_ctx);
         a.m_period_in = g.n_ctx; a.m_valid = g.n_ctx; a.m_period_out = g.n_ctx;
         a.out_mode = 1; a.hs_heads = g.n_heads; a.hs_batch = s->max_batch; a.hs_b0 = b0;
+        ProfScope ps(s, PROF_CROSS_KV, st);
         gemm(a, st);
     }
 }
@@ -474,11 +476,32 @@ void Session::decode_step(cudaStream_t st) {
         ProfScope ps(this, PROF_DEC_GEMM, st);
         gemm(a, st);
     };
+    // Residual GEMMs (out-proj, cross-out, fc2) and the cross-attention q projection are split-K with DEFERRED
+    // reduction: they store raw fp32 partial slabs into dpart, and their consumer (the next LayerNorm, the cross-attention
+    // q load) adds bias + slabs in a fixed order.  One kernel per GEMM, all SMs busy, deterministic.
+    const long long part_stride = (long long)B * d;
+    auto lin_split = [&](const void* A, long long lda, const Linear& l) -> LnPreAdd {
+        GemmArgs a = linear_args(m, A, lda, l, dpart, d, F32, B);
+        a.bias = nullptr; a.active = active;
+        a.k_splits = 0; a.max_k_splits = MAX_K_SPLITS; a.split_stride = part_stride;
+        int chosen = 1;
+        a.chosen_splits = &chosen;
+        { ProfScope ps(this, PROF_DEC_GEMM, st); gemm(a, st); }
+        LnPreAdd pre;
+        pre.parts = dpart; pre.n_parts = chosen; pre.part_stride = part_stride; pre.bias = l.b;
+        return pre;
+    };
+    auto ln = [&](const LNorm& n, const LnPreAdd& pre) {
+        ProfScope ps(this, PROF_LAYERNORM, st);
+        if (pre.n_parts > 0) layernorm_preadd(dx, pre, n.g, n.b, dln, dt, B, d, 1e-5f, active, st);
+        else layernorm(dx, n.g, n.b, dln, dt, nullptr, B, d, 1e-5f, active, st);
+    };
     decoder_embed(tokens, g.max_tgt, state, m->emb, m->dec_pos, dt, dx, B, d, st);
+    LnPreAdd pending;   // residual update still owed to dx (previous layer's fc2)
     for (int l = 0; l < g.dec_layers; ++l) {
         const DecLayer& L = m->dec[l];
         // --- self attention: fused q|k|v projection, in-place paged append, one-query attention
-        layernorm(dx, L.ln1.g, L.ln1.b, dln, dt, nullptr, B, d, 1e-5f, active, st);
+        ln(L.ln1, pending);
         lin(dln, d, L.qkv, dqkv, 3 * d, dt, 0, nullptr);
         {
             DecAttnArgs a;
@@ -491,14 +514,15 @@ void Session::decode_step(cudaStream_t st) {
             ProfScope ps(this, PROF_SELF_ATTN, st);
             decode_attention(a, st);
         }
-        lin(datt, d, L.out, dx, d, F32, 0, dx);
+        const LnPreAdd after_self = lin_split(datt, d, L.out);
         // --- cross attention over the K/V projected once per utterance
-        layernorm(dx, L.ln2.g, L.ln2.b, dln, dt, nullptr, B, d, 1e-5f, active, st);
-        lin(dln, d, L.cq, dq, d, dt, 0, nullptr);
+        ln(L.ln2, after_self);
+        const LnPreAdd qpre = lin_split(dln, d, L.cq);
         {
             DecAttnArgs a;
-            a.dtype = dt; a.q = dq; a.q_stride = d; a.out = datt; a.out_stride = d; a.B = B; a.H = g.n_heads;
-            a.state = nullptr; a.n_keys = g.n_ctx;
+            a.dtype = dt; a.out = datt; a.out_stride = d; a.B = B; a.H = g.n_heads;
+            a.q_parts = qpre.parts; a.q_n_parts = qpre.n_parts; a.q_part_stride = qpre.part_stride; a.q_bias = qpre.bias;
+            a.state = nullptr; a.n_keys = g.n_ctx; a.active = active;
             const size_t per_kv = (size_t)max_batch * g.n_heads * g.n_ctx * 64;
             a.k = eoff(cross, (size_t)l * cross_layer_elems(), dt);
             a.v = eoff(cross, (size_t)l * cross_layer_elems() + per_kv, dt);
@@ -506,13 +530,13 @@ void Session::decode_step(cudaStream_t st) {
             ProfScope ps(this, PROF_CROSS_ATTN, st);
             decode_attention(a, st);
         }
-        lin(datt, d, L.cout, dx, d, F32, 0, dx);
+        const LnPreAdd after_cross = lin_split(datt, d, L.cout);
         // --- MLP
-        layernorm(dx, L.ln3.g, L.ln3.b, dln, dt, nullptr, B, d, 1e-5f, active, st);
+        ln(L.ln3, after_cross);
         lin(dln, d, L.fc1, dffn, g.ffn, dt, 1, nullptr);
-        lin(dffn, g.ffn, L.fc2, dx, d, F32, 0, dx);
+        pending = lin_split(dffn, g.ffn, L.fc2);
     }
-    layernorm(dx, m->dec_ln.g, m->dec_ln.b, dln, dt, nullptr, B, d, 1e-5f, active, st);
+    ln(m->dec_ln, pending);
     {
         // LM head: proj_out shares storage with embed_tokens (modeling_whisper.py:1335,1433), no bias
         GemmArgs a;

@@ -45,6 +45,41 @@ inline std::atomic<long long>& launch_counter() {
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): kernels of the decode step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization so that the NEXT kernel's launch latency and prologue
+// (barrier init, TMEM allocation, descriptor prefetch) overlap the tail of the current one.  Every such kernel
+// calls pdl_wait() before its first global-memory access (reads of the predecessor's outputs AND writes the
+// predecessor might still read) and pdl_trigger() right after, which only allows the dependent grid to start
+// being scheduled; its own pdl_wait() still blocks until this grid has completed and flushed.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool& pdl_enabled() {
+    static bool on = true;
+    return on;
+}
+
+// launch through cudaLaunchKernelEx; `pdl` adds the programmatic-serialization attribute (only for kernels that
+// call pdl_wait()).  Counts the launch like WB_CHECK_LAUNCH.
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                          Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+    ::wb::launch_counter().fetch_add(1, std::memory_order_relaxed);
+    WB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
+// ---------------------------------------------------------------------------------------------
 // dtypes
 // ---------------------------------------------------------------------------------------------
 enum DType : int { F32 = 0, BF16 = 1 };

@@ -30,6 +30,11 @@ struct GemmArgs {
     int m_period_in = 0, m_valid = 0, m_period_out = 0, m_out_offset = 0;  // 0 period = identity
     int out_mode = 0; int hs_heads = 0; int hs_batch = 0; int hs_b0 = 0;   // head-split store
     const int* active = nullptr;  // optional device flag: kernel is a no-op when *active == 0
+    // Split-K with DEFERRED reduction (skinny decode GEMMs): split s accumulates k in [s*K/k_splits, (s+1)*K/k_splits) and
+    // stores its raw fp32 partial at out + s*split_stride (out_dtype must be F32, no bias/act/residual); the consumer
+    // kernel (layernorm pre-add, decode attention q load) sums the slabs in a fixed order and adds the bias.
+    // k_splits == 0: let the launcher choose (<= max_k_splits); the choice is written to *chosen_splits.
+    int k_splits = 1; long long split_stride = 0; int max_k_splits = 1; int* chosen_splits = nullptr;
     // optional second output (same remap, row-major): fp32 copy of the result
     void* out2 = nullptr; long long ldo2 = 0;
 };
@@ -45,6 +50,12 @@ int get_gemm_backend();
 // LayerNorm over the last dim: x fp32 [rows, d] -> out (out_dtype) [rows, d], optional fp32 copy out2
 void layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_dtype, float* out2,
                int rows, int d, float eps, const int* active, cudaStream_t stream);
+// Residual update fused in front of the LayerNorm (consumer side of a split-K GEMM):
+//   x[r, :] += add_bias[:] + sum_{s < n_parts} parts[s * part_stride + r * d + :]   (fixed order; x updated in place)
+//   out[r, :] = LayerNorm(x[r, :])
+struct LnPreAdd { const float* parts = nullptr; int n_parts = 0; long long part_stride = 0; const float* bias = nullptr; };
+void layernorm_preadd(float* x, const LnPreAdd& pre, const float* gamma, const float* beta, void* out, int out_dtype,
+                      int rows, int d, float eps, const int* active, cudaStream_t stream);
 
 // conv1 im2col: mel fp32 [B, n_mels, T] -> A1 [B*T, kpad] (k = tap * n_mels + c, zero padded to kpad)
 void im2col_conv1(const float* mel, void* out, int out_dtype, int B, int n_mels, int T, int kpad, cudaStream_t stream);
@@ -62,6 +73,8 @@ int get_attn_backend();
 struct DecAttnArgs {
     int dtype = F32;
     const void* q = nullptr; long long q_stride = 0;     // q[b*q_stride + h*64 + j] (already scaled)
+    // alternative q source (consumer side of a split-K q projection): q = q_bias + sum_s q_parts[s*stride + b*H*64 + ...], fp32
+    const float* q_parts = nullptr; int q_n_parts = 0; long long q_part_stride = 0; const float* q_bias = nullptr;
     void* out = nullptr; long long out_stride = 0;       // out[b*out_stride + h*64 + j]
     int B = 0, H = 0;
     // --- contiguous K/V (cross attention, or explicit tensors): K[(b*kv_bstride + h*kv_hstride) + s*64 + j]
@@ -69,6 +82,7 @@ struct DecAttnArgs {
     int n_keys = 0;                // fixed key count (cross) when n_keys_dev == nullptr
     // --- paged self-attention: append k_new/v_new at slot (len-1), then attend over len keys
     const StepState* state = nullptr;   // when set: len = state->cur_len, no-op if !state->active
+    const int* active = nullptr;        // optional device flag for kernels without `state` (cross attention): no-op when 0
     const void* k_new = nullptr; const void* v_new = nullptr; long long new_stride = 0;  // [b*new_stride + h*64 + j]
     void* k_pages = nullptr; void* v_pages = nullptr;   // [page][H][page_tokens][64]
     const int* page_table = nullptr; int pages_per_seq = 0; int page_tokens = 64;

@@ -23,6 +23,7 @@ constexpr int CONV1_KPAD = 256;   // 3 * 80 = 240 zero-padded to a multiple of t
 constexpr int H1_ROWS = 3008;     // rows per utterance of the padded conv1 output (1 zero row + 3000 + 7 zero rows)
 constexpr int CONV2_MPERIOD = 1504;
 constexpr int PAGE_TOKENS = 64;
+constexpr int MAX_K_SPLITS = 8;   // split-K slabs of the skinny decode GEMMs (deferred reduction)
 // kernel classes for wb_session_profile
 enum ProfClass { PROF_NONE = 0, PROF_CROSS_ATTN = 1, PROF_SELF_ATTN = 2, PROF_DEC_GEMM = 3, PROF_LM_HEAD = 4,
                  PROF_ENC_GEMM = 5, PROF_ENC_ATTN = 6, PROF_LAYERNORM = 7, PROF_GREEDY = 8, PROF_STEM = 9, PROF_CROSS_KV = 10 };
@@ -78,7 +79,7 @@ struct Buffers {
     void* self_v = nullptr;
     int* page_table = nullptr;  // [max_batch][pages_per_seq]
     // decode activations
-    float* dx = nullptr; void* dln = nullptr; void* dqkv = nullptr; void* datt = nullptr; void* dq = nullptr;
+    float* dx = nullptr; float* dpart = nullptr; void* dln = nullptr; void* dqkv = nullptr; void* datt = nullptr; void* dq = nullptr;
     void* dffn = nullptr; float* logits = nullptr;
     int* tokens = nullptr; int* unfinished = nullptr; StepState* state = nullptr;
 };

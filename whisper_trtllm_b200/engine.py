@@ -215,7 +215,7 @@ class WhisperEngine:
 
     # ------------------------------------------------------------------ live kernel timing (bench roofline)
     PROF_CLASSES = {"cross_attn": 1, "self_attn": 2, "dec_gemm": 3, "lm_head": 4, "enc_gemm": 5, "enc_attn": 6,
-                    "greedy": 8, "stem": 9, "cross_kv": 10}
+                    "layernorm": 7, "greedy": 8, "stem": 9, "cross_kv": 10}
 
     def profile(self, kernel_class: Optional[str]):
         """Record CUDA events around every launch of one kernel class inside the real loop (None = off)."""
