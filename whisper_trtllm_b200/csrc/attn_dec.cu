@@ -20,14 +20,18 @@
 namespace wb {
 
 namespace {
-constexpr int DH = 64, THREADS = 256, WARPS = THREADS / 32, UNROLL = 4;
+constexpr int DH = 64, UNROLL = 4;
+// cross attention (1500 keys per item): 256 threads; paged self attention (<= 447 keys, latency-bound per item): 128
+// threads so that twice as many items are in flight per SM
+constexpr int THREADS_CROSS = 256, THREADS_SELF = 128;
 
 template <typename T> __device__ __forceinline__ float softmax_exp(float x);
 template <> __device__ __forceinline__ float softmax_exp<float>(float x) { return expf(x); }      // exactness path
 template <> __device__ __forceinline__ float softmax_exp<bf16>(float x) { return __expf(x); }     // speed path
 
 template <typename T, bool kPaged>
-__global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
+__global__ void __launch_bounds__(kPaged ? THREADS_SELF : THREADS_CROSS) decode_attn_kernel(DecAttnArgs a) {
+    constexpr int THREADS = kPaged ? THREADS_SELF : THREADS_CROSS, WARPS = THREADS / 32;
     constexpr int VEC = Vec16<T>::N;       // elements per 16-byte load: 8 (bf16) / 4 (fp32)
     constexpr int LPK = DH / VEC;          // lanes per key row: 8 / 16
     constexpr int KPW = 32 / LPK;          // key rows per warp instruction: 4 / 2
@@ -187,6 +191,7 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
 
 template <typename T, bool kPaged>
 void launch(const DecAttnArgs& a, cudaStream_t stream) {
+    constexpr int THREADS = kPaged ? THREADS_SELF : THREADS_CROSS;
     static int blocks_per_sm = 0, sms = 0;
     if (blocks_per_sm == 0) {
         int dev = 0;

@@ -165,12 +165,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                 __syncwarp();
                 const int n0 = n_blk * BN + c * 32 + rchunk * 4;
+                // phase 1: everything this slab needs from memory is requested before the first use (the residual may
+                // alias the output, so the compiler must not be left to interleave these loads with the stores below)
+                EpiRow er[8];
+                float4 f[8], rs[8];
+                const bool col_ok = n0 < ept.N;
+                float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ept.bias != nullptr && col_ok) bb = __ldg(reinterpret_cast<const float4*>(ept.bias + n0));
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int rr = i * 4 + rrow;
-                    const float4 f = st4[rr * 8 + (rchunk ^ (rr & 7))];
-                    float o[4] = {f.x, f.y, f.z, f.w};
-                    epi_store<4, true>(ept, epi_row(ept, row0 + rr), n0, o);
+                    er[i] = epi_row(ept, row0 + rr);
+                    er[i].valid = er[i].valid && col_ok;
+                    f[i] = st4[rr * 8 + (rchunk ^ (rr & 7))];
+                    rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ept.res != nullptr && er[i].valid)
+                        rs[i] = *reinterpret_cast<const float4*>(ept.res + er[i].res_row * ept.ldres + n0);
+                }
+                // phase 2: bias -> erf-GELU -> residual -> typed store
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float o[4] = {f[i].x + bb.x, f[i].y + bb.y, f[i].z + bb.z, f[i].w + bb.w};
+                    if (ept.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) o[j] = gelu_erf_fast(o[j]);
+                    }
+                    o[0] += rs[i].x; o[1] += rs[i].y; o[2] += rs[i].z; o[3] += rs[i].w;
+                    epi_write<4>(ept, er[i], n0, o);
                 }
                 __syncwarp();   // staging tile is rewritten by the next slab
             }

@@ -49,30 +49,10 @@ __device__ __forceinline__ EpiRow epi_row(const EpiParams& p, int m) {
     return r;
 }
 
-// NV consecutive columns starting at n0 (n0 % NV == 0); v holds the raw accumulators.
-template <int NV, bool kFastGelu>
-__device__ __forceinline__ void epi_store(const EpiParams& p, const EpiRow& r, int n0, float* v) {
-    static_assert(NV == 4 || NV == 8, "NV");
+// typed store of NV finished values (row remap / head-split scatter, optional fp32 copy)
+template <int NV>
+__device__ __forceinline__ void epi_write(const EpiParams& p, const EpiRow& r, int n0, const float* v) {
     if (!r.valid || n0 >= p.N) return;
-    if (p.bias != nullptr) {
-#pragma unroll
-        for (int i = 0; i < NV; i += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
-            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-        }
-    }
-    if (p.act == 1) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = kFastGelu ? gelu_erf_fast(v[i]) : gelu_erf(v[i]);
-    }
-    if (p.res != nullptr) {
-        const float* rp = p.res + r.res_row * p.ldres + n0;
-#pragma unroll
-        for (int i = 0; i < NV; i += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(rp + i);
-            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-        }
-    }
     long long off;
     if (p.out_mode == 0) {
         off = r.out_row * p.ldo + n0;
@@ -103,6 +83,33 @@ __device__ __forceinline__ void epi_store(const EpiParams& p, const EpiRow& r, i
 #pragma unroll
         for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     }
+}
+
+// NV consecutive columns starting at n0 (n0 % NV == 0); v holds the raw accumulators.
+template <int NV, bool kFastGelu>
+__device__ __forceinline__ void epi_store(const EpiParams& p, const EpiRow& r, int n0, float* v) {
+    static_assert(NV == 4 || NV == 8, "NV");
+    if (!r.valid || n0 >= p.N) return;
+    if (p.bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < NV; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+        }
+    }
+    if (p.act == 1) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = kFastGelu ? gelu_erf_fast(v[i]) : gelu_erf(v[i]);
+    }
+    if (p.res != nullptr) {
+        const float* rp = p.res + r.res_row * p.ldres + n0;
+#pragma unroll
+        for (int i = 0; i < NV; i += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(rp + i);
+            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+        }
+    }
+    epi_write<NV>(p, r, n0, v);
 }
 
 inline void validate_gemm_common(const GemmArgs& a) {
