@@ -52,6 +52,8 @@ def parse_args():
     p.add_argument("--enc-chunk", type=int, default=32)
     p.add_argument("--max-length", type=int, default=448)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-pdl", action="store_true", help="(dev) disable programmatic dependent launch between decode kernels")
+    p.add_argument("--no-graph", action="store_true", help="(dev) launch every decode kernel individually instead of replaying a CUDA graph")
     p.add_argument("--breakdown", action="store_true", help="(dev) per-kernel-class device time of one extra step, to stderr")
     return p.parse_args()
 
@@ -181,6 +183,11 @@ def main():
     from oracle import synth  # synthetic weights / inputs only (seeded, bit-reproducible)
     from whisper_trtllm_b200 import WhisperEngine
 
+    from whisper_trtllm_b200 import _abi
+    if args.no_pdl:
+        _abi.call("wb_set_pdl", 0)
+    if args.no_graph:
+        _abi.call("wb_set_cuda_graphs", 0)
     B = args.batch
     cfg = synth.make_config(args.size, max_length=args.max_length)
     t0 = time.time()

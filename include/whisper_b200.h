@@ -57,6 +57,8 @@ WB_API int wb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 WB_API int wb_set_backend(int gemm_backend, int attn_backend);
 /* programmatic dependent launch between the kernels of a decode step (default 1 = on); 0 = plain stream order */
 WB_API int wb_set_pdl(int enabled);
+/* wb_decode_run replays the decode step as a CUDA graph (default 1 = on); 0 = one launch per kernel.  Existing graphs are kept. */
+WB_API int wb_set_cuda_graphs(int enabled);
 /* number of kernels this library launched so far on this thread's device (bench `gpu_launches`) */
 WB_API long long wb_launch_count(void);
 

@@ -133,3 +133,28 @@ def test_bf16_teacher_forced_logits_within_tolerance(case):
     enc = eng.encode(mel.to(DEV))
     assert _rel(enc[:, ::ENC_T_STRIDE, ::ENC_D_STRIDE], g["enc_sub"]) < BF16_ENC_TOL
     eng.close()
+
+
+def test_cuda_graph_and_pdl_do_not_change_tokens():
+    """wb_decode_run replays the decode step as a CUDA graph with programmatic dependent launches; both are pure
+    scheduling changes: ids must be bit-identical to one-launch-per-kernel, plain stream order (bf16 and fp32)."""
+    from whisper_trtllm_b200 import _abi
+    cfg = synth.make_config("tiny.en", max_length=48)
+    sd = synth.make_weights(cfg, seed=1)
+    mel = synth.make_mel(5, seed=7).to(DEV)
+    for dtype in ("bfloat16", "float32"):
+        eng = WhisperEngine(cfg, sd, dtype=dtype, max_batch=5, device=DEV)
+        out = {}
+        for graphs, pdl in ((1, 1), (0, 0), (1, 0), (0, 1)):
+            _abi.call("wb_set_cuda_graphs", graphs)
+            _abi.call("wb_set_pdl", pdl)
+            n0 = eng.launch_count()
+            out[(graphs, pdl)] = eng.generate(mel).cpu()
+            assert eng.launch_count() - n0 > 47 * 40      # replays are counted like direct launches
+        _abi.call("wb_set_cuda_graphs", 1)
+        _abi.call("wb_set_pdl", 1)
+        ref = out[(0, 0)]
+        assert ref.shape == (5, 48)
+        for k, v in out.items():
+            assert torch.equal(v, ref), (dtype, k)
+        eng.close()

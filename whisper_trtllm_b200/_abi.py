@@ -36,6 +36,7 @@ SIGNATURES = {
     "wb_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "wb_set_backend": (c_int, [c_int, c_int]),
     "wb_set_pdl": (c_int, [c_int]),
+    "wb_set_cuda_graphs": (c_int, [c_int]),
     "wb_launch_count": (c_longlong, []),
     "wb_model_create": (c_int, [POINTER(wb_config), c_int, POINTER(c_void_p)]),
     "wb_model_destroy": (c_int, [c_void_p]),

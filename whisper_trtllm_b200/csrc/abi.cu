@@ -31,7 +31,7 @@ inline wb::Session* SS(wb_session* s) { return reinterpret_cast<wb::Session*>(s)
 
 #define WB_NOT_NULL(p) WB_REQUIRE((p) != nullptr, #p " is null")
 
-namespace wb { void set_gemm_tc_block_n(int bn); }
+namespace wb { void set_gemm_tc_block_n(int bn); void set_cuda_graphs(bool on); }
 
 extern "C" {
 
@@ -54,6 +54,11 @@ int wb_set_backend(int gemm_backend, int attn_backend) {
         wb::set_gemm_backend(gemm_backend);
         wb::set_attn_backend(attn_backend);
     });
+}
+
+int wb_set_cuda_graphs(int enabled) {
+    wb::set_cuda_graphs(enabled != 0);
+    return WB_OK;
 }
 
 int wb_set_pdl(int enabled) {

@@ -297,6 +297,7 @@ Session::Session(Model* model, int mb, int ec, void* workspace, size_t workspace
 }
 
 Session::~Session() {
+    if (step_graph) cudaGraphExecDestroy(step_graph);
     if (host_state) cudaFreeHost(host_state);
     if (check_event) cudaEventDestroy(check_event);
     for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
@@ -561,13 +562,64 @@ void Session::decode_step(cudaStream_t st) {
     ++steps_enqueued;
 }
 
+static bool& graphs_enabled() {
+    static bool on = true;
+    return on;
+}
+void set_cuda_graphs(bool on) { graphs_enabled() = on; }
+
+bool Session::graph_ok() const {
+    return graphs_enabled() && step_warm && forced_tokens == nullptr && logits_dump == nullptr && prof_class == 0;
+}
+
+void Session::build_step_graph(cudaStream_t st) {
+    if (step_graph) { cudaGraphExecDestroy(step_graph); step_graph = nullptr; }
+    const long long c0 = launch_counter().load();
+    const int enq0 = steps_enqueued;
+    WB_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    cudaGraph_t graph = nullptr;
+    try {
+        decode_step(st);
+    } catch (...) {
+        cudaStreamEndCapture(st, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        steps_enqueued = enq0;
+        launch_counter().store(c0);
+        throw;
+    }
+    WB_CHECK_CUDA(cudaStreamEndCapture(st, &graph));
+    step_graph_launches = launch_counter().load() - c0;
+    launch_counter().store(c0);      // nothing ran yet: replays are counted when they are launched
+    steps_enqueued = enq0;
+    const cudaError_t e = cudaGraphInstantiate(&step_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    WB_CHECK_CUDA(e);
+    step_graph_batch = batch;
+}
+
 int Session::decode_run(int max_steps, int check_every, cudaStream_t st) {
     const ModelConfig& g = m->cfg;
     if (max_steps <= 0 || max_steps > g.max_length - 1) max_steps = g.max_length - 1;
     if (check_every <= 0) check_every = 32;
     bool pending = false, stopped = false;
     for (int i = 0; i < max_steps && !stopped; ++i) {
-        decode_step(st);
+        if (graph_ok()) {
+            if (step_graph == nullptr || step_graph_batch != batch) {
+                try {
+                    build_step_graph(st);
+                } catch (const Error&) {
+                    graphs_enabled() = false;   // capture not possible here: stay on eager launches
+                }
+            }
+        }
+        if (graph_ok() && step_graph != nullptr && step_graph_batch == batch) {
+            WB_CHECK_CUDA(cudaGraphLaunch(step_graph, st));
+            launch_counter().fetch_add(step_graph_launches, std::memory_order_relaxed);
+            ++steps_enqueued;
+        } else {
+            decode_step(st);
+            step_warm = true;
+        }
         if ((i + 1) % check_every == 0 && i + 1 < max_steps) {
             // look at the PREVIOUS snapshot (long finished while a window of steps is still queued), then take a new one
             if (pending) {

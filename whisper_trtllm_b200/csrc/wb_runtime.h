@@ -93,6 +93,14 @@ struct Session : Buffers {
     int batch = 0;
     int steps_enqueued = 0;
     StepState* host_state = nullptr;  // pinned
+    // the decode step captured as a CUDA graph (all kernel arguments are step-invariant: lengths / stop flag live on the
+    // device), replayed by decode_run; eager launches are kept for teacher forcing, logits dumps and live profiling
+    cudaGraphExec_t step_graph = nullptr;
+    int step_graph_batch = 0;
+    long long step_graph_launches = 0;
+    bool step_warm = false;           // one eager step has run (one-time kernel attribute setup done)
+    bool graph_ok() const;
+    void build_step_graph(cudaStream_t s);
     cudaEvent_t check_event = nullptr;
     bool h1p_zeroed = false;
     // live per-kernel-class timing (bench roofline): CUDA events recorded on the launching stream around every
