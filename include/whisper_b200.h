@@ -55,8 +55,11 @@ WB_API int wb_version(void);
 WB_API int wb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* debug/bench switches: gemm 0 = tcgen05 for bf16 (default), 1 = CUDA-core; attention likewise */
 WB_API int wb_set_backend(int gemm_backend, int attn_backend);
-/* programmatic dependent launch between the kernels of a decode step (default 1 = on); 0 = plain stream order */
+/* programmatic dependent launch between the kernels of a decode step (default 0 = plain stream order; measured slower) */
 WB_API int wb_set_pdl(int enabled);
+/* measurement tool: stream `bytes` of device memory once (mode 0: 16-byte L1-bypassing loads, mode 1: cp.async.bulk into a
+ * shared-memory ring); time it with CUDA events to get the pure-read HBM ceiling of this GPU.  sink: 4 device bytes. */
+WB_API int wb_bandwidth_probe(const void* buf, size_t bytes, int mode, int ctas_per_sm, void* sink, wb_stream stream);
 /* wb_decode_run replays the decode step as a CUDA graph (default 1 = on); 0 = one launch per kernel.  Existing graphs are kept. */
 WB_API int wb_set_cuda_graphs(int enabled);
 /* number of kernels this library launched so far on this thread's device (bench `gpu_launches`) */
@@ -111,6 +114,10 @@ WB_API int wb_session_self_kv(wb_session* s, int layer, const void** k_pages, co
  * 4 LM head, 5 encoder GEMMs, 6 encoder attention, 8 greedy/argmax, 9 conv stem, 10 cross-K/V projection; 0 = off.
  * wb_session_profile_read synchronises, returns the summed device time and the launch count, and resets. */
 WB_API int wb_session_profile(wb_session* s, int kernel_class);
+/* like wb_session_profile, but decode-step kernel classes are timed only in the decode step with index `decode_step` of every
+ * greedy loop (that one step is launched eagerly, all others keep replaying the CUDA graph): per-launch events inside the
+ * timed region of the bench without giving up graph replay.  decode_step < 0 = every step. */
+WB_API int wb_session_profile_at(wb_session* s, int kernel_class, int decode_step);
 WB_API int wb_session_profile_read(wb_session* s, double* total_ms, long long* launches);
 
 /* ---- operators (module-level drop-ins and kernel tests) ---------------------------------------- */

@@ -211,5 +211,5 @@ def test_pdl_switch_gives_identical_results():
             ln = G.layernorm(h, w, b, torch.bfloat16)
             h = G.linear(ln, W, b, h, 0, torch.float32, backend=2)
         outs.append(h.clone())
-    _abi.call("wb_set_pdl", 1)
+    _abi.call("wb_set_pdl", 0)
     assert torch.equal(outs[0], outs[1]) and torch.isfinite(outs[0]).all()

@@ -37,6 +37,7 @@ SIGNATURES = {
     "wb_set_backend": (c_int, [c_int, c_int]),
     "wb_set_pdl": (c_int, [c_int]),
     "wb_set_cuda_graphs": (c_int, [c_int]),
+    "wb_bandwidth_probe": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p]),
     "wb_launch_count": (c_longlong, []),
     "wb_model_create": (c_int, [POINTER(wb_config), c_int, POINTER(c_void_p)]),
     "wb_model_destroy": (c_int, [c_void_p]),
@@ -58,6 +59,7 @@ SIGNATURES = {
     "wb_session_cross_kv": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_int64)]),
     "wb_session_self_kv": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_int)]),
     "wb_session_profile": (c_int, [c_void_p, c_int]),
+    "wb_session_profile_at": (c_int, [c_void_p, c_int, c_int]),
     "wb_session_profile_read": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_longlong)]),
     "wb_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "wb_linear": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64,

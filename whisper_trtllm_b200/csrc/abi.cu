@@ -31,7 +31,11 @@ inline wb::Session* SS(wb_session* s) { return reinterpret_cast<wb::Session*>(s)
 
 #define WB_NOT_NULL(p) WB_REQUIRE((p) != nullptr, #p " is null")
 
-namespace wb { void set_gemm_tc_block_n(int bn); void set_cuda_graphs(bool on); }
+namespace wb {
+void set_gemm_tc_block_n(int bn);
+void set_cuda_graphs(bool on);
+void bandwidth_probe(const void* buf, size_t bytes, int mode, int ctas_per_sm, unsigned* sink, cudaStream_t stream);
+}
 
 extern "C" {
 
@@ -54,6 +58,10 @@ int wb_set_backend(int gemm_backend, int attn_backend) {
         wb::set_gemm_backend(gemm_backend);
         wb::set_attn_backend(attn_backend);
     });
+}
+
+int wb_bandwidth_probe(const void* buf, size_t bytes, int mode, int ctas_per_sm, void* sink, wb_stream stream) {
+    return guarded([&] { wb::bandwidth_probe(buf, bytes, mode, ctas_per_sm, (unsigned*)sink, S(stream)); });
 }
 
 int wb_set_cuda_graphs(int enabled) {
@@ -212,6 +220,16 @@ int wb_session_profile(wb_session* s, int kernel_class) {
         WB_NOT_NULL(s);
         WB_REQUIRE(kernel_class >= 0 && kernel_class <= 10, "unknown kernel class");
         SS(s)->prof_class = kernel_class;
+        SS(s)->prof_step = -1;
+        SS(s)->prof_used = 0;
+    });
+}
+int wb_session_profile_at(wb_session* s, int kernel_class, int decode_step) {
+    return guarded([&] {
+        WB_NOT_NULL(s);
+        WB_REQUIRE(kernel_class >= 0 && kernel_class <= 10, "unknown kernel class");
+        SS(s)->prof_class = kernel_class;
+        SS(s)->prof_step = decode_step;
         SS(s)->prof_used = 0;
     });
 }

@@ -294,17 +294,27 @@ Session::Session(Model* model, int mb, int ec, void* workspace, size_t workspace
     WB_CHECK_CUDA(cudaMallocHost(&host_state, sizeof(StepState)));
     std::memset(host_state, 0, sizeof(StepState));
     WB_CHECK_CUDA(cudaEventCreateWithFlags(&check_event, cudaEventDisableTiming));
+    WB_CHECK_CUDA(cudaEventCreateWithFlags(&fence_event, cudaEventDisableTiming));
+    WB_CHECK_CUDA(cudaStreamCreateWithFlags(&loop_stream, cudaStreamNonBlocking));
 }
 
 Session::~Session() {
     if (step_graph) cudaGraphExecDestroy(step_graph);
+    if (loop_stream) cudaStreamDestroy(loop_stream);
+    if (fence_event) cudaEventDestroy(fence_event);
     if (host_state) cudaFreeHost(host_state);
     if (check_event) cudaEventDestroy(check_event);
     for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
 }
 
+static inline bool prof_active(const Session* s, int cls) {
+    if (cls != s->prof_class) return false;
+    if (s->prof_step < 0) return true;
+    return cls >= PROF_ENC_GEMM && cls != PROF_LAYERNORM && cls != PROF_GREEDY ? true : s->steps_enqueued == s->prof_step;
+}
+
 void Session::prof_begin(int cls, cudaStream_t st) {
-    if (cls != prof_class) return;
+    if (!prof_active(this, cls)) return;
     if (prof_used + 2 > prof_events.size()) {
         for (int i = 0; i < 2; ++i) {
             cudaEvent_t e;
@@ -315,7 +325,7 @@ void Session::prof_begin(int cls, cudaStream_t st) {
     WB_CHECK_CUDA(cudaEventRecord(prof_events[prof_used], st));
 }
 void Session::prof_end(int cls, cudaStream_t st) {
-    if (cls != prof_class) return;
+    if (!prof_active(this, cls)) return;
     WB_CHECK_CUDA(cudaEventRecord(prof_events[prof_used + 1], st));
     prof_used += 2;
 }
@@ -569,7 +579,8 @@ static bool& graphs_enabled() {
 void set_cuda_graphs(bool on) { graphs_enabled() = on; }
 
 bool Session::graph_ok() const {
-    return graphs_enabled() && step_warm && forced_tokens == nullptr && logits_dump == nullptr && prof_class == 0;
+    const bool timing_this_step = prof_class != 0 && (prof_step < 0 || steps_enqueued == prof_step);
+    return graphs_enabled() && step_warm && forced_tokens == nullptr && logits_dump == nullptr && !timing_this_step;
 }
 
 void Session::build_step_graph(cudaStream_t st) {
@@ -597,8 +608,13 @@ void Session::build_step_graph(cudaStream_t st) {
     step_graph_batch = batch;
 }
 
-int Session::decode_run(int max_steps, int check_every, cudaStream_t st) {
+int Session::decode_run(int max_steps, int check_every, cudaStream_t caller) {
     const ModelConfig& g = m->cfg;
+    // The loop runs on the session's own stream, fenced against the caller's stream on both sides: the caller may hand us
+    // the legacy default stream (torch's default), on which a CUDA graph can neither be captured nor replayed reliably.
+    cudaStream_t st = loop_stream;
+    WB_CHECK_CUDA(cudaEventRecord(fence_event, caller));
+    WB_CHECK_CUDA(cudaStreamWaitEvent(st, fence_event, 0));
     if (max_steps <= 0 || max_steps > g.max_length - 1) max_steps = g.max_length - 1;
     if (check_every <= 0) check_every = 32;
     bool pending = false, stopped = false;
@@ -609,6 +625,7 @@ int Session::decode_run(int max_steps, int check_every, cudaStream_t st) {
                     build_step_graph(st);
                 } catch (const Error&) {
                     graphs_enabled() = false;   // capture not possible here: stay on eager launches
+                    cudaGetLastError();         // do not leave the (non-sticky) capture error for the next caller to trip over
                 }
             }
         }
@@ -632,6 +649,8 @@ int Session::decode_run(int max_steps, int check_every, cudaStream_t st) {
         }
     }
     WB_CHECK_CUDA(cudaMemcpyAsync(host_state, state, sizeof(StepState), cudaMemcpyDeviceToHost, st));
+    WB_CHECK_CUDA(cudaEventRecord(fence_event, st));
+    WB_CHECK_CUDA(cudaStreamWaitEvent(caller, fence_event, 0));
     WB_CHECK_CUDA(cudaStreamSynchronize(st));
     return host_state->active ? host_state->cur_len : host_state->final_len;
 }

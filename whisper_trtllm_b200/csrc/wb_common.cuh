@@ -55,8 +55,10 @@ inline std::atomic<long long>& launch_counter() {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Default OFF: measured on B200 (bench.py A/B, profiles/r01_ab_graph_pdl.md) PDL gave no gain on eager launches
+// (4.61 s vs 4.58 s per 256 utterances) and cost 15 % inside CUDA-graph replays; the graph alone is the win.
 inline bool& pdl_enabled() {
-    static bool on = true;
+    static bool on = false;
     return on;
 }
 

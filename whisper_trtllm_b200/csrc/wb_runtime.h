@@ -95,6 +95,8 @@ struct Session : Buffers {
     StepState* host_state = nullptr;  // pinned
     // the decode step captured as a CUDA graph (all kernel arguments are step-invariant: lengths / stop flag live on the
     // device), replayed by decode_run; eager launches are kept for teacher forcing, logits dumps and live profiling
+    cudaStream_t loop_stream = nullptr;   // decode_run's own stream (graph capture is impossible on the legacy default stream)
+    cudaEvent_t fence_event = nullptr;
     cudaGraphExec_t step_graph = nullptr;
     int step_graph_batch = 0;
     long long step_graph_launches = 0;
@@ -106,6 +108,7 @@ struct Session : Buffers {
     // live per-kernel-class timing (bench roofline): CUDA events recorded on the launching stream around every
     // launch of the selected class inside the real loop
     int prof_class = 0;
+    int prof_step = -1;   // >= 0: only the decode step with this index is timed (and runs eagerly); the others replay the graph
     std::vector<cudaEvent_t> prof_events;  // pairs
     size_t prof_used = 0;
     void prof_begin(int cls, cudaStream_t s);

@@ -217,9 +217,12 @@ class WhisperEngine:
     PROF_CLASSES = {"cross_attn": 1, "self_attn": 2, "dec_gemm": 3, "lm_head": 4, "enc_gemm": 5, "enc_attn": 6,
                     "layernorm": 7, "greedy": 8, "stem": 9, "cross_kv": 10}
 
-    def profile(self, kernel_class: Optional[str]):
-        """Record CUDA events around every launch of one kernel class inside the real loop (None = off)."""
-        _abi.call("wb_session_profile", self._session, 0 if kernel_class is None else self.PROF_CLASSES[kernel_class])
+    def profile(self, kernel_class: Optional[str], decode_step: int = -1):
+        """Record CUDA events around every launch of one kernel class inside the real loop (None = off).
+        ``decode_step >= 0``: decode kernels are timed only in that step of each greedy loop (it runs eagerly; the other
+        steps keep replaying the CUDA graph)."""
+        _abi.call("wb_session_profile_at", self._session, 0 if kernel_class is None else self.PROF_CLASSES[kernel_class],
+                  int(decode_step))
 
     def profile_read(self):
         """-> (summed device milliseconds, launches) since profile() was armed; synchronises."""
