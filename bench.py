@@ -54,6 +54,7 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--pdl", action="store_true", help="(dev) enable programmatic dependent launch between decode kernels")
     p.add_argument("--no-graph", action="store_true", help="(dev) launch every decode kernel individually instead of replaying a CUDA graph")
+    p.add_argument("--bulk-attn", action="store_true", help="(dev) cp.async.bulk ring kernel for the cross attention")
     p.add_argument("--breakdown", action="store_true", help="(dev) per-kernel-class device time of one extra step, to stderr")
     return p.parse_args()
 
@@ -137,6 +138,16 @@ def cpu_reference_rtfx(size, max_length, sample_batch=2, sample_steps=16):
     return value, cores, sample, total
 
 
+def workload_config(args, world):
+    """The `config` object of the JSON line (same for our arm and the reference arm)."""
+    B = args.batch
+    return {"workload": f"whisper-{args.size} {args.dtype} greedy, batch {B} x 30 s synthetic log-mel per GPU, "
+                        f"{args.max_length}-token max decode, data-parallel by utterance",
+            "size": args.size, "batch_per_gpu": B, "global_batch": B * world, "max_length": args.max_length,
+            "l2": "inputs_exceed_l2 (per step the kernels stream ~49 GB of KV cache + 1.5 GB of weights)",
+            "parallelism": f"dp{world}"}
+
+
 def run_reference(args):
     """--impl reference: the CPU path only, on rank 0."""
     rank = int(os.environ.get("RANK", "0"))
@@ -154,8 +165,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"whisper-{args.size} greedy, synthetic 30 s log-mel 80x3000, {args.max_length}-token max decode",
-                   "size": args.size, "max_length": args.max_length},
+        "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -188,6 +198,8 @@ def main():
         _abi.call("wb_set_pdl", 1)
     if args.no_graph:
         _abi.call("wb_set_cuda_graphs", 0)
+    if args.bulk_attn:
+        _abi.call("wb_set_decode_attention_backend", 1)
     B = args.batch
     cfg = synth.make_config(args.size, max_length=args.max_length)
     t0 = time.time()
@@ -300,11 +312,7 @@ def main():
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(dev_ms / args.steps, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"whisper-{args.size} {args.dtype} greedy, batch {B} x 30 s synthetic log-mel per GPU, "
-                                   f"{args.max_length}-token max decode, data-parallel by utterance",
-                       "size": args.size, "batch_per_gpu": B, "global_batch": B * world, "max_length": args.max_length,
-                       "l2": "inputs_exceed_l2 (per step the kernels stream ~49 GB of KV cache + 1.5 GB of weights)",
-                       "parallelism": f"dp{world}"},
+            "config": workload_config(args, world),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": mel_host.numel() * 4,
                     "d2h_bytes_per_step": B * args.max_length * 4, "ms_per_step": round(e2e_ms / args.steps, 2)},
             "gpu_launches": int(launches),

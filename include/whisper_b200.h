@@ -60,6 +60,9 @@ WB_API int wb_set_pdl(int enabled);
 /* measurement tool: stream `bytes` of device memory once (mode 0: 16-byte L1-bypassing loads, mode 1: cp.async.bulk into a
  * shared-memory ring); time it with CUDA events to get the pure-read HBM ceiling of this GPU.  sink: 4 device bytes. */
 WB_API int wb_bandwidth_probe(const void* buf, size_t bytes, int mode, int ctas_per_sm, void* sink, wb_stream stream);
+/* cross-attention kernel of the decode step: 0 = 16-byte L1-bypassing loads, 4 CTAs/SM (default); 1 = cp.async.bulk into a
+ * 128 KB shared-memory ring, one CTA/SM (bf16 only).  Existing CUDA graphs keep the kernel they were captured with. */
+WB_API int wb_set_decode_attention_backend(int backend);
 /* wb_decode_run replays the decode step as a CUDA graph (default 1 = on); 0 = one launch per kernel.  Existing graphs are kept. */
 WB_API int wb_set_cuda_graphs(int enabled);
 /* number of kernels this library launched so far on this thread's device (bench `gpu_launches`) */

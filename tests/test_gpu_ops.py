@@ -213,3 +213,24 @@ def test_pdl_switch_gives_identical_results():
         outs.append(h.clone())
     _abi.call("wb_set_pdl", 0)
     assert torch.equal(outs[0], outs[1]) and torch.isfinite(outs[0]).all()
+
+
+@pytest.mark.parametrize("B,H,T,n", [(1, 6, 448, 1), (3, 8, 448, 77), (2, 16, 1500, 1500), (5, 2, 1500, 1499), (40, 16, 1500, 1500)])
+def test_decode_attention_bulk_ring_kernel(B, H, T, n):
+    """cp.async.bulk ring variant of the cross-attention kernel == the 16-byte-load kernel == fp32 torch."""
+    from whisper_trtllm_b200 import _abi
+    g = _gen(B + H + T + n + 1)
+    q = (torch.randn(B, H * 64, generator=g) * 0.3).to(DEV).to(torch.bfloat16)
+    k = torch.randn(B, H, T, 64, generator=g).to(DEV).to(torch.bfloat16)
+    v = torch.randn(B, H, T, 64, generator=g).to(DEV).to(torch.bfloat16)
+    w = torch.softmax(torch.einsum("bhd,bhtd->bht", q.float().view(B, H, 64), k.float()[:, :, :n]), dim=-1)
+    ref = torch.einsum("bht,bhtd->bhd", w, v.float()[:, :, :n]).reshape(B, H * 64)
+    base = G.decode_attention(q, k, v, n)
+    _abi.call("wb_set_decode_attention_backend", 1)
+    try:
+        out = G.decode_attention(q, k, v, n)
+        torch.cuda.synchronize()
+    finally:
+        _abi.call("wb_set_decode_attention_backend", 0)
+    assert G.rel_err(out, ref) < 6e-3
+    assert G.rel_err(out, base) < 6e-3

@@ -37,6 +37,7 @@ SIGNATURES = {
     "wb_set_backend": (c_int, [c_int, c_int]),
     "wb_set_pdl": (c_int, [c_int]),
     "wb_set_cuda_graphs": (c_int, [c_int]),
+    "wb_set_decode_attention_backend": (c_int, [c_int]),
     "wb_bandwidth_probe": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p]),
     "wb_launch_count": (c_longlong, []),
     "wb_model_create": (c_int, [POINTER(wb_config), c_int, POINTER(c_void_p)]),

@@ -34,6 +34,7 @@ inline wb::Session* SS(wb_session* s) { return reinterpret_cast<wb::Session*>(s)
 namespace wb {
 void set_gemm_tc_block_n(int bn);
 void set_cuda_graphs(bool on);
+void set_decode_attention_backend(int b);
 void bandwidth_probe(const void* buf, size_t bytes, int mode, int ctas_per_sm, unsigned* sink, cudaStream_t stream);
 }
 
@@ -62,6 +63,13 @@ int wb_set_backend(int gemm_backend, int attn_backend) {
 
 int wb_bandwidth_probe(const void* buf, size_t bytes, int mode, int ctas_per_sm, void* sink, wb_stream stream) {
     return guarded([&] { wb::bandwidth_probe(buf, bytes, mode, ctas_per_sm, (unsigned*)sink, S(stream)); });
+}
+
+int wb_set_decode_attention_backend(int backend) {
+    return guarded([&] {
+        WB_REQUIRE(backend == 0 || backend == 1, "backend must be 0 (16-byte loads) or 1 (cp.async.bulk ring)");
+        wb::set_decode_attention_backend(backend);
+    });
 }
 
 int wb_set_cuda_graphs(int enabled) {

@@ -206,7 +206,16 @@ void launch(const DecAttnArgs& a, cudaStream_t stream) {
 }
 }  // namespace
 
+bool decode_attention_bulk_supported(const DecAttnArgs& a);                 // attn_dec_bulk.cu
+void decode_attention_bulk(const DecAttnArgs& a, cudaStream_t stream);
+static int g_dec_attn_backend = 0;   // 0 = 16-byte load kernel, 1 = cp.async.bulk ring kernel for cross attention
+void set_decode_attention_backend(int b) { g_dec_attn_backend = b; }
+
 void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
+    if (g_dec_attn_backend == 1 && decode_attention_bulk_supported(a)) {
+        decode_attention_bulk(a, stream);
+        return;
+    }
     WB_REQUIRE((a.q || a.q_parts) && a.out && a.B > 0 && a.H > 0, "bad decode attention arguments");
     const bool paged = a.k_pages != nullptr;
     WB_REQUIRE(paged || (a.k && a.v), "missing K/V");
