@@ -54,7 +54,9 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--pdl", action="store_true", help="(dev) enable programmatic dependent launch between decode kernels")
     p.add_argument("--no-graph", action="store_true", help="(dev) launch every decode kernel individually instead of replaying a CUDA graph")
+    p.add_argument("--streams", type=int, default=1, help="sub-batches decoded concurrently on separate streams (per GPU)")
     p.add_argument("--bulk-attn", action="store_true", help="(dev) cp.async.bulk ring kernel for the cross attention")
+    p.add_argument("--attn-variant", type=int, default=0, help="(dev) cross-attention kernel variant 2..6 (threads, unroll)")
     p.add_argument("--breakdown", action="store_true", help="(dev) per-kernel-class device time of one extra step, to stderr")
     return p.parse_args()
 
@@ -200,11 +202,13 @@ def main():
         _abi.call("wb_set_cuda_graphs", 0)
     if args.bulk_attn:
         _abi.call("wb_set_decode_attention_backend", 1)
+    if args.attn_variant:
+        _abi.call("wb_set_decode_attention_backend", args.attn_variant)
     B = args.batch
     cfg = synth.make_config(args.size, max_length=args.max_length)
     t0 = time.time()
     sd = synth.make_weights(cfg, seed=0)
-    eng = WhisperEngine(cfg, sd, dtype=args.dtype, max_batch=B, enc_chunk=min(args.enc_chunk, B), device=dev)
+    eng = WhisperEngine(cfg, sd, dtype=args.dtype, max_batch=B, enc_chunk=min(args.enc_chunk, B), device=dev, n_streams=args.streams)
     del sd
     log(f"[rank {rank}] weights packed in {time.time() - t0:.1f}s; workspace {eng.workspace.numel() / 2**30:.1f} GiB")
     mel_host = synth.make_mel(B, seed=1234 + rank).pin_memory()
@@ -292,13 +296,16 @@ def main():
         es = 2 if args.dtype == "bf16" else 4
         # algorithmic bytes of one cross-attention launch: K and V of every (utterance, head) read once
         # (2 * 1500 * 64 elements) + q read + out written (X / L per utterance)
-        xattn_bytes = B * H * (2 * cfg["max_source_positions"] * 64 * es) + 2 * B * d * es
+        rows = eng.sub_batch if eng.n_streams > 1 else B      # the timed launches are those of sub-session 0
+        xattn_bytes = rows * H * (2 * cfg["max_source_positions"] * 64 * es) + 2 * rows * d * es
         achieved = xattn_bytes / (xattn_ms / max(xattn_n, 1) * 1e-3) / 1e9 if xattn_n else None
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get("decode_attn_cross_dram_bytes_per_launch")
+                traffic = json.load(f).get("decode_attn_cross_dram_bytes_per_launch")   # ncu capture at B = 256
+            if traffic is not None and rows != 256:
+                traffic = int(traffic * rows / 256)
         roofline = {"kernel": "decode_attn_kernel (cross-attention, 1 query x 1500 keys)", "bound": "hbm",
                     "achieved": round(achieved, 1) if achieved else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": round(achieved / peaks["hbm_gbs"], 4) if achieved else None, "traffic": traffic,
@@ -307,7 +314,7 @@ def main():
                     "timed": f"CUDA events on the launching stream around each launch of decode step {prof_step} of every "
                              "greedy loop inside the timed region (that step runs eagerly, the rest replay the CUDA graph)",
                     "share_of_step": round(xattn_ms / max(xattn_n, 1) * cfg["decoder_layers"] * (args.max_length - 1)
-                                           * args.steps / dev_ms, 4)}
+                                           * args.steps * eng.n_streams / dev_ms, 4)}
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(dev_ms / args.steps, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -315,7 +322,7 @@ def main():
             "config": workload_config(args, world),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": mel_host.numel() * 4,
                     "d2h_bytes_per_step": B * args.max_length * 4, "ms_per_step": round(e2e_ms / args.steps, 2)},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "streams_per_gpu": eng.n_streams,
             "clocks": clocks,
             "roofline": roofline,
         }

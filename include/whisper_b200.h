@@ -63,6 +63,9 @@ WB_API int wb_bandwidth_probe(const void* buf, size_t bytes, int mode, int ctas_
 /* cross-attention kernel of the decode step: 0 = 16-byte L1-bypassing loads, 4 CTAs/SM (default); 1 = cp.async.bulk into a
  * 128 KB shared-memory ring, one CTA/SM (bf16 only).  Existing CUDA graphs keep the kernel they were captured with. */
 WB_API int wb_set_decode_attention_backend(int backend);
+/* skinny (decode-step) GEMMs use the variant sized to co-reside with the bulk-ring cross-attention CTA of a concurrent stream
+ * (256 threads, <= 128 registers, <= 90 KB shared memory); set together with wb_decode_run_multi.  Default 0. */
+WB_API int wb_set_lean_decode_gemm(int enabled);
 /* wb_decode_run replays the decode step as a CUDA graph (default 1 = on); 0 = one launch per kernel.  Existing graphs are kept. */
 WB_API int wb_set_cuda_graphs(int enabled);
 /* number of kernels this library launched so far on this thread's device (bench `gpu_launches`) */
@@ -100,6 +103,10 @@ WB_API int wb_set_encoder_output(wb_session* s, const void* enc_states, int dtyp
 WB_API int wb_decode_begin(wb_session* s, int batch, wb_stream stream);
 WB_API int wb_decode_step(wb_session* s, wb_stream stream);
 WB_API int wb_decode_run(wb_session* s, int max_steps, int check_every, int* final_len, wb_stream stream);
+/* Greedy loops of several sessions of ONE model (disjoint sub-batches of utterances) interleaved step by step, each on its
+ * own stream, so that the HBM-bound cross-attention of one sub-batch overlaps the latency-bound GEMM / LayerNorm kernels of
+ * the others.  wb_decode_begin must have been called on every session.  final_lens: one int per session. */
+WB_API int wb_decode_run_multi(wb_session** sessions, int n_sessions, int max_steps, int check_every, int* final_lens, wb_stream stream);
 /* ids int32 [B, max_target_positions] (row stride max_target_positions); device pointer owned by the session */
 WB_API int wb_decode_tokens(wb_session* s, const int32_t** tokens_dev, int* row_stride);
 /* raw next-token logits of the last step, fp32 [B, vocab] (the decoder engine's output tensor, model.py:464) */
@@ -172,6 +179,13 @@ WB_API int wb_conv_stem_workspace_bytes(int batch, int d_model, int n_frames, in
 WB_API int wb_conv_stem(const float* mel, int batch, const void* w1_packed, const float* b1, const void* w2_packed, const float* b2,
                  const float* positions, int dtype, int d_model, int num_mel_bins, int n_frames, void* workspace,
                  size_t workspace_bytes, float* x_out, wb_stream stream);
+/* Log-mel front-end (the step BEFORE the path: WhisperFeatureExtractor, feature_extraction_whisper.py:96-109, numpy on the CPU
+ * in run.py:267).  pcm fp32 [B, 480000] on the device (16 kHz mono, zero padded / trimmed to 30 s); window [400] periodic Hann;
+ * dft_basis [408, 400] rows 0..200 cos(2 pi k j / 400), rows 201..401 -sin(...), rest 0; mel_filters [80, 208] (bins 201.. = 0);
+ * all fp32 device constants built by the caller (whisper_trtllm_b200/frontend.py).  input_features fp32 [B, 80, 3000]. */
+WB_API int wb_log_mel_workspace_bytes(int batch, size_t* bytes);
+WB_API int wb_log_mel(const float* pcm, int batch, const float* window, const float* dft_basis, const float* mel_filters, void* workspace,
+               size_t workspace_bytes, float* input_features, wb_stream stream);
 WB_API int wb_cast(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, wb_stream stream);
 
 #ifdef __cplusplus

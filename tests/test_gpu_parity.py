@@ -158,3 +158,42 @@ def test_cuda_graph_and_pdl_do_not_change_tokens():
         for k, v in out.items():
             assert torch.equal(v, ref), (dtype, k)
         eng.close()
+
+
+def test_multi_stream_sub_batches_give_the_same_tokens():
+    """n_streams > 1: the batch is split into sub-sessions whose greedy loops are interleaved on separate streams
+    (wb_decode_run_multi; bulk-ring cross-attention + lean decode GEMM so that their kernels can share an SM).  Rows are
+    independent, so fp32 ids are bit-identical to the single-session run (uneven shards, early EOS in one shard included);
+    bf16 differs only by split-K summation order (different tile shapes per sub-batch size)."""
+    from whisper_trtllm_b200 import _abi
+    cfg = synth.make_config("tiny.en", max_length=40)
+    sd = synth.make_weights(cfg, seed=3)
+    mel = synth.make_mel(5, seed=11).to(DEV)
+    try:
+        ref_eng = WhisperEngine(cfg, sd, dtype="float32", max_batch=5, device=DEV)
+        ref = ref_eng.generate(mel).cpu()
+        ref_eng.close()
+        for n_streams in (2, 3):
+            eng = WhisperEngine(cfg, sd, dtype="float32", max_batch=5, device=DEV, n_streams=n_streams)
+            assert torch.equal(eng.generate(mel).cpu(), ref), n_streams
+            assert torch.equal(eng.generate(mel[:3]).cpu(), ref[:3])          # fewer rows than sub-sessions can hold
+            eng.close()
+        # early stop of ONE sub-batch: make the token row 0 emits at step 4 the EOS; rows 3-4 (second shard) keep running
+        eos = int(ref[0, 4])
+        cfg2 = dict(cfg, eos_token_id=eos, pad_token_id=eos)
+        want = R.greedy(mel.cpu(), sd, cfg2)
+        eng = WhisperEngine(cfg2, sd, dtype="float32", max_batch=5, device=DEV, n_streams=2)
+        got = eng.generate(mel, check_every=2).cpu()
+        assert torch.equal(got.long(), want), (got[:, :10], want[:, :10])
+        eng.close()
+        # bf16: tcgen05 lean GEMM + bulk-ring attention on two streams vs the single-session kernels
+        e1 = WhisperEngine(cfg, sd, dtype="bfloat16", max_batch=5, device=DEV)
+        a = e1.generate(mel, max_new_tokens=24).cpu()
+        e1.close()
+        e2 = WhisperEngine(cfg, sd, dtype="bfloat16", max_batch=5, device=DEV, n_streams=2)
+        b = e2.generate(mel, max_new_tokens=24).cpu()
+        e2.close()
+        assert a.shape == b.shape and (a == b).float().mean() >= 0.9
+    finally:
+        _abi.call("wb_set_decode_attention_backend", 0)
+        _abi.call("wb_set_lean_decode_gemm", 0)

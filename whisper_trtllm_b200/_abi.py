@@ -37,6 +37,7 @@ SIGNATURES = {
     "wb_set_backend": (c_int, [c_int, c_int]),
     "wb_set_pdl": (c_int, [c_int]),
     "wb_set_cuda_graphs": (c_int, [c_int]),
+    "wb_set_lean_decode_gemm": (c_int, [c_int]),
     "wb_set_decode_attention_backend": (c_int, [c_int]),
     "wb_bandwidth_probe": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p]),
     "wb_launch_count": (c_longlong, []),
@@ -53,6 +54,7 @@ SIGNATURES = {
     "wb_decode_begin": (c_int, [c_void_p, c_int, c_void_p]),
     "wb_decode_step": (c_int, [c_void_p, c_void_p]),
     "wb_decode_run": (c_int, [c_void_p, c_int, c_int, POINTER(c_int), c_void_p]),
+    "wb_decode_run_multi": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, POINTER(c_int), c_void_p]),
     "wb_decode_tokens": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int)]),
     "wb_decode_logits": (c_int, [c_void_p, POINTER(c_void_p)]),
     "wb_decode_set_forced_tokens": (c_int, [c_void_p, c_void_p]),
@@ -80,6 +82,8 @@ SIGNATURES = {
     "wb_conv_stem_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "wb_conv_stem": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                              c_void_p, c_size_t, c_void_p, c_void_p]),
+    "wb_log_mel_workspace_bytes": (c_int, [c_int, POINTER(c_size_t)]),
+    "wb_log_mel": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "wb_cast": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p]),
 }
 

@@ -35,6 +35,10 @@ namespace wb {
 void set_gemm_tc_block_n(int bn);
 void set_cuda_graphs(bool on);
 void set_decode_attention_backend(int b);
+void set_lean_decode_gemm(bool on);
+size_t log_mel_workspace_bytes(int chunk);
+void log_mel(const float* pcm, int B, const float* window, const float* dft_basis, const float* mel_filters, void* workspace,
+             size_t workspace_bytes, float* out, cudaStream_t st);
 void bandwidth_probe(const void* buf, size_t bytes, int mode, int ctas_per_sm, unsigned* sink, cudaStream_t stream);
 }
 
@@ -67,9 +71,26 @@ int wb_bandwidth_probe(const void* buf, size_t bytes, int mode, int ctas_per_sm,
 
 int wb_set_decode_attention_backend(int backend) {
     return guarded([&] {
-        WB_REQUIRE(backend == 0 || backend == 1, "backend must be 0 (16-byte loads) or 1 (cp.async.bulk ring)");
+        WB_REQUIRE(backend >= 0 && backend <= 6, "backend must be 0 (16-byte loads), 1 (cp.async.bulk ring) or a tuning variant 2..6");
         wb::set_decode_attention_backend(backend);
     });
+}
+
+int wb_log_mel_workspace_bytes(int batch, size_t* bytes) {
+    return guarded([&] {
+        WB_NOT_NULL(bytes);
+        WB_REQUIRE(batch > 0, "batch must be positive");
+        *bytes = wb::log_mel_workspace_bytes(batch < 64 ? batch : 64);
+    });
+}
+int wb_log_mel(const float* pcm, int batch, const float* window, const float* dft_basis, const float* mel_filters, void* workspace,
+               size_t workspace_bytes, float* input_features, wb_stream stream) {
+    return guarded([&] { wb::log_mel(pcm, batch, window, dft_basis, mel_filters, workspace, workspace_bytes, input_features, S(stream)); });
+}
+
+int wb_set_lean_decode_gemm(int enabled) {
+    wb::set_lean_decode_gemm(enabled != 0);
+    return WB_OK;
 }
 
 int wb_set_cuda_graphs(int enabled) {
@@ -168,6 +189,12 @@ int wb_decode_run(wb_session* s, int max_steps, int check_every, int* final_len,
         WB_NOT_NULL(s);
         const int n = SS(s)->decode_run(max_steps, check_every, S(stream));
         if (final_len) *final_len = n;
+    });
+}
+int wb_decode_run_multi(wb_session** sessions, int n_sessions, int max_steps, int check_every, int* final_lens, wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(sessions);
+        wb::decode_run_multi(reinterpret_cast<wb::Session**>(sessions), n_sessions, max_steps, check_every, final_lens, S(stream));
     });
 }
 int wb_decode_tokens(wb_session* s, const int32_t** tokens_dev, int* row_stride) {

@@ -20,7 +20,7 @@
 namespace wb {
 
 namespace {
-constexpr int DH = 64, UNROLL = 4;
+constexpr int DH = 64;
 // cross attention (1500 keys per item): 256 threads; paged self attention (<= 447 keys, latency-bound per item): 128
 // threads so that twice as many items are in flight per SM
 constexpr int THREADS_CROSS = 256, THREADS_SELF = 128;
@@ -29,9 +29,9 @@ template <typename T> __device__ __forceinline__ float softmax_exp(float x);
 template <> __device__ __forceinline__ float softmax_exp<float>(float x) { return expf(x); }      // exactness path
 template <> __device__ __forceinline__ float softmax_exp<bf16>(float x) { return __expf(x); }     // speed path
 
-template <typename T, bool kPaged>
-__global__ void __launch_bounds__(kPaged ? THREADS_SELF : THREADS_CROSS) decode_attn_kernel(DecAttnArgs a) {
-    constexpr int THREADS = kPaged ? THREADS_SELF : THREADS_CROSS, WARPS = THREADS / 32;
+template <typename T, bool kPaged, int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
+    constexpr int WARPS = THREADS / 32;
     constexpr int VEC = Vec16<T>::N;       // elements per 16-byte load: 8 (bf16) / 4 (fp32)
     constexpr int LPK = DH / VEC;          // lanes per key row: 8 / 16
     constexpr int KPW = 32 / LPK;          // key rows per warp instruction: 4 / 2
@@ -189,26 +189,27 @@ __global__ void __launch_bounds__(kPaged ? THREADS_SELF : THREADS_CROSS) decode_
     }
 }
 
-template <typename T, bool kPaged>
+template <typename T, bool kPaged, int THREADS, int UNROLL>
 void launch(const DecAttnArgs& a, cudaStream_t stream) {
-    constexpr int THREADS = kPaged ? THREADS_SELF : THREADS_CROSS;
     static int blocks_per_sm = 0, sms = 0;
     if (blocks_per_sm == 0) {
         int dev = 0;
         WB_CHECK_CUDA(cudaGetDevice(&dev));
         WB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        WB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, decode_attn_kernel<T, kPaged>, THREADS, 0));
+        WB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, decode_attn_kernel<T, kPaged, THREADS, UNROLL>, THREADS, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     const int items = a.B * a.H;
     const int grid = std::min(items, sms * blocks_per_sm);
-    launch_kernel(decode_attn_kernel<T, kPaged>, dim3(grid), dim3(THREADS), 0, stream, true, a);
+    launch_kernel(decode_attn_kernel<T, kPaged, THREADS, UNROLL>, dim3(grid), dim3(THREADS), 0, stream, true, a);
 }
 }  // namespace
 
 bool decode_attention_bulk_supported(const DecAttnArgs& a);                 // attn_dec_bulk.cu
 void decode_attention_bulk(const DecAttnArgs& a, cudaStream_t stream);
-static int g_dec_attn_backend = 0;   // 0 = 16-byte load kernel, 1 = cp.async.bulk ring kernel for cross attention
+// 0 = 16-byte load kernel (256 threads, 4 x 2 loads in flight per lane), 1 = cp.async.bulk ring kernel for cross attention,
+// 2..6 = tuning variants of the load kernel for bf16 cross attention: (threads, unroll) = (128,4) (256,8) (128,8) (512,4) (256,2)
+static int g_dec_attn_backend = 0;
 void set_decode_attention_backend(int b) { g_dec_attn_backend = b; }
 
 void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
@@ -222,9 +223,18 @@ void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
     WB_REQUIRE(!paged || (a.page_table && a.v_pages && a.pages_per_seq > 0 && a.page_tokens > 0), "bad paged cache");
     WB_REQUIRE(paged ? a.state != nullptr : a.n_keys > 0, "key count must be positive");
     if (a.dtype == F32) {
-        if (paged) launch<float, true>(a, stream); else launch<float, false>(a, stream);
+        if (paged) launch<float, true, THREADS_SELF, 4>(a, stream); else launch<float, false, THREADS_CROSS, 4>(a, stream);
+    } else if (paged) {
+        launch<bf16, true, THREADS_SELF, 4>(a, stream);
     } else {
-        if (paged) launch<bf16, true>(a, stream); else launch<bf16, false>(a, stream);
+        switch (g_dec_attn_backend) {
+            case 2: launch<bf16, false, 128, 4>(a, stream); break;
+            case 3: launch<bf16, false, 256, 8>(a, stream); break;
+            case 4: launch<bf16, false, 128, 8>(a, stream); break;
+            case 5: launch<bf16, false, 512, 4>(a, stream); break;
+            case 6: launch<bf16, false, 256, 2>(a, stream); break;
+            default: launch<bf16, false, THREADS_CROSS, 4>(a, stream); break;
+        }
     }
 }
 

@@ -21,6 +21,7 @@ constexpr uint32_t CHUNK_BYTES = CHUNK_KEYS * ROW_BYTES;      // 8 KB of K (and 
 constexpr uint32_t STAGE_BYTES = 2 * CHUNK_BYTES;
 constexpr int STAGES = 8;
 constexpr int CW = 8;                                         // consumer warps
+static_assert(STAGES == CW, "stage s is owned by consumer warp s");
 constexpr int THREADS = (1 + CW) * 32;
 constexpr uint32_t SMEM_BAR = STAGES * STAGE_BYTES;
 constexpr uint32_t SMEM_PART = SMEM_BAR + 2 * STAGES * 8;
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(THREADS, 1) cross_attn_bulk_kernel(DecAttnArgs
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full[s], 1);
-            ptx::mbar_init(&empty[s], CW);
+            ptx::mbar_init(&empty[s], 1);   // released by the one consumer warp that owns the stage
         }
         ptx::fence_barrier_init();
     }
@@ -83,8 +84,8 @@ __global__ void __launch_bounds__(THREADS, 1) cross_attn_bulk_kernel(DecAttnArgs
         // ===================== consumers: online softmax out of shared memory =====================
         const int cw = warp - 1, ct = tid - 32;
         const int sub = lane & 7, grp = lane >> 3;     // 8 lanes per key row (16 B each), 4 rows per warp instruction
-        int stage = 0, parity = 0;
-        uint32_t phase = 0;
+        int parity = 0, chunk_base = 0;   // chunk_base: position of the item's first chunk in the ring, mod 8
+        uint32_t phase = 0;               // parity of this warp's own stage
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, parity ^= 1) {
             const int b = item / a.H, h = item - b * a.H;
             float qf[8];
@@ -107,55 +108,59 @@ __global__ void __launch_bounds__(THREADS, 1) cross_attn_bulk_kernel(DecAttnArgs
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 
-            for (int c = 0; c < n_chunks; ++c) {
+            // Stage s of the ring belongs to consumer warp s (STAGES == CW): chunk g of this CTA's chunk sequence lands in
+            // stage g % 8 and is consumed by warp g % 8 alone, 64 keys per mbarrier wait, 16 rows in flight per lane group.
+            const int first = ((cw - chunk_base) % CW + CW) % CW;
+            for (int c = first; c < n_chunks; c += CW) {
                 const int keys = min(CHUNK_KEYS, n - c * CHUNK_KEYS);
-                ptx::mbar_wait(&full[stage], phase);
-                const uint8_t* ks = smem + stage * STAGE_BYTES;
+                ptx::mbar_wait(&full[cw], phase);
+                const uint8_t* ks = smem + cw * STAGE_BYTES;
                 const uint8_t* vs = ks + CHUNK_BYTES;
-                Vec16<bf16> kr[2], vr[2];
-                int row[2];
+                for (int r0 = 0; r0 < keys; r0 += 16) {
+                    Vec16<bf16> kr[4], vr[4];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {       // this warp's 8 rows of the chunk: 2 instructions x 4 rows
-                    row[j] = cw * 8 + j * 4 + grp;
-                    const int r = min(row[j], keys - 1);
-                    kr[j].raw = *reinterpret_cast<const uint4*>(ks + r * ROW_BYTES + sub * 16);
-                    vr[j].raw = *reinterpret_cast<const uint4*>(vs + r * ROW_BYTES + sub * 16);
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = min(r0 + u * 4 + grp, keys - 1);
+                        kr[u].raw = *reinterpret_cast<const uint4*>(ks + r * ROW_BYTES + sub * 16);
+                        vr[u].raw = *reinterpret_cast<const uint4*>(vs + r * ROW_BYTES + sub * 16);
+                    }
+                    float sc[4];
+                    float mb = -INFINITY;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float kf[8];
+                        kr[u].unpack(kf);
+                        float dot = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) dot = fmaf(qf[i], kf[i], dot);
+                        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+                        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+                        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+                        sc[u] = (r0 + u * 4 + grp < keys) ? dot : -INFINITY;
+                        mb = fmaxf(mb, sc[u]);
+                    }
+                    const float m_new = fmaxf(m_run, mb);
+                    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+                    const float scale = __expf(m_run - m_use);
+                    l_run *= scale;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] *= scale;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float p = __expf(sc[u] - m_use);
+                        l_run += p;
+                        float vf[8];
+                        vr[u].unpack(vf);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
+                    }
+                    m_run = m_new;
                 }
-                float sc[2];
-                float mb = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    float kf[8];
-                    kr[j].unpack(kf);
-                    float dot = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) dot = fmaf(qf[i], kf[i], dot);
-                    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-                    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-                    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-                    sc[j] = row[j] < keys ? dot : -INFINITY;
-                    mb = fmaxf(mb, sc[j]);
-                }
-                const float m_new = fmaxf(m_run, mb);
-                const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-                const float scale = __expf(m_run - m_use);
-                l_run *= scale;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] *= scale;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const float p = __expf(sc[j] - m_use);
-                    l_run += p;
-                    float vf[8];
-                    vr[j].unpack(vf);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
-                }
-                m_run = m_new;
                 __syncwarp();                                    // every lane is done reading this stage
-                if (lane == 0) ptx::mbar_arrive(&empty[stage]);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                if (lane == 0) ptx::mbar_arrive(&empty[cw]);
+                phase ^= 1;
             }
+            chunk_base = (chunk_base + n_chunks) % CW;
 
             // ---- merge the 4 key groups of the warp, then the 8 warps
 #pragma unroll

@@ -23,24 +23,27 @@ namespace {
 
 constexpr int BM = 128, BK = 64;
 constexpr uint32_t A_BYTES = BM * BK * 2;
-constexpr int EPI_WARPS = 8, NUM_THREADS = (4 + EPI_WARPS) * 32;
-
-template <int BN> struct TcCfg {
+// kLean: the decode-step variant that must CO-RESIDE with the bulk-ring cross-attention CTA of a concurrent stream
+// (wb_decode_run_multi): 3 stages + 4 epilogue warps = 256 threads, <= 128 registers, <= 90 KB of shared memory.
+template <int BN, bool kLean> struct TcCfg {
+    static constexpr int EPI_WARPS = kLean ? 4 : 8;
+    static constexpr int NUM_THREADS = (4 + EPI_WARPS) * 32;
     static constexpr uint32_t B_BYTES = BN * BK * 2;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+    static constexpr int STAGES = kLean ? 3 : (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
     static constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {32,64,128,256}
     static constexpr uint32_t STAGING_BYTES = EPI_WARPS * 32 * 32 * 4;  // one 32x32 fp32 transpose tile per epilogue warp
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, bool kLean>
+__global__ void __launch_bounds__((TcCfg<BN, kLean>::NUM_THREADS), (kLean ? 2 : 1))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int K,
                int num_m_tiles, int num_n_tiles, int k_splits, long long split_stride, EpiParams ep,
                const int* __restrict__ active) {
-    using Cfg = TcCfg<BN>;
+    using Cfg = TcCfg<BN, kLean>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr int EPI_WARPS = Cfg::EPI_WARPS;
 
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte aligned bases
@@ -136,9 +139,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int q = warp & 3;             // the TMEM lane quarter this warp may read
-        const int half = (warp - 4) >> 2;   // which half of the tile's 32-column slabs this warp owns
+        const int half = (warp - 4) >> 2;   // which share of the tile's 32-column slabs this warp owns
         constexpr int SLABS = BN / 32;
-        constexpr int SLABS_PER_WARP = (SLABS + 1) / 2;
+        constexpr int HALVES = EPI_WARPS / 4;
+        constexpr int SLABS_PER_WARP = (SLABS + HALVES - 1) / HALVES;
         float4* st4 = reinterpret_cast<float4*>(staging + (warp - 4) * 32 * 32);   // [32 rows][8 chunks of 16 B], chunk ^= row & 7
         const int rrow = lane >> 3, rchunk = lane & 7;                             // read-back mapping: 4 rows x 128 B per instruction
         int acc = 0;
@@ -290,12 +294,12 @@ bool gemm_tc_supported(const GemmArgs& a) {
     return true;
 }
 
-template <int BN>
+template <int BN, bool kLean>
 static void launch_tc(const GemmArgs& a, int k_splits, cudaStream_t stream) {
-    using Cfg = TcCfg<BN>;
+    using Cfg = TcCfg<BN, kLean>;
     static bool configured = false;
     if (!configured) {
-        WB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        WB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, kLean>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
     const CUtensorMap tmA = make_tmap_bf16_2d(a.A, a.lda, a.M, a.K, BM);
@@ -303,12 +307,14 @@ static void launch_tc(const GemmArgs& a, int k_splits, cudaStream_t stream) {
     const int mt = ceil_div(a.M, BM), nt = ceil_div(a.N, BN);
     const int grid = std::min(mt * nt * k_splits, sm_count());
     EpiParams ep = make_epi(a);
-    launch_kernel(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES, stream, true, tmA, tmW, a.K, mt, nt, k_splits,
-                  a.split_stride, ep, a.active);
+    launch_kernel(gemm_tc_kernel<BN, kLean>, dim3(grid), dim3(Cfg::NUM_THREADS), Cfg::SMEM_BYTES, stream, true, tmA, tmW, a.K, mt, nt,
+                  k_splits, a.split_stride, ep, a.active);
 }
 
 static int g_force_bn = 0;
 void set_gemm_tc_block_n(int bn) { g_force_bn = bn; }
+static bool g_lean_decode = false;   // skinny GEMMs use the co-residency-friendly variant (set for multi-stream decoding)
+void set_lean_decode_gemm(bool on) { g_lean_decode = on; }
 
 // Tile width / split-K choice.  Large M (encoder): the widest tile that still gives every SM a tile.  Skinny M (decode,
 // one or two M tiles): the kernel is bound by how fast one SM can pull operand bytes (~40 B/clk/SM measured: 64 CTAs
@@ -327,6 +333,7 @@ static void pick_config(const GemmArgs& a, int max_splits, int& bn_out, int& spl
     double best = 1e30;
     bn_out = 32; splits_out = 1;
     for (int bn : {32, 64, 128, 256}) {
+        if (g_lean_decode && bn > 64 && a.N <= 8192) continue;   // lean variant exists for BN <= 64 (LM head keeps the wide tile)
         for (int s = 1; s <= max_splits; s *= 2) {
             if (nkb % s != 0) continue;
             const long long ctas = (long long)mt * ceil_div(a.N, bn) * s;
@@ -352,11 +359,12 @@ void gemm_tc(const GemmArgs& a, cudaStream_t stream) {
         WB_REQUIRE(a.out_dtype == F32 && a.bias == nullptr && a.res == nullptr && a.act == 0 && a.out_mode == 0 && a.out2 == nullptr,
                    "split-K stores raw fp32 partials: bias / activation / residual belong to the consumer");
     if (a.chosen_splits) *a.chosen_splits = splits;
+    const bool lean = g_lean_decode && ceil_div(a.M, BM) <= 2 && bn <= 64;
     switch (bn) {
-        case 256: launch_tc<256>(a, splits, stream); break;
-        case 128: launch_tc<128>(a, splits, stream); break;
-        case 64: launch_tc<64>(a, splits, stream); break;
-        case 32: launch_tc<32>(a, splits, stream); break;
+        case 256: launch_tc<256, false>(a, splits, stream); break;
+        case 128: launch_tc<128, false>(a, splits, stream); break;
+        case 64: if (lean) launch_tc<64, true>(a, splits, stream); else launch_tc<64, false>(a, splits, stream); break;
+        case 32: if (lean) launch_tc<32, true>(a, splits, stream); else launch_tc<32, false>(a, splits, stream); break;
         default: WB_REQUIRE(false, "unsupported BLOCK_N");
     }
 }

@@ -608,51 +608,85 @@ void Session::build_step_graph(cudaStream_t st) {
     step_graph_batch = batch;
 }
 
-int Session::decode_run(int max_steps, int check_every, cudaStream_t caller) {
-    const ModelConfig& g = m->cfg;
-    // The loop runs on the session's own stream, fenced against the caller's stream on both sides: the caller may hand us
-    // the legacy default stream (torch's default), on which a CUDA graph can neither be captured nor replayed reliably.
+// one decode step on the session's loop stream: CUDA-graph replay when possible, eager launches otherwise
+void Session::enqueue_step() {
     cudaStream_t st = loop_stream;
-    WB_CHECK_CUDA(cudaEventRecord(fence_event, caller));
-    WB_CHECK_CUDA(cudaStreamWaitEvent(st, fence_event, 0));
-    if (max_steps <= 0 || max_steps > g.max_length - 1) max_steps = g.max_length - 1;
-    if (check_every <= 0) check_every = 32;
-    bool pending = false, stopped = false;
-    for (int i = 0; i < max_steps && !stopped; ++i) {
-        if (graph_ok()) {
-            if (step_graph == nullptr || step_graph_batch != batch) {
-                try {
-                    build_step_graph(st);
-                } catch (const Error&) {
-                    graphs_enabled() = false;   // capture not possible here: stay on eager launches
-                    cudaGetLastError();         // do not leave the (non-sticky) capture error for the next caller to trip over
-                }
+    if (graph_ok()) {
+        if (step_graph == nullptr || step_graph_batch != batch) {
+            try {
+                build_step_graph(st);
+            } catch (const Error&) {
+                graphs_enabled() = false;   // capture not possible here: stay on eager launches
+                cudaGetLastError();         // do not leave the (non-sticky) capture error for the next caller to trip over
             }
-        }
-        if (graph_ok() && step_graph != nullptr && step_graph_batch == batch) {
-            WB_CHECK_CUDA(cudaGraphLaunch(step_graph, st));
-            launch_counter().fetch_add(step_graph_launches, std::memory_order_relaxed);
-            ++steps_enqueued;
-        } else {
-            decode_step(st);
-            step_warm = true;
-        }
-        if ((i + 1) % check_every == 0 && i + 1 < max_steps) {
-            // look at the PREVIOUS snapshot (long finished while a window of steps is still queued), then take a new one
-            if (pending) {
-                WB_CHECK_CUDA(cudaEventSynchronize(check_event));
-                if (host_state->active == 0) stopped = true;
-            }
-            WB_CHECK_CUDA(cudaMemcpyAsync(host_state, state, sizeof(StepState), cudaMemcpyDeviceToHost, st));
-            WB_CHECK_CUDA(cudaEventRecord(check_event, st));
-            pending = true;
         }
     }
-    WB_CHECK_CUDA(cudaMemcpyAsync(host_state, state, sizeof(StepState), cudaMemcpyDeviceToHost, st));
-    WB_CHECK_CUDA(cudaEventRecord(fence_event, st));
-    WB_CHECK_CUDA(cudaStreamWaitEvent(caller, fence_event, 0));
-    WB_CHECK_CUDA(cudaStreamSynchronize(st));
-    return host_state->active ? host_state->cur_len : host_state->final_len;
+    if (graph_ok() && step_graph != nullptr && step_graph_batch == batch) {
+        WB_CHECK_CUDA(cudaGraphLaunch(step_graph, st));
+        launch_counter().fetch_add(step_graph_launches, std::memory_order_relaxed);
+        ++steps_enqueued;
+    } else {
+        decode_step(st);
+        step_warm = true;
+    }
+}
+
+// Greedy loops of n independent sessions (sub-batches of one model) interleaved step by step, each on its own stream:
+// the HBM-bound cross-attention of one sub-batch overlaps the latency-bound GEMM / LayerNorm kernels of the others.
+// n == 1 is the plain loop.  Loops run on the sessions' own streams, fenced against the caller's stream on both sides
+// (the caller may hand us the legacy default stream, on which a CUDA graph can neither be captured nor replayed).
+void decode_run_multi(Session** ss, int n, int max_steps, int check_every, int* final_lens, cudaStream_t caller) {
+    WB_REQUIRE(ss != nullptr && n >= 1 && n <= 8, "1..8 sessions");
+    for (int k = 0; k < n; ++k) WB_REQUIRE(ss[k] != nullptr && ss[k]->batch > 0, "decode_begin was not called on every session");
+    const ModelConfig& g = ss[0]->m->cfg;
+    if (max_steps <= 0 || max_steps > g.max_length - 1) max_steps = g.max_length - 1;
+    if (check_every <= 0) check_every = 32;
+    bool pending[8] = {}, stopped[8] = {};
+    for (int k = 0; k < n; ++k) {
+        WB_CHECK_CUDA(cudaEventRecord(ss[k]->fence_event, caller));
+        WB_CHECK_CUDA(cudaStreamWaitEvent(ss[k]->loop_stream, ss[k]->fence_event, 0));
+    }
+    for (int i = 0; i < max_steps; ++i) {
+        bool any = false;
+        for (int k = 0; k < n; ++k) {
+            if (stopped[k]) continue;
+            any = true;
+            ss[k]->enqueue_step();
+        }
+        if (!any) break;
+        if ((i + 1) % check_every == 0 && i + 1 < max_steps) {
+            // look at the PREVIOUS snapshot (long finished while a window of steps is still queued), then take a new one
+            for (int k = 0; k < n; ++k) {
+                if (stopped[k]) continue;
+                Session* s = ss[k];
+                if (pending[k]) {
+                    WB_CHECK_CUDA(cudaEventSynchronize(s->check_event));
+                    if (s->host_state->active == 0) { stopped[k] = true; continue; }
+                }
+                WB_CHECK_CUDA(cudaMemcpyAsync(s->host_state, s->state, sizeof(StepState), cudaMemcpyDeviceToHost, s->loop_stream));
+                WB_CHECK_CUDA(cudaEventRecord(s->check_event, s->loop_stream));
+                pending[k] = true;
+            }
+        }
+    }
+    for (int k = 0; k < n; ++k) {
+        Session* s = ss[k];
+        WB_CHECK_CUDA(cudaMemcpyAsync(s->host_state, s->state, sizeof(StepState), cudaMemcpyDeviceToHost, s->loop_stream));
+        WB_CHECK_CUDA(cudaEventRecord(s->fence_event, s->loop_stream));
+        WB_CHECK_CUDA(cudaStreamWaitEvent(caller, s->fence_event, 0));
+    }
+    for (int k = 0; k < n; ++k) {
+        Session* s = ss[k];
+        WB_CHECK_CUDA(cudaStreamSynchronize(s->loop_stream));
+        if (final_lens) final_lens[k] = s->host_state->active ? s->host_state->cur_len : s->host_state->final_len;
+    }
+}
+
+int Session::decode_run(int max_steps, int check_every, cudaStream_t caller) {
+    Session* self = this;
+    int final_len = 0;
+    decode_run_multi(&self, 1, max_steps, check_every, &final_len, caller);
+    return final_len;
 }
 
 }  // namespace wb

@@ -126,8 +126,11 @@ struct Session : Buffers {
     void decode_begin(int B, cudaStream_t s);
     void decode_step(cudaStream_t s);
     int decode_run(int max_steps, int check_every, cudaStream_t s);  // returns final length (syncs)
+    void enqueue_step();                                             // one step on loop_stream (graph replay or eager)
     size_t cross_layer_elems() const;
     size_t self_layer_elems() const;
 };
+
+void decode_run_multi(Session** sessions, int n, int max_steps, int check_every, int* final_lens, cudaStream_t caller);
 
 }  // namespace wb

@@ -29,7 +29,10 @@ def begin_index_of(config: Dict, input_ids_seq_length: int = 1) -> int:
 
 class WhisperEngine:
     def __init__(self, config: Dict, state_dict: Dict[str, torch.Tensor], dtype="float32", max_batch: int = 1,
-                 enc_chunk: Optional[int] = None, device: Optional[torch.device] = None):
+                 enc_chunk: Optional[int] = None, device: Optional[torch.device] = None, n_streams: int = 1):
+        """``n_streams`` > 1 splits the batch into that many sub-batches, each with its own native session (KV caches,
+        token loop) on its own stream; their greedy loops are interleaved (wb_decode_run_multi) so that one sub-batch's
+        HBM-bound cross-attention overlaps the other's latency-bound kernels.  Rows are independent, so the ids are the same."""
         if not torch.cuda.is_available():
             raise _abi.WhisperB200Error(-101, "a CUDA device is required (no CPU fallback)")
         self.lib = _abi.load()
@@ -38,7 +41,9 @@ class WhisperEngine:
         self.torch_dtype = _TORCH_DTYPE[self.dtype_code]
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.max_batch = int(max_batch)
-        self.enc_chunk = int(min(enc_chunk or 32, max_batch))
+        self.n_streams = max(1, min(int(n_streams), self.max_batch))
+        self.sub_batch = -(-self.max_batch // self.n_streams)          # rows per sub-session (last one may be smaller)
+        self.enc_chunk = int(min(enc_chunk or 32, self.sub_batch))
         c = config
         assert c["encoder_attention_heads"] == c["decoder_attention_heads"] and c["encoder_ffn_dim"] == c["decoder_ffn_dim"]
         self._cfg = _abi.wb_config(
@@ -55,10 +60,19 @@ class WhisperEngine:
             self._load_state_dict(state_dict)
             self._set_generation()
             nbytes = c_size_t()
-            _abi.call("wb_session_workspace_bytes", self._model, self.max_batch, self.enc_chunk, byref(nbytes))
-            self.workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
-            _abi.call("wb_session_create", self._model, self.max_batch, self.enc_chunk, ptr(self.workspace),
-                      c_size_t(nbytes.value), byref(self._session))
+            _abi.call("wb_session_workspace_bytes", self._model, self.sub_batch, self.enc_chunk, byref(nbytes))
+            self._subs = []   # (session handle, workspace tensor)
+            for _ in range(self.n_streams):
+                ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+                h = c_void_p()
+                _abi.call("wb_session_create", self._model, self.sub_batch, self.enc_chunk, ptr(ws), c_size_t(nbytes.value), byref(h))
+                self._subs.append((h, ws))
+            self._session, self.workspace = self._subs[0]
+            if self.n_streams > 1:
+                # co-residency of the two streams' kernels on one SM: bulk-ring cross-attention (1 CTA/SM, bytes in flight
+                # in shared memory) + the lean decode GEMM (csrc/attn_dec_bulk.cu, gemm_tc.cu kLean)
+                _abi.call("wb_set_decode_attention_backend", 1)
+                _abi.call("wb_set_lean_decode_gemm", 1)
         self.d_model = c["d_model"]
         self.n_ctx = c["max_source_positions"]
         self.vocab = c["vocab_size"]
@@ -107,24 +121,43 @@ class WhisperEngine:
         assert mel.is_cuda and mel.dtype == torch.float32 and mel.is_contiguous(), "mel must be a contiguous fp32 CUDA tensor"
         B = mel.shape[0]
         out = torch.empty(B, self.n_ctx, self.d_model, dtype=torch.float32, device=mel.device) if return_hidden else None
-        _abi.call("wb_encode", self._session, ptr(mel), B, ptr(out), stream_handle(stream))
+        for k, (b0, b1) in enumerate(self._shards(B)):
+            _abi.call("wb_encode", self._subs[k][0], ptr(mel[b0:b1]), b1 - b0, ptr(out[b0:b1]) if out is not None else None,
+                      stream_handle(stream))
         return out
+
+    def _shards(self, B: int):
+        """Contiguous row ranges of the sub-sessions for a batch of B rows (empty ranges dropped)."""
+        assert 0 < B <= self.max_batch, f"batch {B} exceeds max_batch {self.max_batch}"
+        return [(b0, min(b0 + self.sub_batch, B)) for b0 in range(0, B, self.sub_batch)]
+
+    def _single(self, what: str):
+        if self.n_streams != 1:
+            raise NotImplementedError(f"{what} is only available with n_streams == 1")
 
     def set_encoder_output(self, enc: torch.Tensor, stream=None):
         assert enc.is_cuda and enc.is_contiguous() and enc.dtype in (torch.float32, torch.bfloat16)
-        _abi.call("wb_set_encoder_output", self._session, ptr(enc), _DTYPES[enc.dtype], enc.shape[0], stream_handle(stream))
+        for k, (b0, b1) in enumerate(self._shards(enc.shape[0])):
+            _abi.call("wb_set_encoder_output", self._subs[k][0], ptr(enc[b0:b1]), _DTYPES[enc.dtype], b1 - b0, stream_handle(stream))
 
     # ------------------------------------------------------------------ greedy decode
     def decode_begin(self, batch: int, stream=None):
-        _abi.call("wb_decode_begin", self._session, batch, stream_handle(stream))
+        self._active = self._shards(batch)
+        for k, (b0, b1) in enumerate(self._active):
+            _abi.call("wb_decode_begin", self._subs[k][0], b1 - b0, stream_handle(stream))
 
     def decode_step(self, stream=None):
-        _abi.call("wb_decode_step", self._session, stream_handle(stream))
+        for k in range(len(getattr(self, "_active", [None]))):
+            _abi.call("wb_decode_step", self._subs[k][0], stream_handle(stream))
 
     def decode_run(self, max_steps: int = 0, check_every: int = 32, stream=None) -> int:
-        n = c_int()
-        _abi.call("wb_decode_run", self._session, max_steps, check_every, byref(n), stream_handle(stream))
-        return n.value
+        """Runs the greedy loop(s) to the end; returns the final sequence length (the longest over the sub-batches)."""
+        n = len(getattr(self, "_active", [None]))
+        handles = (c_void_p * n)(*[self._subs[k][0] for k in range(n)])
+        lens = (c_int * n)()
+        _abi.call("wb_decode_run_multi", handles, n, max_steps, check_every, lens, stream_handle(stream))
+        self._final_lens = list(lens)
+        return max(self._final_lens)
 
     def _view(self, address: int, shape, dtype) -> torch.Tensor:
         """Zero-copy torch view of session-owned device memory (lives inside self.workspace)."""
@@ -136,19 +169,37 @@ class WhisperEngine:
         assert 0 <= off and off + nbytes <= self.workspace.numel()
         return self.workspace[off:off + nbytes].view(dtype).view(*shape)
 
+    def _view_of(self, ws: torch.Tensor, address: int, shape, dtype) -> torch.Tensor:
+        off = address - ws.data_ptr()
+        n = 1
+        for s_ in shape:
+            n *= s_
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        assert 0 <= off and off + nbytes <= ws.numel()
+        return ws[off:off + nbytes].view(dtype).view(*shape)
+
     def tokens(self) -> torch.Tensor:
-        """ids int32 [max_batch, max_target_positions] (view into the session)."""
-        p, stride = c_void_p(), c_int()
-        _abi.call("wb_decode_tokens", self._session, byref(p), byref(stride))
-        return self._view(p.value, (self.max_batch, stride.value), torch.int32)
+        """ids int32 [rows, max_target_positions]: a view into the session (n_streams == 1) or the sub-sessions' rows
+        concatenated (copy)."""
+        parts = []
+        for k, (h, ws) in enumerate(self._subs):
+            p, stride = c_void_p(), c_int()
+            _abi.call("wb_decode_tokens", h, byref(p), byref(stride))
+            parts.append(self._view_of(ws, p.value, (self.sub_batch, stride.value), torch.int32))
+        if self.n_streams == 1:
+            return parts[0]
+        shards = getattr(self, "_active", self._shards(self.max_batch))
+        return torch.cat([parts[k][:b1 - b0] for k, (b0, b1) in enumerate(shards)], dim=0)
 
     def logits(self) -> torch.Tensor:
+        self._single("logits()")
         p = c_void_p()
         _abi.call("wb_decode_logits", self._session, byref(p))
         return self._view(p.value, (self.max_batch, self.vocab), torch.float32)
 
     def cross_kv(self, layer: int) -> torch.Tensor:
         """[2, max_batch, H, 1500, 64] view of the cross-attention cache of one decoder layer."""
+        self._single("cross_kv()")
         p, stride = c_void_p(), c_int64()
         _abi.call("wb_session_cross_kv", self._session, layer, byref(p), byref(stride))
         H = self.config["decoder_attention_heads"]
@@ -156,6 +207,7 @@ class WhisperEngine:
 
     def self_kv(self, layer: int, batch: int, length: int):
         """Gather the paged self-attention cache of one layer into dense [B, H, length, 64] K and V."""
+        self._single("self_kv()")
         kp, vp, pt, pps, ptok = c_void_p(), c_void_p(), c_void_p(), c_int(), c_int()
         _abi.call("wb_session_self_kv", self._session, layer, byref(kp), byref(vp), byref(pt), byref(pps), byref(ptok))
         H = self.config["decoder_attention_heads"]
@@ -182,6 +234,8 @@ class WhisperEngine:
     def greedy(self, B: int, max_new_tokens=None, forced_tokens=None, dump_logits_steps: int = 0, check_every: int = 32,
                stream=None):
         dump = None
+        if forced_tokens is not None or dump_logits_steps > 0:
+            self._single("teacher forcing / logits dump")
         if forced_tokens is not None:
             ft = torch.full((B, self.max_tgt), self.config["pad_token_id"], dtype=torch.int32, device=self.device)
             ft[:, :forced_tokens.shape[1]] = forced_tokens.to(device=self.device, dtype=torch.int32)
@@ -196,6 +250,9 @@ class WhisperEngine:
         steps = 0 if max_new_tokens is None else int(max_new_tokens)
         final_len = self.decode_run(steps, check_every, stream)
         ids = self.tokens()[:B, :final_len].clone()
+        if self.n_streams > 1:   # a sub-batch whose rows all hit EOS stopped earlier: its tail is pad (GU:1506-1510)
+            for (b0, b1), n in zip(self._active, self._final_lens):
+                ids[b0:b1, n:] = self.config["pad_token_id"]
         _abi.call("wb_decode_set_logits_dump", self._session, None, 0)
         _abi.call("wb_decode_set_forced_tokens", self._session, None)
         if dump is not None:
@@ -235,9 +292,11 @@ class WhisperEngine:
         return int(self.lib.wb_launch_count())
 
     def close(self):
-        if self._session:
-            _abi.call("wb_session_destroy", self._session)
-            self._session = c_void_p()
+        for h, _ in getattr(self, "_subs", []):
+            if h:
+                _abi.call("wb_session_destroy", h)
+        self._subs = []
+        self._session = c_void_p()
         if self._model:
             _abi.call("wb_model_destroy", self._model)
             self._model = c_void_p()
