@@ -36,6 +36,7 @@ void set_gemm_tc_block_n(int bn);
 void set_cuda_graphs(bool on);
 void set_decode_attention_backend(int b);
 void set_lean_decode_gemm(bool on);
+void set_self_attention_warp_kernel(bool on);
 size_t log_mel_workspace_bytes(int chunk);
 void log_mel(const float* pcm, int B, const float* window, const float* dft_basis, const float* mel_filters, void* workspace,
              size_t workspace_bytes, float* out, cudaStream_t st);
@@ -71,7 +72,7 @@ int wb_bandwidth_probe(const void* buf, size_t bytes, int mode, int ctas_per_sm,
 
 int wb_set_decode_attention_backend(int backend) {
     return guarded([&] {
-        WB_REQUIRE(backend >= 0 && backend <= 6, "backend must be 0 (16-byte loads), 1 (cp.async.bulk ring) or a tuning variant 2..6");
+        WB_REQUIRE(backend >= 0 && backend <= 9, "backend must be 0 (16-byte loads), 1 (cp.async.bulk ring) or a tuning variant 2..9");
         wb::set_decode_attention_backend(backend);
     });
 }
@@ -86,6 +87,11 @@ int wb_log_mel_workspace_bytes(int batch, size_t* bytes) {
 int wb_log_mel(const float* pcm, int batch, const float* window, const float* dft_basis, const float* mel_filters, void* workspace,
                size_t workspace_bytes, float* input_features, wb_stream stream) {
     return guarded([&] { wb::log_mel(pcm, batch, window, dft_basis, mel_filters, workspace, workspace_bytes, input_features, S(stream)); });
+}
+
+int wb_set_self_attention_warp_kernel(int enabled) {
+    wb::set_self_attention_warp_kernel(enabled != 0);
+    return WB_OK;
 }
 
 int wb_set_lean_decode_gemm(int enabled) {

@@ -189,6 +189,107 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
     }
 }
 
+// Paged self-attention, ONE WARP PER (utterance, head) item.  The items are short (<= 447 keys = 57 KB at the mean
+// length) and the CTA-per-item kernel above spends its time in per-item latency chains (q -> page table -> K/V round
+// trips -> smem merge -> barrier): 55 us at length 224 where the bytes need 36 us.  Here every warp owns an item, keeps
+// 2 * UNROLL 16-byte loads in flight per lane, merges its four 8-lane groups with shuffles and never touches shared
+// memory or a block barrier; all 4096 items of a launch are resident at once.
+template <typename T, int UNROLL>
+__global__ void __launch_bounds__(128) self_attn_warp_kernel(DecAttnArgs a) {
+    constexpr int VEC = Vec16<T>::N, LPK = DH / VEC, KPW = 32 / LPK;
+    pdl_wait();
+    pdl_trigger();
+    if (a.state->active == 0) return;
+    const int n = a.state->cur_len;
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= a.B * a.H) return;                       // whole warp
+    const int b = item / a.H, h = item - b * a.H;
+    const int sub = lane % LPK, grp = lane / LPK;
+    const int* pt = a.page_table + (size_t)b * a.pages_per_seq;
+    auto row_off = [&](int s) -> size_t {
+        return (((size_t)pt[s / a.page_tokens] * a.H + h) * a.page_tokens + (s % a.page_tokens)) * DH + sub * VEC;
+    };
+    if (a.k_new != nullptr) {
+        if (grp == 0) {   // in-place append at slot n-1
+            const size_t off = row_off(n - 1);
+            const size_t src = (size_t)b * a.new_stride + h * DH + sub * VEC;
+            st16(reinterpret_cast<T*>(a.k_pages) + off, ld16(reinterpret_cast<const T*>(a.k_new) + src));
+            st16(reinterpret_cast<T*>(a.v_pages) + off, ld16(reinterpret_cast<const T*>(a.v_new) + src));
+        }
+        __syncwarp();     // the appended row is read below by the other lane groups of this warp
+    }
+    float qf[VEC];
+    ld16(reinterpret_cast<const T*>(a.q) + (size_t)b * a.q_stride + h * DH + sub * VEC).unpack(qf);
+    float m_run = -INFINITY, l_run = 0.f;
+    float acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+    for (int sb = 0; sb < n; sb += KPW * UNROLL) {       // warp-uniform trip count
+        const int s0 = sb + grp;
+        Vec16<T> kr[UNROLL], vr[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const size_t off = row_off(min(s0 + u * KPW, n - 1));
+            kr[u] = ld16_issue(reinterpret_cast<const T*>(a.k_pages) + off);
+            vr[u] = ld16_issue(reinterpret_cast<const T*>(a.v_pages) + off);
+        }
+        float sc[UNROLL];
+        float mb = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            float kf[VEC];
+            kr[u].unpack(kf);
+            float dot = 0.f;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) dot = fmaf(qf[i], kf[i], dot);
+#pragma unroll
+            for (int o = LPK / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            sc[u] = (s0 + u * KPW < n) ? dot : -INFINITY;
+            mb = fmaxf(mb, sc[u]);
+        }
+        const float m_new = fmaxf(m_run, mb);
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        const float scale = softmax_exp<T>(m_run - m_use);
+        l_run *= scale;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] *= scale;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const float p = softmax_exp<T>(sc[u] - m_use);
+            l_run += p;
+            float vf[VEC];
+            vr[u].unpack(vf);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
+        }
+        m_run = m_new;
+    }
+#pragma unroll
+    for (int o = LPK; o < 32; o <<= 1) {                 // merge the key groups of the warp
+        const float om = __shfl_xor_sync(0xffffffffu, m_run, o);
+        const float ol = __shfl_xor_sync(0xffffffffu, l_run, o);
+        const float mm = fmaxf(m_run, om);
+        const float s1 = (m_run == -INFINITY) ? 0.f : softmax_exp<T>(m_run - mm);
+        const float s2 = (om == -INFINITY) ? 0.f : softmax_exp<T>(om - mm);
+        l_run = l_run * s1 + ol * s2;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float oa = __shfl_xor_sync(0xffffffffu, acc[i], o);
+            acc[i] = acc[i] * s1 + oa * s2;
+        }
+        m_run = mm;
+    }
+    if (grp == 0) {
+        const float inv = 1.0f / l_run;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] *= inv;
+        Vec16<T> o;
+        o.pack(acc);
+        st16(reinterpret_cast<T*>(a.out) + (size_t)b * a.out_stride + h * DH + sub * VEC, o);
+    }
+}
+
 template <typename T, bool kPaged, int THREADS, int UNROLL>
 void launch(const DecAttnArgs& a, cudaStream_t stream) {
     static int blocks_per_sm = 0, sms = 0;
@@ -208,8 +309,10 @@ void launch(const DecAttnArgs& a, cudaStream_t stream) {
 bool decode_attention_bulk_supported(const DecAttnArgs& a);                 // attn_dec_bulk.cu
 void decode_attention_bulk(const DecAttnArgs& a, cudaStream_t stream);
 // 0 = 16-byte load kernel (256 threads, 4 x 2 loads in flight per lane), 1 = cp.async.bulk ring kernel for cross attention,
-// 2..6 = tuning variants of the load kernel for bf16 cross attention: (threads, unroll) = (128,4) (256,8) (128,8) (512,4) (256,2)
+// 2..9 = tuning variants of the load kernel for bf16 cross attention (threads, unroll); default (128, 8)
 static int g_dec_attn_backend = 0;
+static bool g_self_attn_warp = true;   // paged self-attention: one warp per item (default) vs one CTA per item
+void set_self_attention_warp_kernel(bool on) { g_self_attn_warp = on; }
 void set_decode_attention_backend(int b) { g_dec_attn_backend = b; }
 
 void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
@@ -222,18 +325,29 @@ void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
     WB_REQUIRE(paged || (a.k && a.v), "missing K/V");
     WB_REQUIRE(!paged || (a.page_table && a.v_pages && a.pages_per_seq > 0 && a.page_tokens > 0), "bad paged cache");
     WB_REQUIRE(paged ? a.state != nullptr : a.n_keys > 0, "key count must be positive");
+    if (paged && g_self_attn_warp && a.q != nullptr) {
+        const int items = a.B * a.H;
+        if (a.dtype == F32) launch_kernel(self_attn_warp_kernel<float, 8>, dim3(ceil_div(items, 4)), dim3(128), 0, stream, true, a);
+        else launch_kernel(self_attn_warp_kernel<bf16, 8>, dim3(ceil_div(items, 4)), dim3(128), 0, stream, true, a);
+        return;
+    }
     if (a.dtype == F32) {
         if (paged) launch<float, true, THREADS_SELF, 4>(a, stream); else launch<float, false, THREADS_CROSS, 4>(a, stream);
     } else if (paged) {
         launch<bf16, true, THREADS_SELF, 4>(a, stream);
     } else {
+        // measured on B200 (B = 256, medium.en; us per launch): (256,4) 239.5 | (128,4) 247.1 | (256,8) 235.5 | (128,8) 232.1 |
+        // (512,4) 247.8 | (256,2) 265.4  -> default 128 threads x 8-deep batches (16 requests in flight per lane)
         switch (g_dec_attn_backend) {
             case 2: launch<bf16, false, 128, 4>(a, stream); break;
             case 3: launch<bf16, false, 256, 8>(a, stream); break;
-            case 4: launch<bf16, false, 128, 8>(a, stream); break;
+            case 4: launch<bf16, false, 256, 4>(a, stream); break;
             case 5: launch<bf16, false, 512, 4>(a, stream); break;
             case 6: launch<bf16, false, 256, 2>(a, stream); break;
-            default: launch<bf16, false, THREADS_CROSS, 4>(a, stream); break;
+            case 7: launch<bf16, false, 128, 12>(a, stream); break;
+            case 8: launch<bf16, false, 64, 8>(a, stream); break;
+            case 9: launch<bf16, false, 192, 8>(a, stream); break;
+            default: launch<bf16, false, 128, 8>(a, stream); break;
         }
     }
 }

@@ -143,6 +143,14 @@ template <typename T> __device__ __forceinline__ Vec16<T> ld16_stream(const T* p
     v.raw = *reinterpret_cast<decltype(v.raw)*>(&r);
     return v;
 }
+// 16-byte coherent load the compiler may not sink or merge: keeps a whole batch of independent requests in flight
+template <typename T> __device__ __forceinline__ Vec16<T> ld16_issue(const T* p) {
+    Vec16<T> v;
+    uint4 r;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    v.raw = *reinterpret_cast<decltype(v.raw)*>(&r);
+    return v;
+}
 template <typename T> __device__ __forceinline__ void st16(T* p, const Vec16<T>& v) {
     *reinterpret_cast<decltype(v.raw)*>(p) = v.raw;
 }
