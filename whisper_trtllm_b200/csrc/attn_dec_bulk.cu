@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(THREADS, 1) cross_attn_bulk_kernel(DecAttnArgs
         uint32_t phase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int b = item / a.H, h = item - b * a.H;
+            if (a.row_active != nullptr && a.row_active[b] == 0) continue;   // finished utterance (consumers skip it too)
             const size_t o = (size_t)b * a.kv_bstride + (size_t)h * a.kv_hstride;
             const bf16* kb = reinterpret_cast<const bf16*>(a.k) + o;
             const bf16* vb = reinterpret_cast<const bf16*>(a.v) + o;
@@ -86,8 +87,10 @@ __global__ void __launch_bounds__(THREADS, 1) cross_attn_bulk_kernel(DecAttnArgs
         const int sub = lane & 7, grp = lane >> 3;     // 8 lanes per key row (16 B each), 4 rows per warp instruction
         int parity = 0, chunk_base = 0;   // chunk_base: position of the item's first chunk in the ring, mod 8
         uint32_t phase = 0;               // parity of this warp's own stage
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, parity ^= 1) {
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int b = item / a.H, h = item - b * a.H;
+            if (a.row_active != nullptr && a.row_active[b] == 0) continue;
+            parity ^= 1;
             float qf[8];
             if (a.q_parts != nullptr) {   // q = bias + sum of the split-K slabs of the q projection (fp32, fixed order)
                 const int c0 = h * DH + sub * 8;

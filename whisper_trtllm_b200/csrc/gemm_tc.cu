@@ -156,6 +156,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::tcgen05_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
             const int row0 = m_blk * BM + q * 32;
+            const int g0 = ept.m_period_in > 0 ? row0 / ept.m_period_in : 0;   // one division per tile (period >= 128 rows)
 #pragma unroll 1
             for (int ci = 0; ci < SLABS_PER_WARP; ++ci) {
                 const int c = half * SLABS_PER_WARP + ci;
@@ -179,7 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int rr = i * 4 + rrow;
-                    er[i] = epi_row(ept, row0 + rr);
+                    er[i] = epi_row_near(ept, row0 + rr, g0);
                     er[i].valid = er[i].valid && col_ok;
                     f[i] = st4[rr * 8 + (rchunk ^ (rr & 7))];
                     rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);

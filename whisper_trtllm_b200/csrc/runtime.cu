@@ -517,7 +517,7 @@ void Session::decode_step(cudaStream_t st) {
         {
             DecAttnArgs a;
             a.dtype = dt; a.q = dqkv; a.q_stride = 3 * d; a.out = datt; a.out_stride = d; a.B = B; a.H = g.n_heads;
-            a.state = state;
+            a.state = state; a.row_active = unfinished;
             a.k_new = eoff(dqkv, d, dt); a.v_new = eoff(dqkv, 2 * d, dt); a.new_stride = 3 * d;
             a.k_pages = eoff(self_k, (size_t)l * self_layer_elems(), dt);
             a.v_pages = eoff(self_v, (size_t)l * self_layer_elems(), dt);
@@ -533,7 +533,7 @@ void Session::decode_step(cudaStream_t st) {
             DecAttnArgs a;
             a.dtype = dt; a.out = datt; a.out_stride = d; a.B = B; a.H = g.n_heads;
             a.q_parts = qpre.parts; a.q_n_parts = qpre.n_parts; a.q_part_stride = qpre.part_stride; a.q_bias = qpre.bias;
-            a.state = nullptr; a.n_keys = g.n_ctx; a.active = active;
+            a.state = nullptr; a.n_keys = g.n_ctx; a.active = active; a.row_active = unfinished;
             const size_t per_kv = (size_t)max_batch * g.n_heads * g.n_ctx * 64;
             a.k = eoff(cross, (size_t)l * cross_layer_elems(), dt);
             a.v = eoff(cross, (size_t)l * cross_layer_elems() + per_kv, dt);

@@ -49,6 +49,25 @@ __device__ __forceinline__ EpiRow epi_row(const EpiParams& p, int m) {
     return r;
 }
 
+// Same as epi_row for a row m >= row0 close to row0: g0 = row0 / m_period_in is computed once per tile, no division per row.
+__device__ __forceinline__ EpiRow epi_row_near(const EpiParams& p, int m, int g0) {
+    EpiRow r;
+    r.valid = m < p.M;
+    if (p.m_period_in > 0) {
+        r.g = g0;
+        r.r_in = m - g0 * p.m_period_in;
+        while (r.r_in >= p.m_period_in) { r.r_in -= p.m_period_in; r.g += 1; }   // at most 32 / period + 1 trips
+        r.valid = r.valid && (r.r_in < p.m_valid);
+        r.out_row = (long long)r.g * p.m_period_out + r.r_in + p.m_out_offset;
+    } else {
+        r.g = 0;
+        r.r_in = m;
+        r.out_row = m;
+    }
+    r.res_row = p.res_periodic ? r.r_in : r.out_row;
+    return r;
+}
+
 // typed store of NV finished values (row remap / head-split scatter, optional fp32 copy)
 template <int NV>
 __device__ __forceinline__ void epi_write(const EpiParams& p, const EpiRow& r, int n0, const float* v) {

@@ -83,6 +83,9 @@ struct DecAttnArgs {
     // --- paged self-attention: append k_new/v_new at slot (len-1), then attend over len keys
     const StepState* state = nullptr;   // when set: len = state->cur_len, no-op if !state->active
     const int* active = nullptr;        // optional device flag for kernels without `state` (cross attention): no-op when 0
+    // optional per-utterance flags (the greedy loop's `unfinished_sequences`): rows that already emitted EOS are skipped —
+    // their K/V are not read at all (their next tokens are pad regardless, generation/utils.py:1506-1510)
+    const int* row_active = nullptr;
     const void* k_new = nullptr; const void* v_new = nullptr; long long new_stride = 0;  // [b*new_stride + h*64 + j]
     void* k_pages = nullptr; void* v_pages = nullptr;   // [page][H][page_tokens][64]
     const int* page_table = nullptr; int pages_per_seq = 0; int page_tokens = 64;
