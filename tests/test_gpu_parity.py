@@ -197,3 +197,39 @@ def test_multi_stream_sub_batches_give_the_same_tokens():
     finally:
         _abi.call("wb_set_decode_attention_backend", 0)
         _abi.call("wb_set_lean_decode_gemm", 0)
+
+
+def test_edge_cases_batch_sizes_lengths_and_errors():
+    """Ragged encoder chunks, B = 1, changing batch sizes on one engine (graph re-capture), the shortest possible loop
+    (max_length 2: only the forced token), and loud failures on bad arguments."""
+    from whisper_trtllm_b200 import WhisperB200Error
+    cfg = synth.make_config("micro", max_length=20)
+    sd = synth.make_weights(cfg, seed=4)
+    mel = synth.make_mel(7, seed=21)
+    ref = R.greedy(mel, sd, cfg)
+    eng = WhisperEngine(cfg, sd, dtype="float32", max_batch=7, enc_chunk=3, device=DEV)     # chunks of 3, 3, 1
+    assert torch.equal(eng.generate(mel.to(DEV)).cpu().long(), ref)
+    for b in (1, 4, 7, 2):                                                                   # same engine, other batch sizes
+        assert torch.equal(eng.generate(mel[:b].to(DEV)).cpu().long(), ref[:b]), b
+    assert torch.equal(eng.generate(mel[:3].to(DEV), max_new_tokens=5).cpu().long(), ref[:3, :6])
+    with pytest.raises(AssertionError):
+        eng.generate(synth.make_mel(8, seed=1).to(DEV))                                      # batch > max_batch
+    with pytest.raises(AssertionError):
+        eng.encode(mel.to(DEV).double())
+    with pytest.raises(WhisperB200Error):
+        eng.decode_begin(0)
+    eng.close()
+    cfg2 = dict(cfg, max_length=2)
+    ref2 = R.greedy(mel[:2], sd, cfg2)
+    eng = WhisperEngine(cfg2, sd, dtype="bfloat16", max_batch=2, device=DEV)
+    ids = eng.generate(mel[:2].to(DEV)).cpu().long()
+    assert ids.shape == (2, 2) and torch.equal(ids, ref2) and ids[0, 1] == 50362
+    eng.close()
+    # a state_dict with a missing tensor / a wrong shape is rejected when the engine is built
+    bad = {k: v for k, v in sd.items() if k != "model.decoder.layers.1.fc2.bias"}
+    with pytest.raises(WhisperB200Error):
+        WhisperEngine(cfg, bad, dtype="float32", max_batch=1, device=DEV)
+    bad = dict(sd)
+    bad["model.encoder.conv2.bias"] = torch.zeros(3)
+    with pytest.raises(WhisperB200Error):
+        WhisperEngine(cfg, bad, dtype="float32", max_batch=1, device=DEV)

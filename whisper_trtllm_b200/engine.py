@@ -142,6 +142,8 @@ class WhisperEngine:
 
     # ------------------------------------------------------------------ greedy decode
     def decode_begin(self, batch: int, stream=None):
+        if not 0 < batch <= self.max_batch:
+            raise _abi.WhisperB200Error(-1, f"decode batch {batch} outside (0, {self.max_batch}]")
         self._active = self._shards(batch)
         for k, (b0, b1) in enumerate(self._active):
             _abi.call("wb_decode_begin", self._subs[k][0], b1 - b0, stream_handle(stream))
