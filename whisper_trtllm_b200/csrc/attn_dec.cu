@@ -21,6 +21,9 @@ namespace wb {
 
 namespace {
 constexpr int DH = 64;
+// the page size is a compile-time power of two: the paged kernels were instruction-issue bound (ncu: 0.59 IPC per scheduler,
+// 69 instructions per 512-byte load) with a runtime integer division and modulo in every row address
+constexpr int PAGE_TOKENS_C = 64, PAGE_SHIFT = 6;
 // cross attention (1500 keys per item): 256 threads; paged self attention (<= 447 keys, latency-bound per item): 128
 // threads so that twice as many items are in flight per SM
 constexpr int THREADS_CROSS = 256, THREADS_SELF = 128;
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
             if (a.k_new != nullptr) {
                 if (warp == 0 && grp == 0) {  // in-place append at slot n-1
                     const int s = n - 1;
-                    const size_t off = (((size_t)pt[s / a.page_tokens] * a.H + h) * a.page_tokens + (s % a.page_tokens)) * DH + sub * VEC;
+                    const size_t off = (((size_t)pt[s >> PAGE_SHIFT] * a.H + h) * PAGE_TOKENS_C + (s & (PAGE_TOKENS_C - 1))) * DH + sub * VEC;
                     const size_t src = (size_t)b * a.new_stride + h * DH + sub * VEC;
                     st16(reinterpret_cast<T*>(a.k_pages) + off, ld16(reinterpret_cast<const T*>(a.k_new) + src));
                     st16(reinterpret_cast<T*>(a.v_pages) + off, ld16(reinterpret_cast<const T*>(a.v_new) + src));
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
         }
         auto row_off = [&](int s) -> size_t {
             if constexpr (kPaged)
-                return (((size_t)pt[s / a.page_tokens] * a.H + h) * a.page_tokens + (s % a.page_tokens)) * DH + sub * VEC;
+                return (((size_t)pt[s >> PAGE_SHIFT] * a.H + h) * PAGE_TOKENS_C + (s & (PAGE_TOKENS_C - 1))) * DH + sub * VEC;
             else
                 return (size_t)s * DH + sub * VEC;
         };
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(128) self_attn_warp_kernel(DecAttnArgs a) {
     const int sub = lane % LPK, grp = lane / LPK;
     const int* pt = a.page_table + (size_t)b * a.pages_per_seq;
     auto row_off = [&](int s) -> size_t {
-        return (((size_t)pt[s / a.page_tokens] * a.H + h) * a.page_tokens + (s % a.page_tokens)) * DH + sub * VEC;
+        return (((size_t)pt[s >> PAGE_SHIFT] * a.H + h) * PAGE_TOKENS_C + (s & (PAGE_TOKENS_C - 1))) * DH + sub * VEC;
     };
     if (a.k_new != nullptr) {
         if (grp == 0) {   // in-place append at slot n-1
@@ -328,7 +331,7 @@ void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
     WB_REQUIRE((a.q || a.q_parts) && a.out && a.B > 0 && a.H > 0, "bad decode attention arguments");
     const bool paged = a.k_pages != nullptr;
     WB_REQUIRE(paged || (a.k && a.v), "missing K/V");
-    WB_REQUIRE(!paged || (a.page_table && a.v_pages && a.pages_per_seq > 0 && a.page_tokens > 0), "bad paged cache");
+    WB_REQUIRE(!paged || (a.page_table && a.v_pages && a.pages_per_seq > 0 && a.page_tokens == PAGE_TOKENS_C), "bad paged cache (pages hold 64 tokens)");
     WB_REQUIRE(paged ? a.state != nullptr : a.n_keys > 0, "key count must be positive");
     if (paged && g_self_attn_warp && a.q != nullptr) {
         const int items = a.B * a.H;

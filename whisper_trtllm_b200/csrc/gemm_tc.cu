@@ -84,11 +84,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // PDL: everything above overlapped the previous kernel's tail; from here on we touch its outputs
     pdl_wait();
     pdl_trigger();
-    const bool run = (active == nullptr) || (*active != 0);   // decode loop already stopped: skip the work, keep the teardown
+    // decode loop already stopped (*active == 0): the tile is still computed but nothing is stored — the flag is only
+    // needed by the epilogue, so its load latency hides behind the main loop instead of delaying the first TMA
+    const bool run = (active == nullptr) || (*active != 0);
 
-    if (!run) {
-        // nothing
-    } else if (warp == 0) {
+    if (warp == 0) {
         // ===================== TMA producer =====================
         int stage = 0;
         uint32_t phase = 0;
@@ -181,7 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int i = 0; i < 8; ++i) {
                     const int rr = i * 4 + rrow;
                     er[i] = epi_row_near(ept, row0 + rr, g0);
-                    er[i].valid = er[i].valid && col_ok;
+                    er[i].valid = er[i].valid && col_ok && run;
                     f[i] = st4[rr * 8 + (rchunk ^ (rr & 7))];
                     rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (ept.res != nullptr && er[i].valid)

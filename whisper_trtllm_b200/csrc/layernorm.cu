@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(256) layernorm_row_kernel(float* __restrict__ 
     __shared__ float red[2][8];
     pdl_wait();
     pdl_trigger();
-    if (active != nullptr && *active == 0) return;
+    // the stop flag is only needed before the stores: its load overlaps the row loads instead of preceding them
+    const bool run = (active == nullptr) || (*active != 0);
     const int row = blockIdx.x, t = threadIdx.x, nvec = d >> 2;
     const int warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
     const bool on = t < nvec;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(256) layernorm_row_kernel(float* __restrict__ 
 #pragma unroll
             for (int p = 0; p < MAXP; ++p) { b.x += q[p].x; b.y += q[p].y; b.z += q[p].z; b.w += q[p].w; }   // fixed order
             v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-            reinterpret_cast<float4*>(x + (size_t)row * d)[t] = v;
+            if (run) reinterpret_cast<float4*>(x + (size_t)row * d)[t] = v;
         }
     }
     const float4 g = on ? reinterpret_cast<const float4*>(gamma)[t] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256) layernorm_row_kernel(float* __restrict__ 
     float tot2 = 0.f;
     for (int w = 0; w < nwarps; ++w) tot2 += red[1][w];
     const float rstd = rsqrtf(tot2 / (float)d + eps);
-    if (on) {
+    if (on && run) {
         const float y0 = a * rstd * g.x + be.x, y1 = b2 * rstd * g.y + be.y, y2 = c * rstd * g.z + be.z, y3 = e * rstd * g.w + be.w;
         TOut* o = out + (size_t)row * d + t * 4;
         if constexpr (sizeof(TOut) == 4) {
