@@ -56,8 +56,9 @@ def parse_args():
     p.add_argument("--no-graph", action="store_true", help="(dev) launch every decode kernel individually instead of replaying a CUDA graph")
     p.add_argument("--streams", type=int, default=1, help="sub-batches decoded concurrently on separate streams (per GPU)")
     p.add_argument("--bulk-attn", action="store_true", help="(dev) cp.async.bulk ring kernel for the cross attention")
-    p.add_argument("--self-attn-warp", action="store_true", help="(dev) warp-per-item paged self-attention instead of CTA-per-item")
+    p.add_argument("--self-attn-variant", type=int, default=0, help="(dev) paged self-attention kernel variant 0..4")
     p.add_argument("--attn-variant", type=int, default=0, help="(dev) cross-attention kernel variant 2..6 (threads, unroll)")
+    p.add_argument("--breakdown-only", default="", help="(dev) comma-separated kernel classes for --breakdown (default: all)")
     p.add_argument("--breakdown", action="store_true", help="(dev) per-kernel-class device time of one extra step, to stderr")
     return p.parse_args()
 
@@ -203,8 +204,8 @@ def main():
         _abi.call("wb_set_cuda_graphs", 0)
     if args.bulk_attn:
         _abi.call("wb_set_decode_attention_backend", 1)
-    if args.self_attn_warp:
-        _abi.call("wb_set_self_attention_warp_kernel", 1)
+    if args.self_attn_variant:
+        _abi.call("wb_set_self_attention_warp_kernel", args.self_attn_variant)
     if args.attn_variant:
         _abi.call("wb_set_decode_attention_backend", args.attn_variant)
     B = args.batch
@@ -286,7 +287,8 @@ def main():
     e2e_value = audio_s / (e2e_ms / 1e3)
 
     if args.breakdown and rank == 0:
-        for cls in eng.PROF_CLASSES:
+        only = [c for c in args.breakdown_only.split(",") if c]
+        for cls in (only or eng.PROF_CLASSES):
             eng.profile(cls)   # every step, eager launches
             step_device()
             ms, n = eng.profile_read()

@@ -233,3 +233,23 @@ def test_edge_cases_batch_sizes_lengths_and_errors():
     bad["model.encoder.conv2.bias"] = torch.zeros(3)
     with pytest.raises(WhisperB200Error):
         WhisperEngine(cfg, bad, dtype="float32", max_batch=1, device=DEV)
+
+
+def test_generation_settings_can_change_between_runs():
+    """wb_model_set_generation after a run (run.py builds new processor lists per utterance): the captured decode-step graph
+    holds begin_index by value and must be rebuilt; results follow the oracle with the modified config."""
+    cfg = synth.make_config("micro", max_length=24)
+    sd = synth.make_weights(cfg, seed=6)
+    mel = synth.make_mel(2, seed=3)
+    eng = WhisperEngine(cfg, sd, dtype="float32", max_batch=2, device=DEV)
+    a = eng.generate(mel.to(DEV)).cpu().long()
+    assert torch.equal(a, R.greedy(mel, sd, cfg))
+    banned = int(a[0, 2])
+    cfg2 = dict(cfg, suppress_tokens=cfg["suppress_tokens"] + [banned], forced_decoder_ids=[[1, 50362], [2, 1000]],
+                begin_suppress_tokens=[220, 50256, int(a[1, 3])])
+    from whisper_trtllm_b200 import begin_index_of
+    eng.set_generation(cfg2["suppress_tokens"], cfg2["begin_suppress_tokens"], begin_index_of(cfg2), cfg2["forced_decoder_ids"])
+    b = eng.generate(mel.to(DEV)).cpu().long()
+    want = R.greedy(mel, sd, cfg2)
+    assert torch.equal(b, want) and (b[:, 2] == 1000).all() and banned not in b[0, 3:].tolist()
+    eng.close()

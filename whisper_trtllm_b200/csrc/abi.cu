@@ -36,7 +36,7 @@ void set_gemm_tc_block_n(int bn);
 void set_cuda_graphs(bool on);
 void set_decode_attention_backend(int b);
 void set_lean_decode_gemm(bool on);
-void set_self_attention_warp_kernel(bool on);
+void set_self_attention_variant(int v);
 size_t log_mel_workspace_bytes(int chunk);
 void log_mel(const float* pcm, int B, const float* window, const float* dft_basis, const float* mel_filters, void* workspace,
              size_t workspace_bytes, float* out, cudaStream_t st);
@@ -89,9 +89,11 @@ int wb_log_mel(const float* pcm, int batch, const float* window, const float* df
     return guarded([&] { wb::log_mel(pcm, batch, window, dft_basis, mel_filters, workspace, workspace_bytes, input_features, S(stream)); });
 }
 
-int wb_set_self_attention_warp_kernel(int enabled) {
-    wb::set_self_attention_warp_kernel(enabled != 0);
-    return WB_OK;
+int wb_set_self_attention_warp_kernel(int variant) {
+    return guarded([&] {
+        WB_REQUIRE(variant >= 0 && variant <= 4, "variant must be 0..4");
+        wb::set_self_attention_variant(variant);
+    });
 }
 
 int wb_set_lean_decode_gemm(int enabled) {

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
                     st16(reinterpret_cast<T*>(a.k_pages) + off, ld16(reinterpret_cast<const T*>(a.k_new) + src));
                     st16(reinterpret_cast<T*>(a.v_pages) + off, ld16(reinterpret_cast<const T*>(a.v_new) + src));
                 }
-                __syncthreads();  // the appended row is read below by other warps of this block
+                // no barrier: this step reads row n-1 from k_new / v_new (below); the page copy is for the later steps
             }
         } else {
             const size_t o = (size_t)b * a.kv_bstride + (size_t)h * a.kv_hstride;
@@ -114,11 +114,18 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {          // all loads first: 2 * UNROLL 16-byte requests in flight per lane
                 const int s = min(s0 + u * KPB, n - 1);
-                const size_t off = row_off(s);
                 if constexpr (kPaged) {
-                    kr[u] = ld16(reinterpret_cast<const T*>(a.k_pages) + off);
-                    vr[u] = ld16(reinterpret_cast<const T*>(a.v_pages) + off);
+                    const T* kp = reinterpret_cast<const T*>(a.k_pages) + row_off(s);
+                    const T* vp = reinterpret_cast<const T*>(a.v_pages) + row_off(s);
+                    if (s == n - 1 && a.k_new != nullptr) {      // the row appended in this very step
+                        const size_t src = (size_t)b * a.new_stride + h * DH + sub * VEC;
+                        kp = reinterpret_cast<const T*>(a.k_new) + src;
+                        vp = reinterpret_cast<const T*>(a.v_new) + src;
+                    }
+                    kr[u] = ld16(kp);
+                    vr[u] = ld16(vp);
                 } else {
+                    const size_t off = row_off(s);
                     kr[u] = ld16_stream(kbase + off);
                     vr[u] = ld16_stream(vbase + off);
                 }
@@ -319,8 +326,8 @@ void decode_attention_bulk(const DecAttnArgs& a, cudaStream_t stream);
 static int g_dec_attn_backend = 0;
 // paged self-attention: one CTA per item (default) vs one warp per item.  Measured on B200 (B = 256, medium.en, whole
 // 447-step loop): CTA-per-item 4.231 s, warp-per-item 4.263 s per 256 utterances.
-static bool g_self_attn_warp = false;
-void set_self_attention_warp_kernel(bool on) { g_self_attn_warp = on; }
+static int g_self_attn_variant = 0;   // 0 CTA (128 thr, 4 deep) | 1 warp per item | 2 CTA (128, 8) | 3 CTA (64, 8) | 4 CTA (256, 4)
+void set_self_attention_variant(int v) { g_self_attn_variant = v; }
 void set_decode_attention_backend(int b) { g_dec_attn_backend = b; }
 
 void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
@@ -333,7 +340,7 @@ void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
     WB_REQUIRE(paged || (a.k && a.v), "missing K/V");
     WB_REQUIRE(!paged || (a.page_table && a.v_pages && a.pages_per_seq > 0 && a.page_tokens == PAGE_TOKENS_C), "bad paged cache (pages hold 64 tokens)");
     WB_REQUIRE(paged ? a.state != nullptr : a.n_keys > 0, "key count must be positive");
-    if (paged && g_self_attn_warp && a.q != nullptr) {
+    if (paged && g_self_attn_variant == 1 && a.q != nullptr) {
         const int items = a.B * a.H;
         if (a.dtype == F32) launch_kernel(self_attn_warp_kernel<float, 8>, dim3(ceil_div(items, 4)), dim3(128), 0, stream, true, a);
         else launch_kernel(self_attn_warp_kernel<bf16, 8>, dim3(ceil_div(items, 4)), dim3(128), 0, stream, true, a);
@@ -342,7 +349,12 @@ void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
     if (a.dtype == F32) {
         if (paged) launch<float, true, THREADS_SELF, 4>(a, stream); else launch<float, false, THREADS_CROSS, 4>(a, stream);
     } else if (paged) {
-        launch<bf16, true, THREADS_SELF, 4>(a, stream);
+        switch (g_self_attn_variant) {
+            case 2: launch<bf16, true, 128, 8>(a, stream); break;
+            case 3: launch<bf16, true, 64, 8>(a, stream); break;
+            case 4: launch<bf16, true, 256, 4>(a, stream); break;
+            default: launch<bf16, true, THREADS_SELF, 4>(a, stream); break;
+        }
     } else {
         // measured on B200 (B = 256, medium.en; us per launch): (256,4) 239.5 | (128,4) 247.1 | (256,8) 235.5 | (128,8) 232.1 |
         // (512,4) 247.8 | (256,2) 265.4  -> default 128 threads x 8-deep batches (16 requests in flight per lane)

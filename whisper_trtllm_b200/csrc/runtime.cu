@@ -219,6 +219,7 @@ void Model::set_generation(const int* suppress, int n_suppress, const int* begin
     }
     WB_CHECK_CUDA(cudaMemcpy(force_map, fm.data(), fm.size() * 4, cudaMemcpyHostToDevice));
     cfg.begin_index = begin_index;
+    ++generation_version;
 }
 
 // ------------------------------------------------------------------------------------------------ Session
@@ -606,13 +607,14 @@ void Session::build_step_graph(cudaStream_t st) {
     cudaGraphDestroy(graph);
     WB_CHECK_CUDA(e);
     step_graph_batch = batch;
+    step_graph_generation = m->generation_version;
 }
 
 // one decode step on the session's loop stream: CUDA-graph replay when possible, eager launches otherwise
 void Session::enqueue_step() {
     cudaStream_t st = loop_stream;
     if (graph_ok()) {
-        if (step_graph == nullptr || step_graph_batch != batch) {
+        if (step_graph == nullptr || step_graph_batch != batch || step_graph_generation != m->generation_version) {
             try {
                 build_step_graph(st);
             } catch (const Error&) {
@@ -621,7 +623,7 @@ void Session::enqueue_step() {
             }
         }
     }
-    if (graph_ok() && step_graph != nullptr && step_graph_batch == batch) {
+    if (graph_ok() && step_graph != nullptr && step_graph_batch == batch && step_graph_generation == m->generation_version) {
         WB_CHECK_CUDA(cudaGraphLaunch(step_graph, st));
         launch_counter().fetch_add(step_graph_launches, std::memory_order_relaxed);
         ++steps_enqueued;

@@ -55,6 +55,7 @@ struct Model {
     std::vector<void*> allocs;
     size_t weight_bytes = 0;
     long long loaded = 0;
+    int generation_version = 0;   // bumped by set_generation: captured decode-step graphs hold begin_index by value
 
     Model(const ModelConfig& c, int dt);
     ~Model();
@@ -99,6 +100,7 @@ struct Session : Buffers {
     cudaEvent_t fence_event = nullptr;
     cudaGraphExec_t step_graph = nullptr;
     int step_graph_batch = 0;
+    int step_graph_generation = -1;
     long long step_graph_launches = 0;
     bool step_warm = false;           // one eager step has run (one-time kernel attribute setup done)
     bool graph_ok() const;
