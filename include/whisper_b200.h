@@ -63,8 +63,8 @@ WB_API int wb_bandwidth_probe(const void* buf, size_t bytes, int mode, int ctas_
 /* cross-attention kernel of the decode step: 0 = 16-byte L1-bypassing loads, 4 CTAs/SM (default); 1 = cp.async.bulk into a
  * 128 KB shared-memory ring, one CTA/SM (bf16 only).  Existing CUDA graphs keep the kernel they were captured with. */
 WB_API int wb_set_decode_attention_backend(int backend);
-/* paged self-attention kernel: 0 = one CTA (128 threads, 4-deep batches) per (utterance, head) item (default), 1 = one warp per
- * item, 2..4 = tuning variants of the CTA kernel (threads, depth) = (128, 8) (64, 8) (256, 4) */
+/* paged self-attention kernel: 0 = one warp per (utterance, head) item (default, measured fastest), 1..4 = one CTA per item with
+ * (threads, batch depth) = (128, 4) (128, 8) (64, 8) (256, 4), 5..6 = warp-kernel tuning variants */
 WB_API int wb_set_self_attention_warp_kernel(int variant);
 /* skinny (decode-step) GEMMs use the variant sized to co-reside with the bulk-ring cross-attention CTA of a concurrent stream
  * (256 threads, <= 128 registers, <= 90 KB shared memory); set together with wb_decode_run_multi.  Default 0. */

@@ -91,7 +91,7 @@ int wb_log_mel(const float* pcm, int batch, const float* window, const float* df
 
 int wb_set_self_attention_warp_kernel(int variant) {
     return guarded([&] {
-        WB_REQUIRE(variant >= 0 && variant <= 4, "variant must be 0..4");
+        WB_REQUIRE(variant >= 0 && variant <= 6, "variant must be 0..6");
         wb::set_self_attention_variant(variant);
     });
 }

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
 // trips -> smem merge -> barrier): 55 us at length 224 where the bytes need 36 us.  Here every warp owns an item, keeps
 // 2 * UNROLL 16-byte loads in flight per lane, merges its four 8-lane groups with shuffles and never touches shared
 // memory or a block barrier; all 4096 items of a launch are resident at once.
-template <typename T, int UNROLL>
+template <typename T, int UNROLL, bool kForceBatch>
 __global__ void __launch_bounds__(128) self_attn_warp_kernel(DecAttnArgs a) {
     constexpr int VEC = Vec16<T>::N, LPK = DH / VEC, KPW = 32 / LPK;
     pdl_wait();
@@ -219,13 +219,17 @@ __global__ void __launch_bounds__(128) self_attn_warp_kernel(DecAttnArgs a) {
     const int b = item / a.H, h = item - b * a.H;
     if (a.row_active != nullptr && a.row_active[b] == 0) return;   // finished utterance
     const int sub = lane % LPK, grp = lane / LPK;
+    // the item's page ids live in the warp's registers (lane i holds page i; <= 7 pages for 448 tokens): every row address
+    // costs a shuffle instead of a dependent global load in front of each batch of K/V requests
     const int* pt = a.page_table + (size_t)b * a.pages_per_seq;
+    const int my_page = lane < a.pages_per_seq ? pt[lane] : 0;
     auto row_off = [&](int s) -> size_t {
-        return (((size_t)pt[s >> PAGE_SHIFT] * a.H + h) * PAGE_TOKENS_C + (s & (PAGE_TOKENS_C - 1))) * DH + sub * VEC;
+        const int page = __shfl_sync(0xffffffffu, my_page, s >> PAGE_SHIFT);
+        return (((size_t)page * a.H + h) * PAGE_TOKENS_C + (s & (PAGE_TOKENS_C - 1))) * DH + sub * VEC;
     };
     if (a.k_new != nullptr) {
+        const size_t off = row_off(n - 1);   // all lanes: row_off shuffles
         if (grp == 0) {   // in-place append at slot n-1
-            const size_t off = row_off(n - 1);
             const size_t src = (size_t)b * a.new_stride + h * DH + sub * VEC;
             st16(reinterpret_cast<T*>(a.k_pages) + off, ld16(reinterpret_cast<const T*>(a.k_new) + src));
             st16(reinterpret_cast<T*>(a.v_pages) + off, ld16(reinterpret_cast<const T*>(a.v_new) + src));
@@ -246,6 +250,16 @@ __global__ void __launch_bounds__(128) self_attn_warp_kernel(DecAttnArgs a) {
             const size_t off = row_off(min(s0 + u * KPW, n - 1));
             kr[u] = ld16_issue(reinterpret_cast<const T*>(a.k_pages) + off);
             vr[u] = ld16_issue(reinterpret_cast<const T*>(a.v_pages) + off);
+        }
+        if constexpr (kForceBatch) {
+            // every load of the batch must have been ISSUED before the first value is consumed (ptxas otherwise sinks the
+            // later loads behind the first dot products to save registers, which halves the requests in flight)
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                uint32_t* kw = reinterpret_cast<uint32_t*>(&kr[u].raw);
+                uint32_t* vw = reinterpret_cast<uint32_t*>(&vr[u].raw);
+                asm volatile("" : "+r"(kw[0]), "+r"(kw[1]), "+r"(kw[2]), "+r"(kw[3]), "+r"(vw[0]), "+r"(vw[1]), "+r"(vw[2]), "+r"(vw[3]));
+            }
         }
         float sc[UNROLL];
         float mb = -INFINITY;
@@ -326,7 +340,10 @@ void decode_attention_bulk(const DecAttnArgs& a, cudaStream_t stream);
 static int g_dec_attn_backend = 0;
 // paged self-attention: one CTA per item (default) vs one warp per item.  Measured on B200 (B = 256, medium.en, whole
 // 447-step loop): CTA-per-item 4.231 s, warp-per-item 4.263 s per 256 utterances.
-static int g_self_attn_variant = 0;   // 0 CTA (128 thr, 4 deep) | 1 warp per item | 2 CTA (128, 8) | 3 CTA (64, 8) | 4 CTA (256, 4)
+// paged self-attention variants, us per launch averaged over the 447 steps (B = 256, medium.en, one B200 run):
+//   0 warp per item, 8 deep 49.8 (default) | 1 CTA (128 threads, 4 deep) 55.7 | 2 CTA (128, 8) 59.3 | 3 CTA (64, 8) 53.4 |
+//   4 CTA (256, 4) 70.2 | 5 warp, 8 deep, loads forced into one batch | 6 warp, 4 deep
+static int g_self_attn_variant = 0;
 void set_self_attention_variant(int v) { g_self_attn_variant = v; }
 void set_decode_attention_backend(int b) { g_dec_attn_backend = b; }
 
@@ -338,12 +355,16 @@ void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
     WB_REQUIRE((a.q || a.q_parts) && a.out && a.B > 0 && a.H > 0, "bad decode attention arguments");
     const bool paged = a.k_pages != nullptr;
     WB_REQUIRE(paged || (a.k && a.v), "missing K/V");
-    WB_REQUIRE(!paged || (a.page_table && a.v_pages && a.pages_per_seq > 0 && a.page_tokens == PAGE_TOKENS_C), "bad paged cache (pages hold 64 tokens)");
+    WB_REQUIRE(!paged || (a.page_table && a.v_pages && a.pages_per_seq > 0 && a.pages_per_seq <= 32 && a.page_tokens == PAGE_TOKENS_C),
+               "bad paged cache (pages hold 64 tokens, at most 32 pages per sequence)");
     WB_REQUIRE(paged ? a.state != nullptr : a.n_keys > 0, "key count must be positive");
-    if (paged && g_self_attn_variant == 1 && a.q != nullptr) {
-        const int items = a.B * a.H;
-        if (a.dtype == F32) launch_kernel(self_attn_warp_kernel<float, 8>, dim3(ceil_div(items, 4)), dim3(128), 0, stream, true, a);
-        else launch_kernel(self_attn_warp_kernel<bf16, 8>, dim3(ceil_div(items, 4)), dim3(128), 0, stream, true, a);
+    const bool warp_variant = g_self_attn_variant == 0 || g_self_attn_variant == 5 || g_self_attn_variant == 6;
+    if (paged && warp_variant && a.q != nullptr) {
+        const dim3 grid(ceil_div(a.B * a.H, 4)), block(128);
+        if (a.dtype == F32) launch_kernel(self_attn_warp_kernel<float, 8, false>, grid, block, 0, stream, true, a);
+        else if (g_self_attn_variant == 5) launch_kernel(self_attn_warp_kernel<bf16, 8, true>, grid, block, 0, stream, true, a);
+        else if (g_self_attn_variant == 6) launch_kernel(self_attn_warp_kernel<bf16, 4, false>, grid, block, 0, stream, true, a);
+        else launch_kernel(self_attn_warp_kernel<bf16, 8, false>, grid, block, 0, stream, true, a);
         return;
     }
     if (a.dtype == F32) {
