@@ -341,8 +341,8 @@ static int g_dec_attn_backend = 0;
 // paged self-attention: one CTA per item (default) vs one warp per item.  Measured on B200 (B = 256, medium.en, whole
 // 447-step loop): CTA-per-item 4.231 s, warp-per-item 4.263 s per 256 utterances.
 // paged self-attention variants, us per launch averaged over the 447 steps (B = 256, medium.en, one B200 run):
-//   0 warp per item, 8 deep 49.8 (default) | 1 CTA (128 threads, 4 deep) 55.7 | 2 CTA (128, 8) 59.3 | 3 CTA (64, 8) 53.4 |
-//   4 CTA (256, 4) 70.2 | 5 warp, 8 deep, loads forced into one batch | 6 warp, 4 deep
+//   0 warp per item, 4 deep 48.5 (default) | 1 CTA (128 threads, 4 deep) 55.7 | 2 CTA (128, 8) 59.3 | 3 CTA (64, 8) 53.4 |
+//   4 CTA (256, 4) 70.2 | 5 warp, 8 deep, loads forced into one batch 53.1 | 6 warp, 8 deep 52.9
 static int g_self_attn_variant = 0;
 void set_self_attention_variant(int v) { g_self_attn_variant = v; }
 void set_decode_attention_backend(int b) { g_dec_attn_backend = b; }
@@ -363,8 +363,8 @@ void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
         const dim3 grid(ceil_div(a.B * a.H, 4)), block(128);
         if (a.dtype == F32) launch_kernel(self_attn_warp_kernel<float, 8, false>, grid, block, 0, stream, true, a);
         else if (g_self_attn_variant == 5) launch_kernel(self_attn_warp_kernel<bf16, 8, true>, grid, block, 0, stream, true, a);
-        else if (g_self_attn_variant == 6) launch_kernel(self_attn_warp_kernel<bf16, 4, false>, grid, block, 0, stream, true, a);
-        else launch_kernel(self_attn_warp_kernel<bf16, 8, false>, grid, block, 0, stream, true, a);
+        else if (g_self_attn_variant == 6) launch_kernel(self_attn_warp_kernel<bf16, 8, false>, grid, block, 0, stream, true, a);
+        else launch_kernel(self_attn_warp_kernel<bf16, 4, false>, grid, block, 0, stream, true, a);
         return;
     }
     if (a.dtype == F32) {
