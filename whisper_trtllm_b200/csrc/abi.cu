@@ -72,7 +72,7 @@ int wb_bandwidth_probe(const void* buf, size_t bytes, int mode, int ctas_per_sm,
 
 int wb_set_decode_attention_backend(int backend) {
     return guarded([&] {
-        WB_REQUIRE(backend >= 0 && backend <= 9, "backend must be 0 (16-byte loads), 1 (cp.async.bulk ring) or a tuning variant 2..9");
+        WB_REQUIRE(backend >= 0 && backend <= 12, "backend must be 0 (16-byte loads), 1 (cp.async.bulk ring) or a tuning variant 2..12");
         wb::set_decode_attention_backend(backend);
     });
 }

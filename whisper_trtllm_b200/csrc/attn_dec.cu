@@ -32,7 +32,7 @@ template <typename T> __device__ __forceinline__ float softmax_exp(float x);
 template <> __device__ __forceinline__ float softmax_exp<float>(float x) { return expf(x); }      // exactness path
 template <> __device__ __forceinline__ float softmax_exp<bf16>(float x) { return __expf(x); }     // speed path
 
-template <typename T, bool kPaged, int THREADS, int UNROLL>
+template <typename T, bool kPaged, int THREADS, int UNROLL, bool kPipe = false>
 __global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
     constexpr int WARPS = THREADS / 32;
     constexpr int VEC = Vec16<T>::N;       // elements per 16-byte load: 8 (bf16) / 4 (fp32)
@@ -107,12 +107,11 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
 
-        // warp-uniform trip count (the shuffles below need all 32 lanes): groups whose rows fall past n are masked
-        for (int sb = warp * KPW; sb < n; sb += KPB * UNROLL) {
+        // one batch = UNROLL rows per lane group: all of its 2 * UNROLL 16-byte requests are issued before the first use
+        auto issue = [&](int sb, Vec16<T>* kr, Vec16<T>* vr) {
             const int s0 = sb + grp;
-            Vec16<T> kr[UNROLL], vr[UNROLL];
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {          // all loads first: 2 * UNROLL 16-byte requests in flight per lane
+            for (int u = 0; u < UNROLL; ++u) {
                 const int s = min(s0 + u * KPB, n - 1);
                 if constexpr (kPaged) {
                     const T* kp = reinterpret_cast<const T*>(a.k_pages) + row_off(s);
@@ -130,6 +129,9 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
                     vr[u] = ld16_stream(vbase + off);
                 }
             }
+        };
+        auto consume = [&](int sb, const Vec16<T>* kr, const Vec16<T>* vr) {
+            const int s0 = sb + grp;
             float sc[UNROLL];
             float mb = -INFINITY;
 #pragma unroll
@@ -160,6 +162,30 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
                 for (int i = 0; i < VEC; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
             }
             m_run = m_new;
+        };
+        // warp-uniform trip counts (the shuffles need all 32 lanes): groups whose rows fall past n are masked
+        constexpr int STEP = KPB * UNROLL;
+        if constexpr (kPipe) {
+            // software pipeline: the requests of batch i+1 are in flight while batch i is reduced (two register buffers)
+            Vec16<T> ka[UNROLL], va[UNROLL], kb2[UNROLL], vb2[UNROLL];
+            int sb = warp * KPW;
+            if (sb < n) issue(sb, ka, va);
+            while (sb < n) {
+                const int sb1 = sb + STEP;
+                if (sb1 < n) issue(sb1, kb2, vb2);
+                consume(sb, ka, va);
+                if (sb1 >= n) break;
+                const int sb2 = sb1 + STEP;
+                if (sb2 < n) issue(sb2, ka, va);
+                consume(sb1, kb2, vb2);
+                sb = sb2;
+            }
+        } else {
+            for (int sb = warp * KPW; sb < n; sb += STEP) {
+                Vec16<T> kr[UNROLL], vr[UNROLL];
+                issue(sb, kr, vr);
+                consume(sb, kr, vr);
+            }
         }
 
         // ---- merge the key groups of the warp (lanes with equal sub), then the warps
@@ -317,19 +343,19 @@ __global__ void __launch_bounds__(128) self_attn_warp_kernel(DecAttnArgs a) {
     }
 }
 
-template <typename T, bool kPaged, int THREADS, int UNROLL>
+template <typename T, bool kPaged, int THREADS, int UNROLL, bool kPipe = false>
 void launch(const DecAttnArgs& a, cudaStream_t stream) {
     static int blocks_per_sm = 0, sms = 0;
     if (blocks_per_sm == 0) {
         int dev = 0;
         WB_CHECK_CUDA(cudaGetDevice(&dev));
         WB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        WB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, decode_attn_kernel<T, kPaged, THREADS, UNROLL>, THREADS, 0));
+        WB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, decode_attn_kernel<T, kPaged, THREADS, UNROLL, kPipe>, THREADS, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     const int items = a.B * a.H;
     const int grid = std::min(items, sms * blocks_per_sm);
-    launch_kernel(decode_attn_kernel<T, kPaged, THREADS, UNROLL>, dim3(grid), dim3(THREADS), 0, stream, true, a);
+    launch_kernel(decode_attn_kernel<T, kPaged, THREADS, UNROLL, kPipe>, dim3(grid), dim3(THREADS), 0, stream, true, a);
 }
 }  // namespace
 
@@ -388,6 +414,9 @@ void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
             case 7: launch<bf16, false, 128, 12>(a, stream); break;
             case 8: launch<bf16, false, 64, 8>(a, stream); break;
             case 9: launch<bf16, false, 192, 8>(a, stream); break;
+            case 10: launch<bf16, false, 128, 4, true>(a, stream); break;    // software-pipelined variants
+            case 11: launch<bf16, false, 128, 8, true>(a, stream); break;
+            case 12: launch<bf16, false, 256, 4, true>(a, stream); break;
             default: launch<bf16, false, 128, 8>(a, stream); break;
         }
     }
