@@ -195,7 +195,7 @@ def main():
     if args.warmup < 3 and not os.environ.get("WB_BENCH_DEV"):
         args.warmup = 3  # timing rules: at least 3 warm-up steps
 
-    from oracle import synth  # synthetic weights / inputs only (seeded, bit-reproducible)
+    from whisper_trtllm_b200 import synthetic as synth  # seeded synthetic weights / inputs (bit-reproducible)
     from whisper_trtllm_b200 import WhisperEngine
 
     from whisper_trtllm_b200 import _abi

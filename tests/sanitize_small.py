@@ -8,7 +8,7 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in tests/: it uses the oracle as the checker)
 sys.path.insert(0, ROOT)
 from oracle import logmel_ref as LM  # noqa: E402
 from oracle import synth, whisper_ref as R  # noqa: E402

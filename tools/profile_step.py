@@ -37,8 +37,7 @@ def main():
     p.add_argument("--steps", type=int, default=2)
     a = p.parse_args()
 
-    from oracle import synth
-    from whisper_trtllm_b200 import WhisperEngine
+    from whisper_trtllm_b200 import WhisperEngine, synthetic as synth
 
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
