@@ -69,6 +69,8 @@ WB_API int wb_set_self_attention_warp_kernel(int variant);
 /* skinny (decode-step) GEMMs use the variant sized to co-reside with the bulk-ring cross-attention CTA of a concurrent stream
  * (256 threads, <= 128 registers, <= 90 KB shared memory); set together with wb_decode_run_multi.  Default 0. */
 WB_API int wb_set_lean_decode_gemm(int enabled);
+/* tuning hook: force the tcgen05 GEMM's tile width (0 = automatic choice, see pick_config in csrc/gemm_tc.cu) */
+WB_API int wb_set_gemm_block_n(int block_n);
 /* wb_decode_run replays the decode step as a CUDA graph (default 1 = on); 0 = one launch per kernel.  Existing graphs are kept. */
 WB_API int wb_set_cuda_graphs(int enabled);
 /* number of kernels this library launched so far on this thread's device (bench `gpu_launches`) */

@@ -101,6 +101,13 @@ int wb_set_lean_decode_gemm(int enabled) {
     return WB_OK;
 }
 
+int wb_set_gemm_block_n(int block_n) {
+    return guarded([&] {
+        WB_REQUIRE(block_n == 0 || block_n == 32 || block_n == 64 || block_n == 128 || block_n == 256, "block_n must be 0 (auto), 32, 64, 128 or 256");
+        wb::set_gemm_tc_block_n(block_n);
+    });
+}
+
 int wb_set_cuda_graphs(int enabled) {
     wb::set_cuda_graphs(enabled != 0);
     return WB_OK;
