@@ -162,14 +162,8 @@ class WhisperEngine:
         return max(self._final_lens)
 
     def _view(self, address: int, shape, dtype) -> torch.Tensor:
-        """Zero-copy torch view of session-owned device memory (lives inside self.workspace)."""
-        off = address - self.workspace.data_ptr()
-        n = 1
-        for s in shape:
-            n *= s
-        nbytes = n * torch.empty((), dtype=dtype).element_size()
-        assert 0 <= off and off + nbytes <= self.workspace.numel()
-        return self.workspace[off:off + nbytes].view(dtype).view(*shape)
+        """Zero-copy torch view of session-owned device memory (lives inside sub-session 0's workspace)."""
+        return self._view_of(self.workspace, address, shape, dtype)
 
     def _view_of(self, ws: torch.Tensor, address: int, shape, dtype) -> torch.Tensor:
         off = address - ws.data_ptr()
