@@ -293,6 +293,17 @@ def main():
     value = audio_s / (dev_ms / 1e3)
     e2e_value = audio_s / (e2e_ms / 1e3)
 
+    # phases of one extra identical pass (not part of the timed regions): encoder + cross-K/V projection vs greedy loop
+    pe = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    sync_all()
+    pe[0].record()
+    eng.encode(mel_dev, return_hidden=False)
+    pe[1].record()
+    eng.greedy(B)
+    pe[2].record()
+    torch.cuda.synchronize()
+    enc_ms, dec_ms = pe[0].elapsed_time(pe[1]), pe[1].elapsed_time(pe[2])
+
     if args.breakdown and rank == 0:
         only = [c for c in args.breakdown_only.split(",") if c]
         for cls in (only or eng.PROF_CLASSES):
@@ -335,6 +346,9 @@ def main():
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": mel_host.numel() * 4,
                     "d2h_bytes_per_step": B * args.max_length * 4, "ms_per_step": round(e2e_ms / args.steps, 2)},
             "gpu_launches": int(launches), "streams_per_gpu": eng.n_streams,
+            "phases": {"encoder_ms": round(enc_ms, 1), "decode_ms": round(dec_ms, 1),
+                       "decode_step_us": round(dec_ms / (args.max_length - 1) * 1e3, 1),
+                       "note": "one extra identical pass after the timed regions, rank 0"},
             "clocks": clocks,
             "roofline": roofline,
         }
