@@ -253,3 +253,22 @@ def test_generation_settings_can_change_between_runs():
     want = R.greedy(mel, sd, cfg2)
     assert torch.equal(b, want) and (b[:, 2] == 1000).all() and banned not in b[0, 3:].tolist()
     eng.close()
+
+
+@pytest.mark.parametrize("dtype,tol", [("float32", 1e-4), ("bfloat16", 2e-2)])
+def test_encoder_stem_matches_oracle(dtype, tol):
+    """SURVEY §8 row a1 on its own: gelu(conv1) -> gelu(conv2, stride 2) -> transpose -> + positions (modeling_whisper.py:992-997)
+    through wb_encoder_stem (im2col + two GEMMs with GELU / positional-add epilogues), ragged batch (3 of max 4)."""
+    from whisper_trtllm_b200 import _abi
+    from whisper_trtllm_b200._abi import ptr, stream_handle
+    cfg = synth.make_config("tiny.en")
+    sd = synth.make_weights(cfg, seed=2)
+    mel = synth.make_mel(3, seed=5)
+    ref = R.encoder_stem(mel, sd)
+    eng = WhisperEngine(cfg, sd, dtype=dtype, max_batch=4, enc_chunk=4, device=DEV)
+    x = torch.full((3, 1500, cfg["d_model"]), float("nan"), device=DEV)
+    _abi.call("wb_encoder_stem", eng._session, ptr(mel.to(DEV)), 3, ptr(x), stream_handle())
+    torch.cuda.synchronize()
+    assert torch.isfinite(x).all()
+    assert _rel(x, ref) < tol
+    eng.close()
