@@ -237,18 +237,28 @@ __global__ void __launch_bounds__(128) self_attn_warp_kernel(DecAttnArgs a) {
     constexpr int VEC = Vec16<T>::N, LPK = DH / VEC, KPW = 32 / LPK;
     pdl_wait();
     pdl_trigger();
-    if (a.state->active == 0) return;
-    const int n = a.state->cur_len;
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (item >= a.B * a.H) return;                       // whole warp
     const int b = item / a.H, h = item - b * a.H;
-    if (a.row_active != nullptr && a.row_active[b] == 0) return;   // finished utterance
     const int sub = lane % LPK, grp = lane / LPK;
+    // everything the item needs before its first K/V request is loaded in ONE round trip (independent loads, then the
+    // early-outs): loop state, the row's unfinished flag, its page ids, q and the new k/v row
+    const int* pt = a.page_table + (size_t)b * a.pages_per_seq;
+    const int active = a.state->active;
+    const int n = a.state->cur_len;
+    const int row_on = a.row_active != nullptr ? a.row_active[b] : 1;
     // the item's page ids live in the warp's registers (lane i holds page i; <= 7 pages for 448 tokens): every row address
     // costs a shuffle instead of a dependent global load in front of each batch of K/V requests
-    const int* pt = a.page_table + (size_t)b * a.pages_per_seq;
     const int my_page = lane < a.pages_per_seq ? pt[lane] : 0;
+    const Vec16<T> q_raw = ld16(reinterpret_cast<const T*>(a.q) + (size_t)b * a.q_stride + h * DH + sub * VEC);
+    Vec16<T> k_app, v_app;
+    if (a.k_new != nullptr && grp == 0) {
+        const size_t src = (size_t)b * a.new_stride + h * DH + sub * VEC;
+        k_app = ld16(reinterpret_cast<const T*>(a.k_new) + src);
+        v_app = ld16(reinterpret_cast<const T*>(a.v_new) + src);
+    }
+    if (active == 0 || row_on == 0) return;              // loop stopped / finished utterance (warp-uniform)
     auto row_off = [&](int s) -> size_t {
         const int page = __shfl_sync(0xffffffffu, my_page, s >> PAGE_SHIFT);
         return (((size_t)page * a.H + h) * PAGE_TOKENS_C + (s & (PAGE_TOKENS_C - 1))) * DH + sub * VEC;
@@ -256,14 +266,13 @@ __global__ void __launch_bounds__(128) self_attn_warp_kernel(DecAttnArgs a) {
     if (a.k_new != nullptr) {
         const size_t off = row_off(n - 1);   // all lanes: row_off shuffles
         if (grp == 0) {   // in-place append at slot n-1
-            const size_t src = (size_t)b * a.new_stride + h * DH + sub * VEC;
-            st16(reinterpret_cast<T*>(a.k_pages) + off, ld16(reinterpret_cast<const T*>(a.k_new) + src));
-            st16(reinterpret_cast<T*>(a.v_pages) + off, ld16(reinterpret_cast<const T*>(a.v_new) + src));
+            st16(reinterpret_cast<T*>(a.k_pages) + off, k_app);
+            st16(reinterpret_cast<T*>(a.v_pages) + off, v_app);
         }
         __syncwarp();     // the appended row is read below by the other lane groups of this warp
     }
     float qf[VEC];
-    ld16(reinterpret_cast<const T*>(a.q) + (size_t)b * a.q_stride + h * DH + sub * VEC).unpack(qf);
+    q_raw.unpack(qf);
     float m_run = -INFINITY, l_run = 0.f;
     float acc[VEC];
 #pragma unroll
