@@ -272,3 +272,36 @@ def test_encoder_stem_matches_oracle(dtype, tol):
     assert torch.isfinite(x).all()
     assert _rel(x, ref) < tol
     eng.close()
+
+
+def test_small_and_large_batch_decode_paths_agree():
+    """bf16 decode has two paths: B <= 16 -> weight-streaming GEMV kernels with fused LayerNorm (csrc/gemv.cu), otherwise
+    tcgen05 GEMMs with split-K / deferred reduction.  Both must match the fp32 oracle's teacher-forced logits within the
+    stated bf16 tolerance, and each other far more tightly (same rounding points, different summation order)."""
+    from whisper_trtllm_b200 import _abi
+    cfg = synth.make_config("tiny.en", max_length=20)
+    sd = synth.make_weights(cfg, seed=8)
+    mel = synth.make_mel(20, seed=13)
+    ref_ids, _, ref_logits = R.greedy(mel, sd, cfg, return_logits=True)
+    steps = ref_ids.shape[1] - 1
+    try:
+        # large path at B = 20 (> 16)
+        eng = WhisperEngine(cfg, sd, dtype="bfloat16", max_batch=20, device=DEV)
+        _, lg20 = eng.generate(mel.to(DEV), forced_tokens=ref_ids, dump_logits_steps=steps)
+        for s in (0, 1, 5, steps - 1):
+            assert _rel(lg20[s], ref_logits[s]) < BF16_LOGIT_TOL, s
+        # the same 6 rows through the small path and, with the switch off, through the large path
+        outs = {}
+        for flag in (1, 0):
+            _abi.call("wb_set_small_batch_path", flag)
+            e = WhisperEngine(cfg, sd, dtype="bfloat16", max_batch=6, device=DEV)
+            _, lg = e.generate(mel[:6].to(DEV), forced_tokens=ref_ids[:6], dump_logits_steps=steps)
+            outs[flag] = lg.clone()
+            e.close()
+        for s in (0, 1, 5, steps - 1):
+            assert _rel(outs[1][s], ref_logits[s][:6]) < BF16_LOGIT_TOL, s
+            assert _rel(outs[1][s], outs[0][s]) < 1e-2, s
+            assert _rel(outs[0][s], lg20[s][:6]) < 1e-2, s
+        eng.close()
+    finally:
+        _abi.call("wb_set_small_batch_path", 1)

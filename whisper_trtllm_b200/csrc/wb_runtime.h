@@ -127,6 +127,8 @@ struct Session : Buffers {
     void set_encoder_output(const void* enc_states, int dtype, int B, cudaStream_t s);  // external encoder states
     void decode_begin(int B, cudaStream_t s);
     void decode_step(cudaStream_t s);
+    void decode_step_large(cudaStream_t s);   // tcgen05 / CUDA-core GEMMs, split-K with deferred reduction (any batch)
+    void decode_step_small(cudaStream_t s);   // B <= 16, bf16: weight-streaming GEMV kernels with fused LayerNorm
     int decode_run(int max_steps, int check_every, cudaStream_t s);  // returns final length (syncs)
     void enqueue_step();                                             // one step on loop_stream (graph replay or eager)
     size_t cross_layer_elems() const;
