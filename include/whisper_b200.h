@@ -66,9 +66,10 @@ WB_API int wb_set_decode_attention_backend(int backend);
 /* paged self-attention kernel: 0 = one warp per (utterance, head) item (default, measured fastest), 1..4 = one CTA per item with
  * (threads, batch depth) = (128, 4) (128, 8) (64, 8) (256, 4), 5..6 = warp-kernel tuning variants */
 WB_API int wb_set_self_attention_warp_kernel(int variant);
-/* decode steps of <= 16 utterances (bf16) use weight-streaming GEMV kernels with the LayerNorm fused in front, 8 launches per
- * layer instead of 11 (csrc/gemv.cu); default 1 = on.  Captured CUDA graphs keep the path they were captured with. */
-WB_API int wb_set_small_batch_path(int enabled);
+/* decode steps of <= 16 utterances (bf16): 2 (default) = ONE persistent cooperative kernel per token, phases separated by grid
+ * barriers (csrc/step_mega.cu); 1 = weight-streaming GEMV kernels with the LayerNorm fused in front, 8 launches per layer
+ * (csrc/gemv.cu); 0 = the large-batch kernels.  Captured CUDA graphs keep the path they were captured with. */
+WB_API int wb_set_small_batch_path(int mode);
 /* skinny (decode-step) GEMMs use the variant sized to co-reside with the bulk-ring cross-attention CTA of a concurrent stream
  * (256 threads, <= 128 registers, <= 90 KB shared memory); set together with wb_decode_run_multi.  Default 0. */
 WB_API int wb_set_lean_decode_gemm(int enabled);

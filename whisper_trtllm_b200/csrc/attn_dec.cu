@@ -368,6 +368,16 @@ void launch(const DecAttnArgs& a, cudaStream_t stream) {
 }
 }  // namespace
 
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        WB_CHECK_CUDA(cudaGetDevice(&dev));
+        WB_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    }
+    return n;
+}
+
 bool decode_attention_bulk_supported(const DecAttnArgs& a);                 // attn_dec_bulk.cu
 void decode_attention_bulk(const DecAttnArgs& a, cudaStream_t stream);
 // 0 = 16-byte load kernel (256 threads, 4 x 2 loads in flight per lane), 1 = cp.async.bulk ring kernel for cross attention,
@@ -393,6 +403,13 @@ void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
     WB_REQUIRE(!paged || (a.page_table && a.v_pages && a.pages_per_seq > 0 && a.pages_per_seq <= 32 && a.page_tokens == PAGE_TOKENS_C),
                "bad paged cache (pages hold 64 tokens, at most 32 pages per sequence)");
     WB_REQUIRE(paged ? a.state != nullptr : a.n_keys > 0, "key count must be positive");
+    // few items (small batch): one warp per item would leave most SMs idle and serialise a whole sequence behind one warp's
+    // round trips -> give every item a 256-thread CTA instead
+    const bool few_items = a.B * a.H <= 2 * num_sms();
+    if (paged && few_items && a.dtype == BF16 && g_self_attn_variant == 0) {
+        launch<bf16, true, 256, 4>(a, stream);
+        return;
+    }
     const bool warp_variant = g_self_attn_variant == 0 || g_self_attn_variant == 5 || g_self_attn_variant == 6;
     if (paged && warp_variant && a.q != nullptr) {
         const dim3 grid(ceil_div(a.B * a.H, 4)), block(128);
@@ -426,7 +443,12 @@ void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
             case 10: launch<bf16, false, 128, 4, true>(a, stream); break;    // software-pipelined variants
             case 11: launch<bf16, false, 128, 8, true>(a, stream); break;
             case 12: launch<bf16, false, 256, 4, true>(a, stream); break;
-            default: launch<bf16, false, 128, 8>(a, stream); break;
+            default:
+                // few items (small batch): 512 threads per item so that one CTA keeps 128 KB of requests in flight
+                if (a.B * a.H <= num_sms()) launch<bf16, false, 512, 8>(a, stream);
+                else if (few_items) launch<bf16, false, 256, 8>(a, stream);
+                else launch<bf16, false, 128, 8>(a, stream);
+                break;
         }
     }
 }

@@ -265,6 +265,8 @@ size_t layout(Buffers& b, const Model* m, int max_batch, int enc_chunk, void* ba
     c.take(b.tokens, B * g.max_tgt * 4);
     c.take(b.unfinished, B * 4);
     c.take(b.state, sizeof(StepState));
+    c.take(b.mega_part, mega_part_bytes(max_batch, g.n_heads));
+    c.take(b.mega_sync, mega_sync_bytes(max_batch, g.n_heads));
     return c.off + 1024;
 }
 }  // namespace
@@ -292,6 +294,7 @@ Session::Session(Model* model, int mb, int ec, void* workspace, size_t workspace
     WB_CHECK_CUDA(cudaMemcpy(page_table, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice));
     WB_CHECK_CUDA(cudaMemset(h1p, 0, ((size_t)ec * H1_ROWS + 8) * model->cfg.d_model * dtype_size(model->dtype)));
     WB_CHECK_CUDA(cudaMemset(state, 0, sizeof(StepState)));
+    WB_CHECK_CUDA(cudaMemset(mega_sync, 0, mega_sync_bytes(mb, model->cfg.n_heads)));
     WB_CHECK_CUDA(cudaMallocHost(&host_state, sizeof(StepState)));
     std::memset(host_state, 0, sizeof(StepState));
     WB_CHECK_CUDA(cudaEventCreateWithFlags(&check_event, cudaEventDisableTiming));
@@ -477,11 +480,12 @@ void Session::decode_begin(int B, cudaStream_t st) {
     greedy_init(tokens, g.max_tgt, unfinished, state, B, g.sot, g.pad, g.max_tgt, st);
 }
 
-static bool& small_batch_path_enabled() {
-    static bool on = true;
-    return on;
+// 0 = always the large-batch kernels, 1 = GEMV kernels (8 launches per layer), 2 = one persistent kernel per token (default)
+static int& small_batch_mode() {
+    static int mode = 2;
+    return mode;
 }
-void set_small_batch_path(bool on) { small_batch_path_enabled() = on; }
+void set_small_batch_path(int mode) { small_batch_mode() = mode; }
 
 // B <= 16 (bf16): weight-streaming GEMV kernels with the LayerNorm fused in front, 8 launches per layer (gemv.cu)
 void Session::decode_step_small(cudaStream_t st) {
@@ -539,9 +543,10 @@ void Session::decode_step(cudaStream_t st) {
     WB_REQUIRE(batch > 0, "decode_begin was not called");
     const ModelConfig& g = m->cfg;
     const int d = g.d_model, dt = m->dtype, B = batch;
-    const bool small = small_batch_path_enabled() && get_gemm_backend() == 0 && skinny_gemv_supported(B, d, dt) &&
+    const bool small = small_batch_mode() != 0 && get_gemm_backend() == 0 && skinny_gemv_supported(B, d, dt) &&
                        skinny_gemv_supported(B, g.ffn, dt) && d <= 1024;
-    if (small) decode_step_small(st);
+    if (small && small_batch_mode() == 2 && mega_supported()) decode_step_mega(st);
+    else if (small) decode_step_small(st);
     else decode_step_large(st);
     // logits -> processors -> argmax -> EOS / length bookkeeping, common to both paths
     if (logits_dump != nullptr && steps_enqueued < logits_dump_steps)

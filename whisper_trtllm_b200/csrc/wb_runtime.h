@@ -83,7 +83,11 @@ struct Buffers {
     float* dx = nullptr; float* dpart = nullptr; void* dln = nullptr; void* dqkv = nullptr; void* datt = nullptr; void* dq = nullptr;
     void* dffn = nullptr; float* logits = nullptr;
     int* tokens = nullptr; int* unfinished = nullptr; StepState* state = nullptr;
+    // whole-step kernel (step_mega.cu): attention partials of split items, grid-barrier / per-item arrival counters
+    float* mega_part = nullptr; unsigned* mega_sync = nullptr;
 };
+size_t mega_part_bytes(int max_batch, int heads);
+size_t mega_sync_bytes(int max_batch, int heads);
 
 struct Session : Buffers {
     Model* m;
@@ -129,6 +133,8 @@ struct Session : Buffers {
     void decode_step(cudaStream_t s);
     void decode_step_large(cudaStream_t s);   // tcgen05 / CUDA-core GEMMs, split-K with deferred reduction (any batch)
     void decode_step_small(cudaStream_t s);   // B <= 16, bf16: weight-streaming GEMV kernels with fused LayerNorm
+    void decode_step_mega(cudaStream_t s);    // B <= 16, bf16: ONE persistent cooperative kernel per token (step_mega.cu)
+    bool mega_supported() const;
     int decode_run(int max_steps, int check_every, cudaStream_t s);  // returns final length (syncs)
     void enqueue_step();                                             // one step on loop_stream (graph replay or eager)
     size_t cross_layer_elems() const;
