@@ -40,6 +40,7 @@ SIGNATURES = {
     "wb_set_gemm_block_n": (c_int, [c_int]),
     "wb_set_lean_decode_gemm": (c_int, [c_int]),
     "wb_set_small_batch_path": (c_int, [c_int]),
+    "wb_set_step_trace": (c_int, [c_void_p]),
     "wb_set_self_attention_warp_kernel": (c_int, [c_int]),
     "wb_set_decode_attention_backend": (c_int, [c_int]),
     "wb_bandwidth_probe": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p]),

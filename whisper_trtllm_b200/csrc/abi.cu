@@ -37,6 +37,7 @@ void set_cuda_graphs(bool on);
 void set_decode_attention_backend(int b);
 void set_lean_decode_gemm(bool on);
 void set_small_batch_path(int mode);
+void set_step_trace(long long* dev_ptr);
 void set_self_attention_variant(int v);
 size_t log_mel_workspace_bytes(int chunk);
 void log_mel(const float* pcm, int B, const float* window, const float* dft_basis, const float* mel_filters, void* workspace,
@@ -102,6 +103,11 @@ int wb_set_small_batch_path(int mode) {
         WB_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (off), 1 (GEMV kernels) or 2 (whole-step kernel)");
         wb::set_small_batch_path(mode);
     });
+}
+
+int wb_set_step_trace(void* device_buffer) {
+    wb::set_step_trace(reinterpret_cast<long long*>(device_buffer));
+    return WB_OK;
 }
 
 int wb_set_lean_decode_gemm(int enabled) {

@@ -52,6 +52,7 @@ struct MegaParams {
     const int* tokens; const StepState* state; const int* unfinished; const int* page_table;
     const bf16 *emb, *pos; const float *lnf_g, *lnf_b;
     float* x; bf16 *q, *ctx, *ffn_act; float* logits; float* part;
+    long long* trace;  // optional (tools/step_trace.py): SM clock of CTA 0 after every phase and after every barrier
     unsigned* sync;    // [0] grid barrier counter, [32 ..) per-item arrival counters; all zero between launches
     MegaLayer layer[MG_MAX_LAYERS];
 };
@@ -117,19 +118,32 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
 }
 
 // ---- activation staging: the (normalised) rows of all M utterances as bf16 in shared memory, row stride K + MG_ACT_PAD
-template <class LoadRow>
-__device__ __forceinline__ void stage_layernorm(bf16* act_s, int M, int d, const float* __restrict__ gamma,
-                                                const float* __restrict__ beta, LoadRow load_row, float* x_store) {
+// rows come from the fp32 residual stream, or (first layer) straight from the embedding tables: x = E[token] + P[position]
+// with token = ids[m, cur_len - 1] (model.py:423-425); CTA 0 then also writes the residual stream
+__device__ __forceinline__ void stage_layernorm(const MegaParams& p, bf16* act_s, const float* __restrict__ gamma,
+                                                const float* __restrict__ beta, bool embed, int pos) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nvec = d >> 2, astride = d + MG_ACT_PAD;
-    for (int m = warp; m < M; m += MG_WARPS) {
+    const int d = p.d, nvec = d >> 2, astride = d + MG_ACT_PAD;
+    float* x_store = (embed && blockIdx.x == 0) ? p.x : nullptr;
+    for (int m = warp; m < p.M; m += MG_WARPS) {
         float4 v[8];
         float s = 0.f;
+        const bf16* erow = nullptr;
+        if (embed) erow = p.emb + (size_t)p.tokens[(size_t)m * p.tokens_stride + pos] * d;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int idx = lane + 32 * i;
             if (idx < nvec) {
-                v[i] = load_row(m, idx);
+                if (embed) {
+                    const uint2 e = __ldg(reinterpret_cast<const uint2*>(erow) + idx);
+                    const uint2 q = __ldg(reinterpret_cast<const uint2*>(p.pos + (size_t)pos * d) + idx);
+                    v[i].x = __uint_as_float(e.x << 16) + __uint_as_float(q.x << 16);
+                    v[i].y = __uint_as_float(e.x & 0xffff0000u) + __uint_as_float(q.x & 0xffff0000u);
+                    v[i].z = __uint_as_float(e.y << 16) + __uint_as_float(q.y << 16);
+                    v[i].w = __uint_as_float(e.y & 0xffff0000u) + __uint_as_float(q.y & 0xffff0000u);
+                } else {
+                    v[i] = ldg_cg_f4(p.x + (size_t)m * d + idx * 4);
+                }
                 s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
             }
         }
@@ -204,12 +218,81 @@ __device__ __forceinline__ void prefetch_gemv(const bf16* __restrict__ W, int N,
     }
 }
 
-// out[m, n] = epi( sum_k act[m, k] * W[n, k] ) for all n < N, m < 8 * NM.   stage(): fills the shared activation rows.
-// epi(n, m, v) is called exactly once per output element by exactly one thread of the grid.
-template <int NM, class Stage, class Epi>
-__device__ __forceinline__ void gemv_phase(const bf16* __restrict__ W, int N, int K, GemvCfg cfg, uint8_t* smem, Stage stage, Epi epi) {
+// One linear layer of the step, described at run time.  The kernel body is a small interpreter over these descriptors with ONE
+// copy of the linear-layer code and one of each attention flavour: the whole step has to stay inside the instruction cache
+// (a first version that inlined the eight phases of a layer was 20 K instructions per layer iteration and ran 1.6x SLOWER
+// than the multi-kernel path: every phase was an instruction-cache miss streak).
+enum { ST_LN_X = 0, ST_LN_EMBED = 1, ST_COPY = 2 };
+enum { EP_QKV = 0, EP_RESIDUAL = 1, EP_BF16 = 2, EP_GELU_BF16 = 3, EP_F32 = 4 };
+struct LinearPhase {
+    const bf16* W; const float* bias; int N, K; GemvCfg cfg;
+    int stage; const float *gamma, *beta; const bf16* src;      // LayerNorm parameters / bf16 rows to copy
+    int epi; bf16* out_bf16; float* out_f32; bf16 *k_pages, *v_pages;
+};
+
+// phase k of layer l: 0 LN1+qkv, 2 out-proj, 3 LN2+cross-q, 5 cross-out, 6 LN3+fc1, 7 fc2, 8 final LN + LM head
+__device__ __forceinline__ void make_linear_phase(const MegaParams& p, int l, int k, LinearPhase& o) {
+    const MegaLayer& L = p.layer[l < p.n_layers ? l : 0];
+    o.src = nullptr; o.gamma = nullptr; o.beta = nullptr; o.out_bf16 = nullptr; o.out_f32 = nullptr; o.k_pages = nullptr; o.v_pages = nullptr;
+    o.K = p.d; o.N = p.d; o.cfg = p.c_dd; o.stage = ST_LN_X; o.epi = EP_RESIDUAL;
+    switch (k) {
+        case 0:
+            o.W = L.qkv_w; o.bias = L.qkv_b; o.N = 3 * p.d; o.cfg = p.c_qkv; o.stage = l == 0 ? ST_LN_EMBED : ST_LN_X;
+            o.gamma = L.ln1_g; o.beta = L.ln1_b; o.epi = EP_QKV; o.out_bf16 = p.q; o.k_pages = L.self_k; o.v_pages = L.self_v;
+            break;
+        case 2: o.W = L.out_w; o.bias = L.out_b; o.stage = ST_COPY; o.src = p.ctx; break;
+        case 3:
+            o.W = L.cq_w; o.bias = L.cq_b; o.gamma = L.ln2_g; o.beta = L.ln2_b; o.epi = EP_BF16; o.out_bf16 = p.q;
+            break;
+        case 5: o.W = L.cout_w; o.bias = L.cout_b; o.stage = ST_COPY; o.src = p.ctx; break;
+        case 6:
+            o.W = L.fc1_w; o.bias = L.fc1_b; o.N = p.ffn; o.cfg = p.c_fc1; o.gamma = L.ln3_g; o.beta = L.ln3_b;
+            o.epi = EP_GELU_BF16; o.out_bf16 = p.ffn_act;
+            break;
+        case 7: o.W = L.fc2_w; o.bias = L.fc2_b; o.K = p.ffn; o.cfg = p.c_fc2; o.stage = ST_COPY; o.src = p.ffn_act; break;
+        default:
+            o.W = p.emb; o.bias = nullptr; o.N = p.vocab; o.cfg = p.c_head; o.gamma = p.lnf_g; o.beta = p.lnf_b;
+            o.epi = EP_F32; o.out_f32 = p.logits;
+            break;
+    }
+}
+
+// called exactly once per output element (n, m) by exactly one thread of the grid
+__device__ __forceinline__ void linear_epilogue(const MegaParams& p, const LinearPhase& ph, int pos, int n, int m, float v) {
+    if (n >= ph.N || m >= p.M) return;
+    if (ph.bias != nullptr) v += __ldg(ph.bias + n);
+    const int d = p.d;
+    switch (ph.epi) {
+        case EP_QKV: {   // q -> activation buffer; k / v rows straight into the paged cache at slot cur_len - 1
+            const int which = n / d, c = n - which * d;
+            if (which == 0) {
+                ph.out_bf16[(size_t)m * d + c] = __float2bfloat16_rn(v);
+            } else {
+                const int page = p.page_table[(size_t)m * p.pages_per_seq + (pos >> 6)];
+                const size_t off = (((size_t)page * p.H + (c >> 6)) * 64 + (pos & 63)) * 64 + (c & 63);
+                (which == 1 ? ph.k_pages : ph.v_pages)[off] = __float2bfloat16_rn(v);
+            }
+            break;
+        }
+        case EP_RESIDUAL: {   // fp32 residual stream, updated in place: this thread owns (m, n)
+            float* xp = p.x + (size_t)m * d + n;
+            *xp = ldg_cg_f(xp) + v;
+            break;
+        }
+        case EP_BF16: ph.out_bf16[(size_t)m * ph.N + n] = __float2bfloat16_rn(v); break;
+        case EP_GELU_BF16: ph.out_bf16[(size_t)m * ph.N + n] = __float2bfloat16_rn(gelu_erf_fast(v)); break;
+        default: ph.out_f32[(size_t)m * ph.N + n] = v; break;
+    }
+}
+
+// out[m, n] = epilogue( sum_k act[m, k] * W[n, k] ) for all n < N, m < 8 * NM
+template <int NM>
+__device__ __forceinline__ void linear_phase(const MegaParams& p, const LinearPhase& ph, int pos, uint8_t* smem) {
     float* red_s = reinterpret_cast<float*>(smem);
-    const bf16* act_s = reinterpret_cast<const bf16*>(smem + MG_RED_BYTES);
+    bf16* act_s = reinterpret_cast<bf16*>(smem + MG_RED_BYTES);
+    const bf16* __restrict__ W = ph.W;
+    const int N = ph.N, K = ph.K;
+    const GemvCfg cfg = ph.cfg;
     const int astride = K + MG_ACT_PAD;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
     const GemvGeom gm(N, K, cfg);
@@ -247,11 +330,11 @@ __device__ __forceinline__ void gemv_phase(const bf16* __restrict__ W, int N, in
         if (cfg.ks == 1) {
 #pragma unroll
             for (int mb = 0; mb < NM; ++mb) {
-                epi(n0 + g, mb * 8 + 2 * tq, acc[mb][0]);
-                epi(n0 + g, mb * 8 + 2 * tq + 1, acc[mb][1]);
+                linear_epilogue(p, ph, pos, n0 + g, mb * 8 + 2 * tq, acc[mb][0]);
+                linear_epilogue(p, ph, pos, n0 + g, mb * 8 + 2 * tq + 1, acc[mb][1]);
                 if (rows16) {
-                    epi(n0 + g + 8, mb * 8 + 2 * tq, acc[mb][2]);
-                    epi(n0 + g + 8, mb * 8 + 2 * tq + 1, acc[mb][3]);
+                    linear_epilogue(p, ph, pos, n0 + g + 8, mb * 8 + 2 * tq, acc[mb][2]);
+                    linear_epilogue(p, ph, pos, n0 + g + 8, mb * 8 + 2 * tq + 1, acc[mb][3]);
                 }
             }
         } else {
@@ -274,7 +357,7 @@ __device__ __forceinline__ void gemv_phase(const bf16* __restrict__ W, int N, in
                 const float* rr = red_s + ((r & 1) * MG_WARPS + t2 * cfg.ks) * WSTRIDE + m * MG_RS + n_l;
                 float v = 0.f;
                 for (int k = 0; k < cfg.ks; ++k) v += rr[k * WSTRIDE];     // fixed order: deterministic
-                epi((gm.tile_of(r, t2) << gm.rt_shift) + n_l, m, v);
+                linear_epilogue(p, ph, pos, (gm.tile_of(r, t2) << gm.rt_shift) + n_l, m, v);
             }
         }
     };
@@ -306,7 +389,8 @@ __device__ __forceinline__ void gemv_phase(const bf16* __restrict__ W, int N, in
     uint4 cur[8], nxt[8];
     if (total > 0) {
         issue(0, cur);     // in flight while the activations are staged
-        stage();
+        if (ph.stage == ST_COPY) stage_copy(act_s, ph.src, p.M, K);
+        else stage_layernorm(p, act_s, ph.gamma, ph.beta, ph.stage == ST_LN_EMBED, pos);
     }
     __syncthreads();
 #pragma unroll 1
@@ -319,8 +403,7 @@ __device__ __forceinline__ void gemv_phase(const bf16* __restrict__ W, int N, in
 }
 
 // ---- one-query attention, one CTA per (item, key split) unit; 8 lanes per key row, 4 rows per warp instruction
-template <bool kPaged>
-__device__ __forceinline__ void attention_phase(const MegaParams& p, const bf16* __restrict__ kbase, const bf16* __restrict__ vbase,
+__device__ __forceinline__ void attention_phase(const MegaParams& p, const bool kPaged, const bf16* __restrict__ kbase, const bf16* __restrict__ vbase,
                                                 int n_keys, int splits, uint8_t* smem, unsigned* item_cnt) {
     float* pm = reinterpret_cast<float*>(smem);
     float* pl = pm + MG_WARPS;
@@ -336,9 +419,9 @@ __device__ __forceinline__ void attention_phase(const MegaParams& p, const bf16*
         float qf[8];
         unpack8(ldg_cg16(p.q + (size_t)b * d + h * 64 + sub * 8), qf);
         int my_page = 0;
-        if constexpr (kPaged) my_page = lane < p.pages_per_seq ? p.page_table[(size_t)b * p.pages_per_seq + lane] : 0;
+        if (kPaged) my_page = lane < p.pages_per_seq ? p.page_table[(size_t)b * p.pages_per_seq + lane] : 0;
         auto row_off = [&](int s) -> size_t {
-            if constexpr (kPaged) {
+            if (kPaged) {   // CTA-uniform
                 const int page = __shfl_sync(0xffffffffu, my_page, s >> 6);
                 return (((size_t)page * H + h) * 64 + (s & 63)) * 64 + sub * 8;
             } else {
@@ -353,13 +436,8 @@ __device__ __forceinline__ void attention_phase(const MegaParams& p, const bf16*
 #pragma unroll
             for (int u = 0; u < MG_ATT_UNROLL; ++u) {
                 const size_t off = row_off(min(sb + grp + u * 32, s_end - 1));
-                if constexpr (kPaged) {
-                    kr[u] = ldg_cg16(kbase + off);      // the newest row was written by another CTA in the previous phase
-                    vr[u] = ldg_cg16(vbase + off);
-                } else {
-                    kr[u] = ldg_nc16(kbase + off);
-                    vr[u] = ldg_nc16(vbase + off);
-                }
+                kr[u] = ldg_cg16(kbase + off);          // L2-coherent: the newest self-attention row was written by another CTA
+                vr[u] = ldg_cg16(vbase + off);          // in the previous phase (cross K/V are read-only; same L1 bypass)
             }
             float sc[MG_ATT_UNROLL], mb = -INFINITY;
 #pragma unroll
@@ -477,99 +555,37 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_mega_kernel(const _
     extern __shared__ __align__(128) uint8_t mg_smem[];
     if (p.state->active == 0) return;          // the loop has stopped: grid-uniform, nobody touches the barrier
     const int cur_len = p.state->cur_len, pos = cur_len - 1;
-    const int M = p.M, d = p.d, H = p.H;
-    bf16* act_s = reinterpret_cast<bf16*>(mg_smem + MG_RED_BYTES);
     unsigned* bar = p.sync;
     unsigned* item_cnt = p.sync + 32;
     unsigned epoch = 0;
-
-    auto load_x = [&](int m, int idx) -> float4 { return ldg_cg_f4(p.x + (size_t)m * d + idx * 4); };
-    // decoder embedding: x = E[token] + P[position] (fp32), token = ids[m, cur_len - 1]
-    auto load_embed = [&](int m, int idx) -> float4 {
-        const int tok = p.tokens[(size_t)m * p.tokens_stride + pos];
-        const uint2 e = __ldg(reinterpret_cast<const uint2*>(p.emb + (size_t)tok * d) + idx);
-        const uint2 q = __ldg(reinterpret_cast<const uint2*>(p.pos + (size_t)pos * d) + idx);
-        float4 r;
-        r.x = __uint_as_float(e.x << 16) + __uint_as_float(q.x << 16);
-        r.y = __uint_as_float(e.x & 0xffff0000u) + __uint_as_float(q.x & 0xffff0000u);
-        r.z = __uint_as_float(e.y << 16) + __uint_as_float(q.y << 16);
-        r.w = __uint_as_float(e.y & 0xffff0000u) + __uint_as_float(q.y & 0xffff0000u);
-        return r;
-    };
-    // x[m, n] += v + bias[n]: every (m, n) is owned by one thread of the grid
-    auto residual_epi = [&](const float* bias, int N) {
-        return [&, bias, N](int n, int m, float v) {
-            if (n < N && m < M) {
-                float* xp = p.x + (size_t)m * d + n;
-                *xp = ldg_cg_f(xp) + v + (bias != nullptr ? __ldg(bias + n) : 0.f);
-            }
-        };
-    };
-
-    for (int l = 0; l < p.n_layers; ++l) {
-        const MegaLayer& L = p.layer[l];
-        // ---- LN1 + fused q|k|v projection; k / v rows go straight into the paged cache at slot cur_len - 1
-        gemv_phase<NM>(L.qkv_w, 3 * d, d, p.c_qkv, mg_smem,
-            [&]() {
-                if (l == 0) stage_layernorm(act_s, M, d, L.ln1_g, L.ln1_b, load_embed, blockIdx.x == 0 ? p.x : nullptr);
-                else stage_layernorm(act_s, M, d, L.ln1_g, L.ln1_b, load_x, nullptr);
-            },
-            [&](int n, int m, float v) {
-                if (n < 3 * d && m < M) {
-                    v += L.qkv_b != nullptr ? __ldg(L.qkv_b + n) : 0.f;
-                    const int which = n / d, c = n - which * d;
-                    if (which == 0) {
-                        p.q[(size_t)m * d + c] = __float2bfloat16_rn(v);
-                    } else {
-                        const int page = p.page_table[(size_t)m * p.pages_per_seq + (pos >> 6)];
-                        const size_t off = (((size_t)page * H + (c >> 6)) * 64 + (pos & 63)) * 64 + (c & 63);
-                        (which == 1 ? L.self_k : L.self_v)[off] = __float2bfloat16_rn(v);
-                    }
-                }
-            });
-        prefetch_gemv(L.out_w, d, d, p.c_dd);
+    const int n_phases = 8 * p.n_layers + 1;   // 8 per layer + final LayerNorm / LM head
+    if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[0] = clock64();
+#pragma unroll 1
+    for (int ph = 0; ph < n_phases; ++ph) {
+        const int l = ph >> 3, k = (ph == n_phases - 1) ? 8 : (ph & 7);
+        if (k == 1) {          // cached self-attention over cur_len keys (the newest row was appended by phase 0's epilogue)
+            attention_phase(p, true, p.layer[l].self_k, p.layer[l].self_v, cur_len, 1, mg_smem, item_cnt);
+        } else if (k == 4) {   // cross-attention over the encoder K/V projected once per utterance
+            attention_phase(p, false, p.layer[l].cross_k, p.layer[l].cross_v, p.n_ctx, p.cross_splits, mg_smem, item_cnt);
+        } else {
+            LinearPhase lp;
+            make_linear_phase(p, l, k, lp);
+            linear_phase<NM>(p, lp, pos, mg_smem);
+        }
+        if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[2 * ph + 1] = clock64();
+        if (ph + 1 == n_phases) break;
+        // request what the next phase reads first, then meet the other CTAs
+        const int l2 = (ph + 1) >> 3, k2 = (ph + 2 == n_phases) ? 8 : ((ph + 1) & 7);
+        if (k2 == 4) {
+            prefetch_cross(p, p.layer[l2].cross_k, p.layer[l2].cross_v);
+        } else if (k2 != 1) {
+            LinearPhase np;
+            make_linear_phase(p, l2, k2, np);
+            prefetch_gemv(np.W, np.N, np.K, np.cfg);
+        }
         grid_barrier(bar, epoch);
-        // ---- cached self-attention over cur_len keys
-        attention_phase<true>(p, L.self_k, L.self_v, cur_len, 1, mg_smem, item_cnt);
-        grid_barrier(bar, epoch);
-        gemv_phase<NM>(L.out_w, d, d, p.c_dd, mg_smem, [&]() { stage_copy(act_s, p.ctx, M, d); }, residual_epi(L.out_b, d));
-        prefetch_gemv(L.cq_w, d, d, p.c_dd);
-        grid_barrier(bar, epoch);
-        // ---- LN2 + cross-attention q projection
-        gemv_phase<NM>(L.cq_w, d, d, p.c_dd, mg_smem,
-            [&]() { stage_layernorm(act_s, M, d, L.ln2_g, L.ln2_b, load_x, nullptr); },
-            [&](int n, int m, float v) {
-                if (n < d && m < M) p.q[(size_t)m * d + n] = __float2bfloat16_rn(v + (L.cq_b != nullptr ? __ldg(L.cq_b + n) : 0.f));
-            });
-        prefetch_cross(p, L.cross_k, L.cross_v);
-        grid_barrier(bar, epoch);
-        // ---- cross-attention over the encoder K/V projected once per utterance
-        attention_phase<false>(p, L.cross_k, L.cross_v, p.n_ctx, p.cross_splits, mg_smem, item_cnt);
-        prefetch_gemv(L.cout_w, d, d, p.c_dd);
-        grid_barrier(bar, epoch);
-        gemv_phase<NM>(L.cout_w, d, d, p.c_dd, mg_smem, [&]() { stage_copy(act_s, p.ctx, M, d); }, residual_epi(L.cout_b, d));
-        prefetch_gemv(L.fc1_w, p.ffn, d, p.c_fc1);
-        grid_barrier(bar, epoch);
-        // ---- MLP
-        gemv_phase<NM>(L.fc1_w, p.ffn, d, p.c_fc1, mg_smem,
-            [&]() { stage_layernorm(act_s, M, d, L.ln3_g, L.ln3_b, load_x, nullptr); },
-            [&](int n, int m, float v) {
-                if (n < p.ffn && m < M)
-                    p.ffn_act[(size_t)m * p.ffn + n] = __float2bfloat16_rn(gelu_erf_fast(v + (L.fc1_b != nullptr ? __ldg(L.fc1_b + n) : 0.f)));
-            });
-        prefetch_gemv(L.fc2_w, d, p.ffn, p.c_fc2);
-        grid_barrier(bar, epoch);
-        gemv_phase<NM>(L.fc2_w, d, p.ffn, p.c_fc2, mg_smem, [&]() { stage_copy(act_s, p.ffn_act, M, p.ffn); }, residual_epi(L.fc2_b, d));
-        if (l + 1 < p.n_layers) prefetch_gemv(p.layer[l + 1].qkv_w, 3 * d, d, p.c_qkv);
-        else prefetch_gemv(p.emb, p.vocab, d, p.c_head);
-        grid_barrier(bar, epoch);
+        if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[2 * ph + 2] = clock64();
     }
-    // ---- final LayerNorm + LM head (weights shared with the embedding table, no bias) -> fp32 logits
-    gemv_phase<NM>(p.emb, p.vocab, d, p.c_head, mg_smem,
-        [&]() { stage_layernorm(act_s, M, d, p.lnf_g, p.lnf_b, load_x, nullptr); },
-        [&](int n, int m, float v) {
-            if (n < p.vocab && m < M) p.logits[(size_t)m * p.vocab + n] = v;
-        });
     // leave the barrier counter at zero for the next launch: the last CTA to get here resets it (nobody polls it any more)
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -577,6 +593,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_mega_kernel(const _
         if (old == epoch + gridDim.x - 1) atomicExch(bar, 0u);
     }
 }
+
 
 // rounds x (serial 16-byte loads per lane + fixed per-round cost): smallest wins, ties go to fewer K splits
 GemvCfg pick_gemv_cfg(int N, int K, int grid) {
@@ -610,6 +627,12 @@ int pick_cross_splits(int items, int n_keys, int grid) {
 
 size_t mega_smem_bytes(int nm, int ffn) { return (size_t)MG_RED_BYTES + (size_t)8 * nm * (ffn + MG_ACT_PAD) * sizeof(bf16); }
 }  // namespace
+
+long long*& step_trace_ptr() {
+    static long long* ptr = nullptr;
+    return ptr;
+}
+void set_step_trace(long long* dev_ptr) { step_trace_ptr() = dev_ptr; }
 
 size_t mega_part_bytes(int max_batch, int heads) {
     return (size_t)std::min(max_batch, 16) * heads * MG_MAX_SPLITS * MG_PART * sizeof(float);
@@ -659,7 +682,7 @@ void Session::decode_step_mega(cudaStream_t st) {
     p.tokens = tokens; p.state = state; p.unfinished = unfinished; p.page_table = page_table;
     p.emb = (const bf16*)m->emb; p.pos = (const bf16*)m->dec_pos; p.lnf_g = m->dec_ln.g; p.lnf_b = m->dec_ln.b;
     p.x = dx; p.q = (bf16*)dq; p.ctx = (bf16*)datt; p.ffn_act = (bf16*)dffn; p.logits = logits;
-    p.part = mega_part; p.sync = mega_sync;
+    p.part = mega_part; p.sync = mega_sync; p.trace = step_trace_ptr();
     const size_t per_kv = (size_t)max_batch * g.n_heads * g.n_ctx * 64;
     for (int l = 0; l < g.dec_layers; ++l) {
         const DecLayer& L = m->dec[l];
