@@ -103,11 +103,14 @@ __device__ __forceinline__ void unpack8(const uint4& r, float* f) {
 // All CTAs of the (co-resident, cooperative) grid meet here.  Writes made before the barrier by any thread of any CTA are
 // visible to every thread after it: bar.sync orders the CTA's writes before thread 0's gpu-scope release, the acquire poll
 // plus bar.sync orders the other CTAs' writes before this CTA's later reads.  A lost CTA traps instead of hanging the GPU.
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
+// Split in two so that the requests for the next phase's weights are issued between the arrival and the wait.
+__device__ __forceinline__ void grid_arrive(unsigned* counter) {
     __syncthreads();
+    if (threadIdx.x == 0) red_release_gpu(counter, 1u);
+}
+__device__ __forceinline__ void grid_wait(unsigned* counter, unsigned& epoch) {
     epoch += gridDim.x;
     if (threadIdx.x == 0) {
-        red_release_gpu(counter, 1u);
         unsigned spins = 0;
         while (ld_acquire_gpu(counter) < epoch) {
             if (++spins > MG_SPIN_LIMIT) __trap();
@@ -118,74 +121,101 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
 }
 
 // ---- activation staging: the (normalised) rows of all M utterances as bf16 in shared memory, row stride K + MG_ACT_PAD
-// rows come from the fp32 residual stream, or (first layer) straight from the embedding tables: x = E[token] + P[position]
-// with token = ids[m, cur_len - 1] (model.py:423-425); CTA 0 then also writes the residual stream
-__device__ __forceinline__ void stage_layernorm(const MegaParams& p, bf16* act_s, const float* __restrict__ gamma,
+// LayerNorm of all M rows at once: thread t owns float4 t of EVERY row (d <= 1024 -> one float4 per thread and row), so all
+// the loads of the phase (x rows, gamma, beta) are issued together - one round trip - and the row statistics are reduced over
+// the 8 warps through shared memory.  (A first version gave each row to one warp, 8 float4 per lane in a guarded loop: ptxas
+// serialised the 8 gamma/beta loads, 8 dependent round trips = 5 us per phase.)
+// Rows come from the fp32 residual stream, or (first layer) straight from the embedding tables: x = E[token] + P[position]
+// with token = ids[m, cur_len - 1] (model.py:423-425); CTA 0 then also writes the residual stream.
+template <int NM>
+__device__ __forceinline__ void stage_layernorm(const MegaParams& p, bf16* act_s, float* red_s, const float* __restrict__ gamma,
                                                 const float* __restrict__ beta, bool embed, int pos) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int d = p.d, nvec = d >> 2, astride = d + MG_ACT_PAD;
-    float* x_store = (embed && blockIdx.x == 0) ? p.x : nullptr;
-    for (int m = warp; m < p.M; m += MG_WARPS) {
-        float4 v[8];
-        float s = 0.f;
-        const bf16* erow = nullptr;
-        if (embed) erow = p.emb + (size_t)p.tokens[(size_t)m * p.tokens_stride + pos] * d;
+    constexpr int MR = 8 * NM;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int d = p.d, nvec = d >> 2, astride = d + MG_ACT_PAD, M = p.M;
+    const bool on = tid < nvec;
+    const int idx = on ? tid : 0;
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + idx), b4 = __ldg(reinterpret_cast<const float4*>(beta) + idx);
+    float4 v[MR];
+    if (embed) {
+        int tok[MR];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int idx = lane + 32 * i;
-            if (idx < nvec) {
-                if (embed) {
-                    const uint2 e = __ldg(reinterpret_cast<const uint2*>(erow) + idx);
-                    const uint2 q = __ldg(reinterpret_cast<const uint2*>(p.pos + (size_t)pos * d) + idx);
-                    v[i].x = __uint_as_float(e.x << 16) + __uint_as_float(q.x << 16);
-                    v[i].y = __uint_as_float(e.x & 0xffff0000u) + __uint_as_float(q.x & 0xffff0000u);
-                    v[i].z = __uint_as_float(e.y << 16) + __uint_as_float(q.y << 16);
-                    v[i].w = __uint_as_float(e.y & 0xffff0000u) + __uint_as_float(q.y & 0xffff0000u);
-                } else {
-                    v[i] = ldg_cg_f4(p.x + (size_t)m * d + idx * 4);
-                }
-                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-            }
+        for (int m = 0; m < MR; ++m) tok[m] = p.tokens[(size_t)min(m, M - 1) * p.tokens_stride + pos];
+        const uint2 q = __ldg(reinterpret_cast<const uint2*>(p.pos + (size_t)pos * d) + idx);
+#pragma unroll
+        for (int m = 0; m < MR; ++m) {
+            const uint2 e = __ldg(reinterpret_cast<const uint2*>(p.emb + (size_t)tok[m] * d) + idx);
+            v[m].x = __uint_as_float(e.x << 16) + __uint_as_float(q.x << 16);
+            v[m].y = __uint_as_float(e.x & 0xffff0000u) + __uint_as_float(q.x & 0xffff0000u);
+            v[m].z = __uint_as_float(e.y << 16) + __uint_as_float(q.y << 16);
+            v[m].w = __uint_as_float(e.y & 0xffff0000u) + __uint_as_float(q.y & 0xffff0000u);
         }
-        const float mean = warp_sum(s) / (float)d;
-        float ss = 0.f;
+        if (blockIdx.x == 0 && on) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int idx = lane + 32 * i;
-            if (idx < nvec) {
-                const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
-                ss += (a * a + b * b) + (c * c + e * e);
-            }
+            for (int m = 0; m < MR; ++m)
+                if (m < M) *reinterpret_cast<float4*>(p.x + (size_t)m * d + idx * 4) = v[m];
         }
-        const float rstd = rsqrtf(warp_sum(ss) / (float)d + 1e-5f);
+    } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int idx = lane + 32 * i;
-            if (idx < nvec) {
-                if (x_store != nullptr) *reinterpret_cast<float4*>(x_store + (size_t)m * d + idx * 4) = v[i];
-                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + idx), b = __ldg(reinterpret_cast<const float4*>(beta) + idx);
-                __nv_bfloat162 p0 = __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
-                __nv_bfloat162 p1 = __floats2bfloat162_rn((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
-                uint2 u;
-                u.x = *reinterpret_cast<uint32_t*>(&p0);
-                u.y = *reinterpret_cast<uint32_t*>(&p1);
-                *reinterpret_cast<uint2*>(act_s + (size_t)m * astride + idx * 4) = u;
-            }
+        for (int m = 0; m < MR; ++m) v[m] = ldg_cg_f4(p.x + (size_t)min(m, M - 1) * d + idx * 4);
+    }
+    float* rs = red_s;                  // [MR][8] partial sums, then [MR][8] partial sums of squares
+    float* rq = red_s + MR * MG_WARPS;
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+        const float s = warp_sum(on ? (v[m].x + v[m].y) + (v[m].z + v[m].w) : 0.f);
+        if (lane == 0) rs[m * MG_WARPS + warp] = s;
+    }
+    __syncthreads();
+    float mean[MR];
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+        const float4 a = *reinterpret_cast<const float4*>(rs + m * MG_WARPS), b = *reinterpret_cast<const float4*>(rs + m * MG_WARPS + 4);
+        mean[m] = (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) / (float)d;
+        const float c0 = v[m].x - mean[m], c1 = v[m].y - mean[m], c2 = v[m].z - mean[m], c3 = v[m].w - mean[m];
+        const float ss = warp_sum(on ? (c0 * c0 + c1 * c1) + (c2 * c2 + c3 * c3) : 0.f);
+        if (lane == 0) rq[m * MG_WARPS + warp] = ss;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+        const float4 a = *reinterpret_cast<const float4*>(rq + m * MG_WARPS), b = *reinterpret_cast<const float4*>(rq + m * MG_WARPS + 4);
+        const float rstd = rsqrtf((((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) / (float)d + 1e-5f);
+        if (on && m < M) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn((v[m].x - mean[m]) * rstd * g4.x + b4.x, (v[m].y - mean[m]) * rstd * g4.y + b4.y);
+            __nv_bfloat162 p1 = __floats2bfloat162_rn((v[m].z - mean[m]) * rstd * g4.z + b4.z, (v[m].w - mean[m]) * rstd * g4.w + b4.w);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&p0);
+            u.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(act_s + (size_t)m * astride + idx * 4) = u;
         }
     }
 }
 
+// bf16 rows of the previous phase -> shared memory; 8 independent 16-byte requests per thread and trip
 __device__ __forceinline__ void stage_copy(bf16* act_s, const bf16* src, int M, int K) {
-    const int vpr = K >> 3, astride = K + MG_ACT_PAD;
-    for (int i = threadIdx.x; i < M * vpr; i += MG_THREADS) {
-        const int m = i / vpr, j = i - m * vpr;
-        *reinterpret_cast<uint4*>(act_s + (size_t)m * astride + j * 8) = ldg_cg16(src + (size_t)m * K + j * 8);
+    const int vpr = K >> 3, astride = K + MG_ACT_PAD, total = M * vpr;
+    for (int base = 0; base < total; base += MG_THREADS * 8) {
+        uint4 r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = min(base + u * MG_THREADS + (int)threadIdx.x, total - 1);
+            r[u] = ldg_cg16(src + (size_t)i * 8);           // rows are contiguous: element offset = i * 8
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * MG_THREADS + (int)threadIdx.x;
+            if (i < total) {
+                const int m = i / vpr, j = i - m * vpr;
+                *reinterpret_cast<uint4*>(act_s + (size_t)m * astride + j * 8) = r[u];
+            }
+        }
     }
 }
 
 // ---- geometry of one linear layer on this CTA / warp
 struct GemvGeom {
-    int rt, rt_shift, tpr, tl, ks_id, c0, c1, nsc, n_tiles, rounds;
+    int rt, rt_shift, tpr, tl, ks_id, c0, c1, cps, nsc, n_tiles, rounds;
     __device__ __forceinline__ GemvGeom(int N, int K, GemvCfg cfg) {
         const int warp = threadIdx.x >> 5;
         rt_shift = cfg.rows16 ? 4 : 3;
@@ -196,27 +226,15 @@ struct GemvGeom {
         const int C = K >> 5;                                  // 32-element chunks along K
         c0 = ks_id * C / cfg.ks;
         c1 = (ks_id + 1) * C / cfg.ks;
-        nsc = ((C + cfg.ks - 1) / cfg.ks + 3) >> 2;            // super-chunks (4 chunks = 8 x 16-byte loads per lane) per tile
+        // super-chunk = 8 x 16-byte loads per lane: 4 chunks x 2 weight rows (16-row tiles) or 8 chunks x 1 row (8-row tiles)
+        cps = cfg.rows16 ? 4 : 8;
+        nsc = ((C + cfg.ks - 1) / cfg.ks + cps - 1) / cps;
         n_tiles = (N + rt - 1) >> rt_shift;
         const int first = (int)blockIdx.x * tpr, stride = (int)gridDim.x * tpr;
         rounds = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
     }
     __device__ __forceinline__ int tile_of(int r, int t_local) const { return (r * (int)gridDim.x + (int)blockIdx.x) * tpr + t_local; }
 };
-
-// request this warp's first tile of the next linear layer into L2 (issued BEFORE the grid barrier: weights do not depend on
-// the activations the barrier is waiting for)
-__device__ __forceinline__ void prefetch_gemv(const bf16* __restrict__ W, int N, int K, GemvCfg cfg) {
-    const GemvGeom gm(N, K, cfg);
-    if (gm.rounds == 0) return;
-    const int lane = threadIdx.x & 31;
-    const int n0 = gm.tile_of(0, gm.tl) << gm.rt_shift;
-    const int lines = ((gm.c1 - gm.c0) * 64 + 127) >> 7;
-    for (int i = lane; i < gm.rt * lines; i += 32) {
-        const int r = i / lines, ln = i - r * lines;
-        prefetch_l2(W + (size_t)min(n0 + r, N - 1) * K + gm.c0 * 32 + ln * 64);
-    }
-}
 
 // One linear layer of the step, described at run time.  The kernel body is a small interpreter over these descriptors with ONE
 // copy of the linear-layer code and one of each attention flavour: the whole step has to stay inside the instruction cache
@@ -254,6 +272,26 @@ __device__ __forceinline__ void make_linear_phase(const MegaParams& p, int l, in
             o.W = p.emb; o.bias = nullptr; o.N = p.vocab; o.cfg = p.c_head; o.gamma = p.lnf_g; o.beta = p.lnf_b;
             o.epi = EP_F32; o.out_f32 = p.logits;
             break;
+    }
+}
+
+// request what the next linear layer reads first into L2: this warp's first weight tile, the LayerNorm parameters, the bias
+// of the tile (issued between the arrival at the grid barrier and the wait: none of it depends on the other CTAs)
+__device__ __forceinline__ void prefetch_linear(const MegaParams& p, const LinearPhase& ph) {
+    const GemvGeom gm(ph.N, ph.K, ph.cfg);
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (ph.gamma != nullptr) {
+        const int lines = p.d >> 5;                   // 128-byte lines per fp32 vector of d elements (<= 32)
+        if (tid < lines) prefetch_l2(ph.gamma + tid * 32);
+        else if (tid < 2 * lines) prefetch_l2(ph.beta + (tid - lines) * 32);
+    }
+    if (gm.rounds == 0) return;
+    const int n0 = gm.tile_of(0, gm.tl) << gm.rt_shift;
+    if (ph.bias != nullptr && lane == 31) prefetch_l2(ph.bias + min(n0, ph.N - 1));
+    const int lines = ((gm.c1 - gm.c0) * 64 + 127) >> 7;
+    for (int i = lane; i < gm.rt * lines; i += 32) {
+        const int r = i / lines, ln = i - r * lines;
+        prefetch_l2(ph.W + (size_t)min(n0 + r, ph.N - 1) * ph.K + gm.c0 * 32 + ln * 64);
     }
 }
 
@@ -303,24 +341,28 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const LinearPh
         const int r = idx / gm.nsc, sc = idx - r * gm.nsc;
         const int n0 = gm.tile_of(r, gm.tl) << gm.rt_shift;
         const bf16* pa = W + (size_t)min(n0 + g, N - 1) * K + tq * 8;
-        const bf16* pb = W + (size_t)min(n0 + g + 8, N - 1) * K + tq * 8;
+        if (rows16) {
+            const bf16* pb = W + (size_t)min(n0 + g + 8, N - 1) * K + tq * 8;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int chunk = gm.c0 + sc * 4 + j;
-            if (chunk < gm.c1) {
-                buf[2 * j] = ldg_nc16(pa + chunk * 32);
-                buf[2 * j + 1] = rows16 ? ldg_nc16(pb + chunk * 32) : make_uint4(0, 0, 0, 0);
-            } else {
-                buf[2 * j] = make_uint4(0, 0, 0, 0);
-                buf[2 * j + 1] = make_uint4(0, 0, 0, 0);
+            for (int j = 0; j < 4; ++j) {
+                const int chunk = gm.c0 + sc * 4 + j;
+                const bool in = chunk < gm.c1;
+                buf[2 * j] = in ? ldg_nc16(pa + chunk * 32) : make_uint4(0, 0, 0, 0);
+                buf[2 * j + 1] = in ? ldg_nc16(pb + chunk * 32) : make_uint4(0, 0, 0, 0);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int chunk = gm.c0 + sc * 8 + j;
+                buf[j] = chunk < gm.c1 ? ldg_nc16(pa + chunk * 32) : make_uint4(0, 0, 0, 0);
             }
         }
         if (idx + 3 < total) {   // keep the stream ahead of the two register buffers: one L2 prefetch per lane, 3 super-chunks on
             const int i3 = idx + 3, r3 = i3 / gm.nsc, sc3 = i3 - r3 * gm.nsc;
             const int n3 = gm.tile_of(r3, gm.tl) << gm.rt_shift;
-            const int row = lane >> 1;
-            if (row < gm.rt && gm.c0 + sc3 * 4 + (lane & 1) * 2 < gm.c1)
-                prefetch_l2(W + (size_t)min(n3 + row, N - 1) * K + (gm.c0 + sc3 * 4) * 32 + (lane & 1) * 64);
+            const int row = rows16 ? lane >> 1 : lane >> 2, line = rows16 ? lane & 1 : lane & 3;   // 256 / 512 bytes per row
+            const int chunk = gm.c0 + sc3 * gm.cps + line * 2;
+            if (chunk < gm.c1) prefetch_l2(W + (size_t)min(n3 + row, N - 1) * K + chunk * 32);
         }
     };
 
@@ -369,17 +411,32 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const LinearPh
 #pragma unroll
                 for (int i = 0; i < 4; ++i) acc[mb][i] = 0.f;
         }
+        const bf16* arow = act_s + (size_t)g * astride + tq * 8;
+        // K is permuted identically in both operands: lane tq supplies elements [8 tq, 8 tq + 8) of every 32-element chunk
+        if (rows16) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int chunk = gm.c0 + sc * 4 + j;
-            if (chunk < gm.c1) {   // warp-uniform
-                const bf16* ap = act_s + (size_t)g * astride + chunk * 32 + tq * 8;
+            for (int j = 0; j < 4; ++j) {
+                const int chunk = gm.c0 + sc * 4 + j;
+                if (chunk < gm.c1) {   // warp-uniform
 #pragma unroll
-                for (int mb = 0; mb < NM; ++mb) {
-                    const uint4 a = *reinterpret_cast<const uint4*>(ap + (size_t)mb * 8 * astride);
-                    // K is permuted identically in both operands: lane tq supplies elements [8 tq, 8 tq + 8) of the chunk
-                    mma_16816(acc[mb], buf[2 * j].x, buf[2 * j + 1].x, buf[2 * j].y, buf[2 * j + 1].y, a.x, a.y);
-                    mma_16816(acc[mb], buf[2 * j].z, buf[2 * j + 1].z, buf[2 * j].w, buf[2 * j + 1].w, a.z, a.w);
+                    for (int mb = 0; mb < NM; ++mb) {
+                        const uint4 a = *reinterpret_cast<const uint4*>(arow + (size_t)mb * 8 * astride + chunk * 32);
+                        mma_16816(acc[mb], buf[2 * j].x, buf[2 * j + 1].x, buf[2 * j].y, buf[2 * j + 1].y, a.x, a.y);
+                        mma_16816(acc[mb], buf[2 * j].z, buf[2 * j + 1].z, buf[2 * j].w, buf[2 * j + 1].w, a.z, a.w);
+                    }
+                }
+            }
+        } else {               // 8-row tiles: MMA rows 8..15 are zero
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int chunk = gm.c0 + sc * 8 + j;
+                if (chunk < gm.c1) {
+#pragma unroll
+                    for (int mb = 0; mb < NM; ++mb) {
+                        const uint4 a = *reinterpret_cast<const uint4*>(arow + (size_t)mb * 8 * astride + chunk * 32);
+                        mma_16816(acc[mb], buf[j].x, 0u, buf[j].y, 0u, a.x, a.y);
+                        mma_16816(acc[mb], buf[j].z, 0u, buf[j].w, 0u, a.z, a.w);
+                    }
                 }
             }
         }
@@ -390,7 +447,7 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const LinearPh
     if (total > 0) {
         issue(0, cur);     // in flight while the activations are staged
         if (ph.stage == ST_COPY) stage_copy(act_s, ph.src, p.M, K);
-        else stage_layernorm(p, act_s, ph.gamma, ph.beta, ph.stage == ST_LN_EMBED, pos);
+        else stage_layernorm<NM>(p, act_s, red_s, ph.gamma, ph.beta, ph.stage == ST_LN_EMBED, pos);
     }
     __syncthreads();
 #pragma unroll 1
@@ -515,17 +572,28 @@ __device__ __forceinline__ void attention_phase(const MegaParams& p, const bool 
             __syncthreads();
             if (tid == 0) *flag = (atomicAdd(&item_cnt[item], 1u) == (unsigned)(splits - 1));
             __syncthreads();
-            if (*flag) {
+            if (*flag) {                        // CTA-uniform
                 __threadfence();
+                // all partials of the item in ONE round trip: 256 threads x <= 5 independent loads -> shared memory
+                float* pbuf = reinterpret_cast<float*>(smem) + 1024;
+                const float* pp = p.part + (size_t)item * splits * MG_PART;
+                const int n_f = splits * MG_PART;
+                float r[(MG_MAX_SPLITS * MG_PART + MG_THREADS - 1) / MG_THREADS];
+#pragma unroll
+                for (int u = 0; u < (MG_MAX_SPLITS * MG_PART + MG_THREADS - 1) / MG_THREADS; ++u)
+                    r[u] = ldg_cg_f(pp + min(u * MG_THREADS + tid, n_f - 1));
+#pragma unroll
+                for (int u = 0; u < (MG_MAX_SPLITS * MG_PART + MG_THREADS - 1) / MG_THREADS; ++u)
+                    if (u * MG_THREADS + tid < n_f) pbuf[u * MG_THREADS + tid] = r[u];
+                __syncthreads();
                 if (tid < 64) {
-                    const float* pp = p.part + (size_t)item * splits * MG_PART;
                     float mm = -INFINITY;
-                    for (int s = 0; s < splits; ++s) mm = fmaxf(mm, ldg_cg_f(pp + s * MG_PART));
+                    for (int s = 0; s < splits; ++s) mm = fmaxf(mm, pbuf[s * MG_PART]);
                     float l = 0.f, o = 0.f;
                     for (int s = 0; s < splits; ++s) {
-                        const float w = __expf(ldg_cg_f(pp + s * MG_PART) - mm);
-                        l = fmaf(ldg_cg_f(pp + s * MG_PART + 1), w, l);
-                        o = fmaf(ldg_cg_f(pp + s * MG_PART + 8 + tid), w, o);
+                        const float w = __expf(pbuf[s * MG_PART] - mm);
+                        l = fmaf(pbuf[s * MG_PART + 1], w, l);
+                        o = fmaf(pbuf[s * MG_PART + 8 + tid], w, o);
                     }
                     p.ctx[(size_t)b * d + h * 64 + tid] = __float2bfloat16_rn(o / l);
                 }
@@ -547,6 +615,19 @@ __device__ __forceinline__ void prefetch_cross(const MegaParams& p, const bf16* 
     for (int i = threadIdx.x; i < s_end - s_beg; i += MG_THREADS) {   // one 128-byte row per request
         prefetch_l2(kbase + off + (size_t)i * 64);
         prefetch_l2(vbase + off + (size_t)i * 64);
+    }
+}
+
+// same for the first self-attention item of this CTA (pages of utterance b, head h; the newest row is still being written)
+__device__ __forceinline__ void prefetch_self(const MegaParams& p, const bf16* kbase, const bf16* vbase, int n_keys) {
+    const int item = blockIdx.x;
+    if (item >= p.M * p.H) return;
+    const int b = item / p.H, h = item - b * p.H;
+    for (int s = threadIdx.x; s < n_keys - 1; s += MG_THREADS) {
+        const int page = p.page_table[(size_t)b * p.pages_per_seq + (s >> 6)];
+        const size_t off = (((size_t)page * p.H + h) * 64 + (s & 63)) * 64;
+        prefetch_l2(kbase + off);
+        prefetch_l2(vbase + off);
     }
 }
 
@@ -574,16 +655,19 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_mega_kernel(const _
         }
         if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[2 * ph + 1] = clock64();
         if (ph + 1 == n_phases) break;
-        // request what the next phase reads first, then meet the other CTAs
+        // arrive at the grid barrier, request what the next phase reads first, then wait for the other CTAs
+        grid_arrive(bar);
         const int l2 = (ph + 1) >> 3, k2 = (ph + 2 == n_phases) ? 8 : ((ph + 1) & 7);
         if (k2 == 4) {
             prefetch_cross(p, p.layer[l2].cross_k, p.layer[l2].cross_v);
-        } else if (k2 != 1) {
+        } else if (k2 == 1) {
+            prefetch_self(p, p.layer[l2].self_k, p.layer[l2].self_v, cur_len);
+        } else {
             LinearPhase np;
             make_linear_phase(p, l2, k2, np);
-            prefetch_gemv(np.W, np.N, np.K, np.cfg);
+            prefetch_linear(p, np);
         }
-        grid_barrier(bar, epoch);
+        grid_wait(bar, epoch);
         if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[2 * ph + 2] = clock64();
     }
     // leave the barrier counter at zero for the next launch: the last CTA to get here resets it (nobody polls it any more)
