@@ -70,9 +70,10 @@ WB_API int wb_set_self_attention_warp_kernel(int variant);
  * barriers (csrc/step_mega.cu); 1 = weight-streaming GEMV kernels with the LayerNorm fused in front, 8 launches per layer
  * (csrc/gemv.cu); 0 = the large-batch kernels.  Captured CUDA graphs keep the path they were captured with. */
 WB_API int wb_set_small_batch_path(int mode);
-/* measurement hook of the whole-step kernel: device buffer of 2 * (8 * decoder_layers + 1) + 1 int64; CTA 0 stores its SM clock
- * at kernel start, after every phase and after every grid barrier (tools/step_trace.py).  NULL (default) = off.  Decode-step
- * graphs captured afterwards carry the pointer. */
+/* measurement hook of the whole-step kernel: device buffer of 8 * (8 * decoder_layers + 2) int64; CTA 0 stores its SM clock
+ * at 8 points of every phase: [0] start, [1] first weight tile requested, [2] activations staged, [3] block barrier passed,
+ * [4] phase done, [5] arrived at the grid barrier + next phase prefetched, [8] = next [0] grid barrier passed
+ * (tools/step_trace.py).  NULL (default) = off.  Decode-step graphs captured afterwards carry the pointer. */
 WB_API int wb_set_step_trace(void* device_buffer);
 /* skinny (decode-step) GEMMs use the variant sized to co-reside with the bulk-ring cross-attention CTA of a concurrent stream
  * (256 threads, <= 128 registers, <= 90 KB shared memory); set together with wb_decode_run_multi.  Default 0. */

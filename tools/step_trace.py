@@ -30,7 +30,7 @@ def main():
     sd = synth.make_weights(cfg, seed=0)
     L = cfg["decoder_layers"]
     n_phases = 8 * L + 1
-    trace = torch.zeros(2 * n_phases + 1, dtype=torch.int64, device=dev)
+    trace = torch.zeros(8 * (n_phases + 1), dtype=torch.int64, device=dev)
     _abi.call("wb_set_small_batch_path", 2)
     _abi.call("wb_set_step_trace", ptr(trace))
     eng = WhisperEngine(cfg, sd, dtype="bf16", max_batch=a.batch, enc_chunk=min(a.batch, 32), device=dev)
@@ -46,27 +46,35 @@ def main():
     torch.cuda.synchronize()
     step_us = e0.elapsed_time(e1) / 8 * 1e3
     t = trace.cpu().tolist()
-    total_cycles = t[2 * n_phases - 1] - t[0]
-    # the kernel is all but the argmax kernel and the launch gap of a step: calibrate the SM clock on a second measurement
+    total_cycles = t[8 * (n_phases - 1) + 4] - t[0]
     mhz = float(os.popen("nvidia-smi --query-gpu=clocks.sm --format=csv,noheader,nounits -i 0").read().split()[0] or 0)
     print(f"# Whole-step kernel phase trace: {a.size} bf16, batch {a.batch}, length {a.length + 8}\n")
     print(f"step (CUDA events, graph replay) {step_us:.0f} us; kernel {total_cycles} SM cycles; nvidia-smi SM clock after the run {mhz:.0f} MHz\n")
-    print("| phase | count | work cycles (mean) | barrier cycles (mean) | share of kernel |")
-    print("|---|---|---|---|---|")
-    work = [0] * 9
-    barrier = [0] * 9
+    print("Mean SM cycles of CTA 0 per phase kind (linear layers: request first weight tile -> stage activations (LayerNorm / copy) "
+          "-> block barrier -> weight stream + MMA + reduction + epilogue; then arrive + prefetch of the next phase -> wait for the grid).\n")
+    print("| phase | count | issue | stage | block barrier | stream + epilogue | work total | arrive + prefetch | grid wait | share of kernel |")
+    print("|---|---|---|---|---|---|---|---|---|---|")
+    acc = [[0] * 7 for _ in range(9)]
     count = [0] * 9
     for ph in range(n_phases):
         k = 8 if ph == n_phases - 1 else ph % 8
-        start = t[2 * ph]
-        work[k] += t[2 * ph + 1] - start
+        s0 = t[8 * ph: 8 * ph + 9]
+        linear = k not in (1, 4)
+        if linear:
+            acc[k][0] += s0[1] - s0[0]
+            acc[k][1] += s0[2] - s0[1]
+            acc[k][2] += s0[3] - s0[2]
+            acc[k][3] += s0[4] - s0[3]
+        acc[k][4] += s0[4] - s0[0]
         if ph + 1 < n_phases:
-            barrier[k] += t[2 * ph + 2] - t[2 * ph + 1]
+            acc[k][5] += s0[5] - s0[4]
+            acc[k][6] += s0[8] - s0[5]
         count[k] += 1
     for k in range(9):
-        share = (work[k] + barrier[k]) / max(total_cycles, 1)
-        print(f"| {KINDS[k]} | {count[k]} | {work[k] / count[k]:.0f} | {barrier[k] / count[k]:.0f} | {share:.1%} |")
-    print(f"\nwork = phase body of CTA 0 (staging, weight stream, MMA, epilogue); barrier = prefetch of the next phase + waiting for the slowest CTA + release / acquire round trips.")
+        c = count[k]
+        share = (acc[k][4] + acc[k][5] + acc[k][6]) / max(total_cycles, 1)
+        cells = " | ".join(f"{acc[k][i] / c:.0f}" for i in range(7))
+        print(f"| {KINDS[k]} | {c} | {cells} | {share:.1%} |")
     _abi.call("wb_set_step_trace", None)
     eng.close()
 

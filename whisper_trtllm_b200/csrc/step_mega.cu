@@ -32,7 +32,7 @@ constexpr int MG_RS = 20;            // reduction buffer: floats between consecu
 constexpr int MG_RED_BYTES = 2 * MG_WARPS * 16 * MG_RS * 4;   // two parities x 8 warps x 16 rows
 constexpr int MG_ACT_PAD = 32;       // bf16 elements of padding per staged row (row stride = 64 mod 128 bytes)
 constexpr unsigned MG_SPIN_LIMIT = 1u << 26;
-constexpr int MG_ATT_UNROLL = 8;
+constexpr int MG_ATT_UNROLL = 4;
 
 struct MegaLayer {
     const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
@@ -43,7 +43,14 @@ struct MegaLayer {
 };
 
 // work split of one linear layer over the grid: tiles of 8 or 16 weight rows, K split over `ks` warps of a CTA
-struct GemvCfg { int ks; int rows16; };
+// (everything that needs a division is computed once on the host: the phases are latency-bound instruction streams)
+struct GemvCfg {
+    int ks, ks_shift, rows16;
+    int C;                 // 32-element chunks along K
+    int cps, nsc;          // chunks per super-chunk (8 x 16-byte loads per lane), super-chunks per tile
+    int n_tiles, tpr;      // tiles of 8 / 16 weight rows, tiles per CTA and round
+    int rounds_base, rounds_rem;   // rounds of CTA c = rounds_base + (c * tpr < rounds_rem)
+};
 
 struct MegaParams {
     int M, d, H, ffn, vocab, n_layers, n_ctx, cross_splits, pages_per_seq, tokens_stride;
@@ -52,7 +59,7 @@ struct MegaParams {
     const int* tokens; const StepState* state; const int* unfinished; const int* page_table;
     const bf16 *emb, *pos; const float *lnf_g, *lnf_b;
     float* x; bf16 *q, *ctx, *ffn_act; float* logits; float* part;
-    long long* trace;  // optional (tools/step_trace.py): SM clock of CTA 0 after every phase and after every barrier
+    long long* trace;  // optional (tools/step_trace.py): SM clock stamps of CTA 0, 8 slots per phase (see the kernel body)
     unsigned* sync;    // [0] grid barrier counter, [32 ..) per-item arrival counters; all zero between launches
     MegaLayer layer[MG_MAX_LAYERS];
 };
@@ -121,73 +128,79 @@ __device__ __forceinline__ void grid_wait(unsigned* counter, unsigned& epoch) {
 }
 
 // ---- activation staging: the (normalised) rows of all M utterances as bf16 in shared memory, row stride K + MG_ACT_PAD
-// LayerNorm of all M rows at once: thread t owns float4 t of EVERY row (d <= 1024 -> one float4 per thread and row), so all
-// the loads of the phase (x rows, gamma, beta) are issued together - one round trip - and the row statistics are reduced over
-// the 8 warps through shared memory.  (A first version gave each row to one warp, 8 float4 per lane in a guarded loop: ptxas
-// serialised the 8 gamma/beta loads, 8 dependent round trips = 5 us per phase.)
+// LayerNorm staging, one warp per row (rows m = warp, warp + 8): the 24 loads of a row (x, gamma, beta: 8 float4 each per lane
+// at d = 1024) are all issued before the first use - one round trip - and the statistics need only warp shuffles.  The phases
+// are latency-bound instruction streams (2 warps per scheduler): what counts is the number of instructions per warp on the
+// critical path.  (First version: guarded per-element loop, ptxas serialised the gamma / beta loads into 8 dependent round
+// trips; second version: every thread touched every row - 1300 instructions per warp, 6.4 K cycles, profiles/r01_step_trace*.)
 // Rows come from the fp32 residual stream, or (first layer) straight from the embedding tables: x = E[token] + P[position]
 // with token = ids[m, cur_len - 1] (model.py:423-425); CTA 0 then also writes the residual stream.
-template <int NM>
-__device__ __forceinline__ void stage_layernorm(const MegaParams& p, bf16* act_s, float* red_s, const float* __restrict__ gamma,
+template <bool kFull>   // kFull: d == 1024, every lane owns 8 float4 of the row (no predicates)
+__device__ __forceinline__ void stage_layernorm(const MegaParams& p, bf16* act_s, const float* __restrict__ gamma,
                                                 const float* __restrict__ beta, bool embed, int pos) {
-    constexpr int MR = 8 * NM;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int d = p.d, nvec = d >> 2, astride = d + MG_ACT_PAD, M = p.M;
-    const bool on = tid < nvec;
-    const int idx = on ? tid : 0;
-    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + idx), b4 = __ldg(reinterpret_cast<const float4*>(beta) + idx);
-    float4 v[MR];
-    if (embed) {
-        int tok[MR];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = p.d, nvec = d >> 2, astride = d + MG_ACT_PAD;
+    const float inv_d = 1.0f / (float)d;
+    for (int m = warp; m < p.M; m += MG_WARPS) {
+        float4 v[8];
+        if (embed) {
+            const int tok = p.tokens[(size_t)m * p.tokens_stride + pos];
+            const uint2* erow = reinterpret_cast<const uint2*>(p.emb + (size_t)tok * d);
+            const uint2* prow = reinterpret_cast<const uint2*>(p.pos + (size_t)pos * d);
 #pragma unroll
-        for (int m = 0; m < MR; ++m) tok[m] = p.tokens[(size_t)min(m, M - 1) * p.tokens_stride + pos];
-        const uint2 q = __ldg(reinterpret_cast<const uint2*>(p.pos + (size_t)pos * d) + idx);
+            for (int i = 0; i < 8; ++i) {
+                const int idx = lane + 32 * i;
+                const uint2 e = (kFull || idx < nvec) ? __ldg(erow + idx) : make_uint2(0u, 0u);
+                const uint2 q = (kFull || idx < nvec) ? __ldg(prow + idx) : make_uint2(0u, 0u);
+                v[i].x = __uint_as_float(e.x << 16) + __uint_as_float(q.x << 16);
+                v[i].y = __uint_as_float(e.x & 0xffff0000u) + __uint_as_float(q.x & 0xffff0000u);
+                v[i].z = __uint_as_float(e.y << 16) + __uint_as_float(q.y << 16);
+                v[i].w = __uint_as_float(e.y & 0xffff0000u) + __uint_as_float(q.y & 0xffff0000u);
+            }
+        } else {
 #pragma unroll
-        for (int m = 0; m < MR; ++m) {
-            const uint2 e = __ldg(reinterpret_cast<const uint2*>(p.emb + (size_t)tok[m] * d) + idx);
-            v[m].x = __uint_as_float(e.x << 16) + __uint_as_float(q.x << 16);
-            v[m].y = __uint_as_float(e.x & 0xffff0000u) + __uint_as_float(q.x & 0xffff0000u);
-            v[m].z = __uint_as_float(e.y << 16) + __uint_as_float(q.y << 16);
-            v[m].w = __uint_as_float(e.y & 0xffff0000u) + __uint_as_float(q.y & 0xffff0000u);
+            for (int i = 0; i < 8; ++i) {
+                const int idx = lane + 32 * i;
+                v[i] = (kFull || idx < nvec) ? ldg_cg_f4(p.x + (size_t)m * d + idx * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
-        if (blockIdx.x == 0 && on) {
+        float s = 0.f;
 #pragma unroll
-            for (int m = 0; m < MR; ++m)
-                if (m < M) *reinterpret_cast<float4*>(p.x + (size_t)m * d + idx * 4) = v[m];
+        for (int i = 0; i < 8; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);      // lanes past the row hold zeros
+        const float mean = warp_sum(s) * inv_d;
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (kFull || lane + 32 * i < nvec) {
+                const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+                ss += (a * a + b * b) + (c * c + e * e);
+            }
         }
-    } else {
+        const float rstd = rsqrtf(warp_sum(ss) * inv_d + 1e-5f);
+        // gamma / beta were requested into L2 before the grid barrier: two half-batches of 8 loads (an L2 round trip each) keep
+        // the register peak at v[8] + 8 float4 next to the weight tile that is already in flight
 #pragma unroll
-        for (int m = 0; m < MR; ++m) v[m] = ldg_cg_f4(p.x + (size_t)min(m, M - 1) * d + idx * 4);
-    }
-    float* rs = red_s;                  // [MR][8] partial sums, then [MR][8] partial sums of squares
-    float* rq = red_s + MR * MG_WARPS;
+        for (int half = 0; half < 2; ++half) {
+            float4 g4[4], b4[4];
 #pragma unroll
-    for (int m = 0; m < MR; ++m) {
-        const float s = warp_sum(on ? (v[m].x + v[m].y) + (v[m].z + v[m].w) : 0.f);
-        if (lane == 0) rs[m * MG_WARPS + warp] = s;
-    }
-    __syncthreads();
-    float mean[MR];
+            for (int j = 0; j < 4; ++j) {
+                const int idx = lane + 32 * (half * 4 + j);
+                g4[j] = (kFull || idx < nvec) ? __ldg(reinterpret_cast<const float4*>(gamma) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                b4[j] = (kFull || idx < nvec) ? __ldg(reinterpret_cast<const float4*>(beta) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-    for (int m = 0; m < MR; ++m) {
-        const float4 a = *reinterpret_cast<const float4*>(rs + m * MG_WARPS), b = *reinterpret_cast<const float4*>(rs + m * MG_WARPS + 4);
-        mean[m] = (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) / (float)d;
-        const float c0 = v[m].x - mean[m], c1 = v[m].y - mean[m], c2 = v[m].z - mean[m], c3 = v[m].w - mean[m];
-        const float ss = warp_sum(on ? (c0 * c0 + c1 * c1) + (c2 * c2 + c3 * c3) : 0.f);
-        if (lane == 0) rq[m * MG_WARPS + warp] = ss;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int m = 0; m < MR; ++m) {
-        const float4 a = *reinterpret_cast<const float4*>(rq + m * MG_WARPS), b = *reinterpret_cast<const float4*>(rq + m * MG_WARPS + 4);
-        const float rstd = rsqrtf((((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) / (float)d + 1e-5f);
-        if (on && m < M) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn((v[m].x - mean[m]) * rstd * g4.x + b4.x, (v[m].y - mean[m]) * rstd * g4.y + b4.y);
-            __nv_bfloat162 p1 = __floats2bfloat162_rn((v[m].z - mean[m]) * rstd * g4.z + b4.z, (v[m].w - mean[m]) * rstd * g4.w + b4.w);
-            uint2 u;
-            u.x = *reinterpret_cast<uint32_t*>(&p0);
-            u.y = *reinterpret_cast<uint32_t*>(&p1);
-            *reinterpret_cast<uint2*>(act_s + (size_t)m * astride + idx * 4) = u;
+            for (int j = 0; j < 4; ++j) {
+                const int i = half * 4 + j, idx = lane + 32 * i;
+                if (kFull || idx < nvec) {
+                    if (embed && blockIdx.x == 0) *reinterpret_cast<float4*>(p.x + (size_t)m * d + idx * 4) = v[i];
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn((v[i].x - mean) * rstd * g4[j].x + b4[j].x, (v[i].y - mean) * rstd * g4[j].y + b4[j].y);
+                    __nv_bfloat162 p1 = __floats2bfloat162_rn((v[i].z - mean) * rstd * g4[j].z + b4[j].z, (v[i].w - mean) * rstd * g4[j].w + b4[j].w);
+                    uint2 u;
+                    u.x = *reinterpret_cast<uint32_t*>(&p0);
+                    u.y = *reinterpret_cast<uint32_t*>(&p1);
+                    *reinterpret_cast<uint2*>(act_s + (size_t)m * astride + idx * 4) = u;
+                }
+            }
         }
     }
 }
@@ -199,8 +212,8 @@ __device__ __forceinline__ void stage_copy(bf16* act_s, const bf16* src, int M, 
         uint4 r[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int i = min(base + u * MG_THREADS + (int)threadIdx.x, total - 1);
-            r[u] = ldg_cg16(src + (size_t)i * 8);           // rows are contiguous: element offset = i * 8
+            const int i = base + u * MG_THREADS + (int)threadIdx.x;   // no clamped duplicates: 148 SMs x 256 threads asking for one
+            r[u] = i < total ? ldg_cg16(src + (size_t)i * 8) : make_uint4(0, 0, 0, 0);   // line serialise in its L2 slice
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -215,23 +228,19 @@ __device__ __forceinline__ void stage_copy(bf16* act_s, const bf16* src, int M, 
 
 // ---- geometry of one linear layer on this CTA / warp
 struct GemvGeom {
-    int rt, rt_shift, tpr, tl, ks_id, c0, c1, cps, nsc, n_tiles, rounds;
-    __device__ __forceinline__ GemvGeom(int N, int K, GemvCfg cfg) {
+    int rt_shift, rt, tpr, tl, ks_id, c0, c1, cps, nsc, rounds;
+    __device__ __forceinline__ GemvGeom(const GemvCfg& cfg) {
         const int warp = threadIdx.x >> 5;
         rt_shift = cfg.rows16 ? 4 : 3;
         rt = 1 << rt_shift;
-        tpr = MG_WARPS / cfg.ks;
-        tl = warp / cfg.ks;
-        ks_id = warp - tl * cfg.ks;
-        const int C = K >> 5;                                  // 32-element chunks along K
-        c0 = ks_id * C / cfg.ks;
-        c1 = (ks_id + 1) * C / cfg.ks;
-        // super-chunk = 8 x 16-byte loads per lane: 4 chunks x 2 weight rows (16-row tiles) or 8 chunks x 1 row (8-row tiles)
-        cps = cfg.rows16 ? 4 : 8;
-        nsc = ((C + cfg.ks - 1) / cfg.ks + cps - 1) / cps;
-        n_tiles = (N + rt - 1) >> rt_shift;
-        const int first = (int)blockIdx.x * tpr, stride = (int)gridDim.x * tpr;
-        rounds = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+        tpr = cfg.tpr;
+        tl = warp >> cfg.ks_shift;
+        ks_id = warp & (cfg.ks - 1);
+        c0 = (ks_id * cfg.C) >> cfg.ks_shift;
+        c1 = ((ks_id + 1) * cfg.C) >> cfg.ks_shift;
+        cps = cfg.cps;
+        nsc = cfg.nsc;
+        rounds = cfg.rounds_base + ((int)blockIdx.x * tpr < cfg.rounds_rem ? 1 : 0);
     }
     __device__ __forceinline__ int tile_of(int r, int t_local) const { return (r * (int)gridDim.x + (int)blockIdx.x) * tpr + t_local; }
 };
@@ -278,7 +287,7 @@ __device__ __forceinline__ void make_linear_phase(const MegaParams& p, int l, in
 // request what the next linear layer reads first into L2: this warp's first weight tile, the LayerNorm parameters, the bias
 // of the tile (issued between the arrival at the grid barrier and the wait: none of it depends on the other CTAs)
 __device__ __forceinline__ void prefetch_linear(const MegaParams& p, const LinearPhase& ph) {
-    const GemvGeom gm(ph.N, ph.K, ph.cfg);
+    const GemvGeom gm(ph.cfg);
     const int tid = threadIdx.x, lane = tid & 31;
     if (ph.gamma != nullptr) {
         const int lines = p.d >> 5;                   // 128-byte lines per fp32 vector of d elements (<= 32)
@@ -288,10 +297,10 @@ __device__ __forceinline__ void prefetch_linear(const MegaParams& p, const Linea
     if (gm.rounds == 0) return;
     const int n0 = gm.tile_of(0, gm.tl) << gm.rt_shift;
     if (ph.bias != nullptr && lane == 31) prefetch_l2(ph.bias + min(n0, ph.N - 1));
-    const int lines = ((gm.c1 - gm.c0) * 64 + 127) >> 7;
-    for (int i = lane; i < gm.rt * lines; i += 32) {
-        const int r = i / lines, ln = i - r * lines;
-        prefetch_l2(ph.W + (size_t)min(n0 + r, ph.N - 1) * ph.K + gm.c0 * 32 + ln * 64);
+    const int lines = ((gm.c1 - gm.c0) * 64 + 127) >> 7;      // <= 32 for K <= 4096
+    if (lane < lines) {
+        const bf16* base = ph.W + gm.c0 * 32 + lane * 64;
+        for (int r = 0; r < gm.rt; ++r) prefetch_l2(base + (size_t)min(n0 + r, ph.N - 1) * ph.K);
     }
 }
 
@@ -302,7 +311,7 @@ __device__ __forceinline__ void linear_epilogue(const MegaParams& p, const Linea
     const int d = p.d;
     switch (ph.epi) {
         case EP_QKV: {   // q -> activation buffer; k / v rows straight into the paged cache at slot cur_len - 1
-            const int which = n / d, c = n - which * d;
+            const int which = (n >= d ? 1 : 0) + (n >= 2 * d ? 1 : 0), c = n - which * d;
             if (which == 0) {
                 ph.out_bf16[(size_t)m * d + c] = __float2bfloat16_rn(v);
             } else {
@@ -325,7 +334,7 @@ __device__ __forceinline__ void linear_epilogue(const MegaParams& p, const Linea
 
 // out[m, n] = epilogue( sum_k act[m, k] * W[n, k] ) for all n < N, m < 8 * NM
 template <int NM>
-__device__ __forceinline__ void linear_phase(const MegaParams& p, const LinearPhase& ph, int pos, uint8_t* smem) {
+__device__ __forceinline__ void linear_phase(const MegaParams& p, const LinearPhase& ph, int pos, uint8_t* smem, long long* tr) {
     float* red_s = reinterpret_cast<float*>(smem);
     bf16* act_s = reinterpret_cast<bf16*>(smem + MG_RED_BYTES);
     const bf16* __restrict__ W = ph.W;
@@ -333,12 +342,12 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const LinearPh
     const GemvCfg cfg = ph.cfg;
     const int astride = K + MG_ACT_PAD;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
-    const GemvGeom gm(N, K, cfg);
+    const GemvGeom gm(cfg);
     const int total = gm.rounds * gm.nsc;
     const bool rows16 = cfg.rows16 != 0;
 
-    auto issue = [&](int idx, uint4(&buf)[8]) __attribute__((always_inline)) {
-        const int r = idx / gm.nsc, sc = idx - r * gm.nsc;
+    // (r, sc) = (round, super-chunk) of the tile being requested / computed; advanced incrementally, no divisions
+    auto issue = [&](int idx, int r, int sc, uint4(&buf)[8]) __attribute__((always_inline)) {
         const int n0 = gm.tile_of(r, gm.tl) << gm.rt_shift;
         const bf16* pa = W + (size_t)min(n0 + g, N - 1) * K + tq * 8;
         if (rows16) {
@@ -358,7 +367,8 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const LinearPh
             }
         }
         if (idx + 3 < total) {   // keep the stream ahead of the two register buffers: one L2 prefetch per lane, 3 super-chunks on
-            const int i3 = idx + 3, r3 = i3 / gm.nsc, sc3 = i3 - r3 * gm.nsc;
+            int r3 = r, sc3 = sc + 3;
+            while (sc3 >= gm.nsc) { sc3 -= gm.nsc; ++r3; }
             const int n3 = gm.tile_of(r3, gm.tl) << gm.rt_shift;
             const int row = rows16 ? lane >> 1 : lane >> 2, line = rows16 ? lane & 1 : lane & 3;   // 256 / 512 bytes per row
             const int chunk = gm.c0 + sc3 * gm.cps + line * 2;
@@ -403,8 +413,7 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const LinearPh
             }
         }
     };
-    auto compute = [&](int idx, const uint4(&buf)[8]) __attribute__((always_inline)) {
-        const int r = idx / gm.nsc, sc = idx - r * gm.nsc;
+    auto compute = [&](int r, int sc, const uint4(&buf)[8]) __attribute__((always_inline)) {
         if (sc == 0) {
 #pragma unroll
             for (int mb = 0; mb < NM; ++mb)
@@ -445,17 +454,26 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const LinearPh
 
     uint4 cur[8], nxt[8];
     if (total > 0) {
-        issue(0, cur);     // in flight while the activations are staged
+        issue(0, 0, 0, cur);     // in flight while the activations are staged
+        if (tr != nullptr) tr[1] = clock64();
         if (ph.stage == ST_COPY) stage_copy(act_s, ph.src, p.M, K);
-        else stage_layernorm<NM>(p, act_s, red_s, ph.gamma, ph.beta, ph.stage == ST_LN_EMBED, pos);
+        else if (p.d == 1024) stage_layernorm<true>(p, act_s, ph.gamma, ph.beta, ph.stage == ST_LN_EMBED, pos);
+        else stage_layernorm<false>(p, act_s, ph.gamma, ph.beta, ph.stage == ST_LN_EMBED, pos);
     }
+    if (tr != nullptr) tr[2] = clock64();
     __syncthreads();
+    if (tr != nullptr) tr[3] = clock64();
+    int r = 0, sc = 0;
 #pragma unroll 1
     for (int idx = 0; idx < total; ++idx) {   // trip counts are CTA-uniform (finish() contains a block barrier)
-        if (idx + 1 < total) issue(idx + 1, nxt);
-        compute(idx, cur);
+        int r1 = r, sc1 = sc + 1;
+        if (sc1 == gm.nsc) { sc1 = 0; ++r1; }
+        if (idx + 1 < total) issue(idx + 1, r1, sc1, nxt);
+        compute(r, sc, cur);
 #pragma unroll
         for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+        r = r1;
+        sc = sc1;
     }
 }
 
@@ -488,14 +506,22 @@ __device__ __forceinline__ void attention_phase(const MegaParams& p, const bool 
         float m_run = -INFINITY, l_run = 0.f, acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        for (int sb = s_beg + warp * 4; sb < s_end; sb += 32 * MG_ATT_UNROLL) {   // warp-uniform trip count
-            uint4 kr[MG_ATT_UNROLL], vr[MG_ATT_UNROLL];
+        // software pipeline: the 16 requests per lane of batch i + 1 are in flight while batch i is reduced (one CTA per SM
+        // and 8 warps in lock step: without it the SM alternates between waiting for HBM and computing, 13 B/clk)
+        auto issue = [&](int sb, uint4(&kr)[MG_ATT_UNROLL], uint4(&vr)[MG_ATT_UNROLL]) __attribute__((always_inline)) {
 #pragma unroll
             for (int u = 0; u < MG_ATT_UNROLL; ++u) {
                 const size_t off = row_off(min(sb + grp + u * 32, s_end - 1));
                 kr[u] = ldg_cg16(kbase + off);          // L2-coherent: the newest self-attention row was written by another CTA
                 vr[u] = ldg_cg16(vbase + off);          // in the previous phase (cross K/V are read-only; same L1 bypass)
             }
+        };
+        uint4 kr[MG_ATT_UNROLL], vr[MG_ATT_UNROLL], kn[MG_ATT_UNROLL], vn[MG_ATT_UNROLL];
+        const int sb0 = s_beg + warp * 4;
+        if (sb0 < s_end) issue(sb0, kr, vr);
+        for (int sb = sb0; sb < s_end; sb += 32 * MG_ATT_UNROLL) {   // warp-uniform trip count
+            const bool more = sb + 32 * MG_ATT_UNROLL < s_end;
+            if (more) issue(sb + 32 * MG_ATT_UNROLL, kn, vn);
             float sc[MG_ATT_UNROLL], mb = -INFINITY;
 #pragma unroll
             for (int u = 0; u < MG_ATT_UNROLL; ++u) {
@@ -526,6 +552,10 @@ __device__ __forceinline__ void attention_phase(const MegaParams& p, const bool 
                 for (int i = 0; i < 8; ++i) acc[i] = fmaf(pr, vf[i], acc[i]);
             }
             m_run = m_new;
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < MG_ATT_UNROLL; ++u) { kr[u] = kn[u]; vr[u] = vn[u]; }
+            }
         }
 #pragma unroll
         for (int o = 8; o < 32; o <<= 1) {      // merge the four key groups of the warp
@@ -640,7 +670,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_mega_kernel(const _
     unsigned* item_cnt = p.sync + 32;
     unsigned epoch = 0;
     const int n_phases = 8 * p.n_layers + 1;   // 8 per layer + final LayerNorm / LM head
-    if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[0] = clock64();
+    long long* const trace = (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) ? p.trace : nullptr;
+    if (trace != nullptr) trace[0] = clock64();
 #pragma unroll 1
     for (int ph = 0; ph < n_phases; ++ph) {
         const int l = ph >> 3, k = (ph == n_phases - 1) ? 8 : (ph & 7);
@@ -651,9 +682,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_mega_kernel(const _
         } else {
             LinearPhase lp;
             make_linear_phase(p, l, k, lp);
-            linear_phase<NM>(p, lp, pos, mg_smem);
+            linear_phase<NM>(p, lp, pos, mg_smem, trace != nullptr ? trace + 8 * ph : nullptr);
         }
-        if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[2 * ph + 1] = clock64();
+        if (trace != nullptr) trace[8 * ph + 4] = clock64();
         if (ph + 1 == n_phases) break;
         // arrive at the grid barrier, request what the next phase reads first, then wait for the other CTAs
         grid_arrive(bar);
@@ -667,8 +698,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_mega_kernel(const _
             make_linear_phase(p, l2, k2, np);
             prefetch_linear(p, np);
         }
+        if (trace != nullptr) trace[8 * ph + 5] = clock64();
         grid_wait(bar, epoch);
-        if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[2 * ph + 2] = clock64();
+        if (trace != nullptr) trace[8 * ph + 8] = clock64();   // = slot 0 of the next phase
     }
     // leave the barrier counter at zero for the next launch: the last CTA to get here resets it (nobody polls it any more)
     __syncthreads();
@@ -681,17 +713,29 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_mega_kernel(const _
 
 // rounds x (serial 16-byte loads per lane + fixed per-round cost): smallest wins, ties go to fewer K splits
 GemvCfg pick_gemv_cfg(int N, int K, int grid) {
-    GemvCfg best{8, 1};
+    GemvCfg best{};
     double best_cost = 1e30;
     const int C = K / 32;
     for (int rows16 = 1; rows16 >= 0; --rows16) {
-        for (int ks = 1; ks <= 8; ks *= 2) {
+        for (int ks = 1, shift = 0; ks <= 8; ks *= 2, ++shift) {
             if (C < ks) break;
             const int rt = rows16 ? 16 : 8, tpr = MG_WARPS / ks;
             const int n_tiles = (N + rt - 1) / rt;
-            const int rounds = (n_tiles + grid * tpr - 1) / (grid * tpr);
+            const int stride = grid * tpr;
+            const int rounds = (n_tiles + stride - 1) / stride;
             const double cost = rounds * ((double)((C + ks - 1) / ks) * (rows16 ? 1.0 : 0.5) + 2.0);
-            if (cost < best_cost - 1e-9) { best_cost = cost; best = GemvCfg{ks, rows16}; }
+            if (cost < best_cost - 1e-9) {
+                best_cost = cost;
+                GemvCfg c{};
+                c.ks = ks; c.ks_shift = shift; c.rows16 = rows16; c.C = C;
+                c.cps = rows16 ? 4 : 8;
+                c.nsc = ((C + ks - 1) / ks + c.cps - 1) / c.cps;
+                c.n_tiles = n_tiles; c.tpr = tpr;
+                // CTA c owns tiles (r * grid + c) * tpr + [0, tpr): it has a round r iff (r * grid + c) * tpr < n_tiles
+                c.rounds_base = n_tiles / stride;
+                c.rounds_rem = n_tiles % stride;
+                best = c;
+            }
         }
     }
     return best;
