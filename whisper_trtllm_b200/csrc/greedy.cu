@@ -140,12 +140,33 @@ __global__ void __launch_bounds__(1024) greedy_step_kernel(GreedyArgs a) {
         const int bits = 1 | (n == a.begin_index ? 2 : 0);
         tok = block_masked_argmax(a.logits + (size_t)b * a.ld, a.V, a.vocab_mask, bits);
     }
+    __shared__ int s_tok;
     if (threadIdx.x == 0) {
         const int unf = a.unfinished[b];
         tok = unf ? tok : a.pad_id;
         if (a.forced_tokens != nullptr) tok = a.forced_tokens[(size_t)b * a.tokens_stride + n];
         a.tokens[(size_t)b * a.tokens_stride + n] = tok;
+        s_tok = tok;
         if (tok == a.eos_id) a.unfinished[b] = 0;
+    }
+    if (a.embed_x != nullptr && n < a.tokens_stride) {
+        // embedding of the token just chosen = the input of the NEXT step (position n): x[b, :] = E[tok, :] + P[n, :], so that the
+        // whole-step decoder kernel (step_mega.cu) starts from the residual stream (model.py:423-425)
+        __syncthreads();
+        const int t = s_tok;
+        const bf16* e = reinterpret_cast<const bf16*>(a.embed_table) + (size_t)t * a.embed_d;
+        const bf16* pp = reinterpret_cast<const bf16*>(a.embed_pos) + (size_t)n * a.embed_d;
+        for (int i = threadIdx.x * 8; i < a.embed_d; i += blockDim.x * 8) {
+            float ef[8], pf[8];
+            ld16(e + i).unpack(ef);
+            ld16(pp + i).unpack(pf);
+#pragma unroll
+            for (int j = 0; j < 8; j += 4)
+                *reinterpret_cast<float4*>(a.embed_x + (size_t)b * a.embed_d + i + j) =
+                    make_float4(ef[j] + pf[j], ef[j + 1] + pf[j + 1], ef[j + 2] + pf[j + 2], ef[j + 3] + pf[j + 3]);
+        }
+    }
+    if (threadIdx.x == 0) {
         __threadfence();
         const int prev = atomicAdd(&st->done_counter, 1);
         if (prev == a.B - 1) {  // last row of this step: advance the shared length / stop flag

@@ -267,6 +267,7 @@ size_t layout(Buffers& b, const Model* m, int max_batch, int enc_chunk, void* ba
     c.take(b.state, sizeof(StepState));
     c.take(b.mega_part, mega_part_bytes(max_batch, g.n_heads));
     c.take(b.mega_sync, mega_sync_bytes(max_batch, g.n_heads));
+    c.take(b.mega_table, mega_table_bytes(g.dec_layers));
     return c.off + 1024;
 }
 }  // namespace
@@ -295,6 +296,7 @@ Session::Session(Model* model, int mb, int ec, void* workspace, size_t workspace
     WB_CHECK_CUDA(cudaMemset(h1p, 0, ((size_t)ec * H1_ROWS + 8) * model->cfg.d_model * dtype_size(model->dtype)));
     WB_CHECK_CUDA(cudaMemset(state, 0, sizeof(StepState)));
     WB_CHECK_CUDA(cudaMemset(mega_sync, 0, mega_sync_bytes(mb, model->cfg.n_heads)));
+    build_mega_table();
     WB_CHECK_CUDA(cudaMallocHost(&host_state, sizeof(StepState)));
     std::memset(host_state, 0, sizeof(StepState));
     WB_CHECK_CUDA(cudaEventCreateWithFlags(&check_event, cudaEventDisableTiming));
@@ -478,6 +480,9 @@ void Session::decode_begin(int B, cudaStream_t st) {
     batch = B;
     steps_enqueued = 0;
     greedy_init(tokens, g.max_tgt, unfinished, state, B, g.sot, g.pad, g.max_tgt, st);
+    // the whole-step kernel starts from the residual stream: embedding of the start token here, of every later token by the
+    // greedy kernel of the step that chose it
+    if (use_mega()) decoder_embed(tokens, g.max_tgt, state, m->emb, m->dec_pos, m->dtype, dx, B, g.d_model, st);
 }
 
 // 0 = always the large-batch kernels, 1 = GEMV kernels (8 launches per layer), 2 = one persistent kernel per token (default)
@@ -486,6 +491,11 @@ static int& small_batch_mode() {
     return mode;
 }
 void set_small_batch_path(int mode) { small_batch_mode() = mode; }
+
+bool Session::use_mega() const {
+    const ModelConfig& g = m->cfg;
+    return small_batch_mode() == 2 && get_gemm_backend() == 0 && skinny_gemv_supported(batch, g.d_model, m->dtype) && mega_supported();
+}
 
 // B <= 16 (bf16): weight-streaming GEMV kernels with the LayerNorm fused in front, 8 launches per layer (gemv.cu)
 void Session::decode_step_small(cudaStream_t st) {
@@ -545,7 +555,8 @@ void Session::decode_step(cudaStream_t st) {
     const int d = g.d_model, dt = m->dtype, B = batch;
     const bool small = small_batch_mode() != 0 && get_gemm_backend() == 0 && skinny_gemv_supported(B, d, dt) &&
                        skinny_gemv_supported(B, g.ffn, dt) && d <= 1024;
-    if (small && small_batch_mode() == 2 && mega_supported()) decode_step_mega(st);
+    const bool mega = use_mega();
+    if (mega) decode_step_mega(st);
     else if (small) decode_step_small(st);
     else decode_step_large(st);
     // logits -> processors -> argmax -> EOS / length bookkeeping, common to both paths
@@ -559,6 +570,8 @@ void Session::decode_step(cudaStream_t st) {
         a.pad_id = g.pad; a.eos_id = g.eos; a.max_length = g.max_length;
         a.tokens = tokens; a.tokens_stride = g.max_tgt; a.unfinished = unfinished; a.state = state;
         a.forced_tokens = forced_tokens;
+        // whole-step kernel: the greedy kernel also embeds the token it chose (the next step starts from the residual stream)
+        if (mega) { a.embed_x = dx; a.embed_table = m->emb; a.embed_pos = m->dec_pos; a.embed_d = d; }
         ProfScope ps(this, PROF_GREEDY, st);
         greedy_step(a, st);
     }

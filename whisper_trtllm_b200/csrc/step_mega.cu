@@ -19,6 +19,8 @@
 // position = cur_len - 1 (model.py:423-425), tied LM head without bias (modeling_whisper.py:1335,1433).
 // (tcgen05 needs M = 128 row tiles and a TMEM round trip per phase: at <= 16 rows mma.sync from registers is the right tool.)
 #include <algorithm>
+#include <cstring>
+#include <vector>
 
 #include "wb_runtime.h"
 
@@ -26,42 +28,46 @@ namespace wb {
 
 namespace {
 constexpr int MG_THREADS = 256, MG_WARPS = 8;
-constexpr int MG_MAX_LAYERS = 32, MG_MAX_SPLITS = 16;
+constexpr int MG_MAX_LAYERS = 64, MG_MAX_SPLITS = 16;
 constexpr int MG_PART = 72;          // floats per attention partial: [0] max, [1] sum, [8..72) acc
 constexpr int MG_RS = 20;            // reduction buffer: floats between consecutive utterance rows (bank-conflict free)
 constexpr int MG_RED_BYTES = 2 * MG_WARPS * 16 * MG_RS * 4;   // two parities x 8 warps x 16 rows
 constexpr int MG_ACT_PAD = 32;       // bf16 elements of padding per staged row (row stride = 64 mod 128 bytes)
 constexpr unsigned MG_SPIN_LIMIT = 1u << 26;
-constexpr int MG_ATT_UNROLL = 4;
+constexpr int MG_ATT_UNROLL = 8;
+// linear layers of a decoder layer: tiles of 8 weight rows, K split over the 8 warps of the CTA (one tile per CTA and round);
+// LM head (51864 rows): tiles of 16 rows, one tile per warp, no K split
+constexpr int MG_HEAD_KS = 1, MG_LAYER_KS = 8;
 
-struct MegaLayer {
-    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
-    const bf16 *qkv_w, *out_w, *cq_w, *cout_w, *fc1_w, *fc2_w;
-    const float *qkv_b, *out_b, *cq_b, *cout_b, *fc1_b, *fc2_b;
-    bf16 *self_k, *self_v;
-    const bf16 *cross_k, *cross_v;
-};
+enum { PH_LINEAR = 0, PH_SELF_ATTN = 1, PH_CROSS_ATTN = 2, PH_HEAD = 3 };
+enum { ST_LN_X = 0, ST_COPY = 2 };
+enum { EP_QKV = 0, EP_RESIDUAL = 1, EP_BF16 = 2, EP_GELU_BF16 = 3, EP_F32 = 4 };
 
-// work split of one linear layer over the grid: tiles of 8 or 16 weight rows, K split over `ks` warps of a CTA
-// (everything that needs a division is computed once on the host: the phases are latency-bound instruction streams)
-struct GemvCfg {
-    int ks, ks_shift, rows16;
-    int C;                 // 32-element chunks along K
-    int cps, nsc;          // chunks per super-chunk (8 x 16-byte loads per lane), super-chunks per tile
-    int n_tiles, tpr;      // tiles of 8 / 16 weight rows, tiles per CTA and round
-    int rounds_base, rounds_rem;   // rounds of CTA c = rounds_base + (c * tpr < rounds_rem)
+// One phase of the step.  The table of all 8 * layers + 1 phases is built once per session on the host (everything that needs
+// a division or a pointer chase is resolved there) and lives in global memory; the kernel is an interpreter over it: warp 0
+// copies the NEXT descriptor into shared memory while the CTA waits at the grid barrier.  The phases are latency-bound
+// instruction streams (8 warps per SM, ~5 cycles per dependent instruction): the instruction count per warp on the critical
+// path is what counts, and the whole interpreter has to stay small for the instruction cache (profiles/r01_step_trace_*.md).
+struct alignas(16) PhaseDesc {
+    const bf16* W; const float* bias; const float* gamma; const float* beta;   // linear: weights [N, K], bias, LayerNorm in front
+    const bf16* src; bf16* out_bf16; float* out_f32;                            // rows to copy when there is no LayerNorm; outputs
+    bf16* k_pages; bf16* v_pages;      // qkv epilogue + self-attention: this layer's pages; cross-attention: this layer's K / V
+    int kind, N, K, stage, epi;
+    int nsc;                           // super-chunks (8 x 16-byte loads per lane) per tile
+    int rounds_base, rounds_rem;       // rounds of CTA c = rounds_base + (c * tiles_per_round < rounds_rem)
+    unsigned vpr_rcp;                  // ceil(2^32 / (K / 8)): row of a 16-byte vector without a division
+    int pad[5];
 };
+static_assert(sizeof(PhaseDesc) == 128, "PhaseDesc is copied as 16 x 8 bytes");
 
 struct MegaParams {
-    int M, d, H, ffn, vocab, n_layers, n_ctx, cross_splits, pages_per_seq, tokens_stride;
+    int M, d, H, ffn, vocab, n_phases, n_ctx, cross_splits, pages_per_seq;
     long long cross_bstride;
-    GemvCfg c_qkv, c_dd, c_fc1, c_fc2, c_head;
-    const int* tokens; const StepState* state; const int* unfinished; const int* page_table;
-    const bf16 *emb, *pos; const float *lnf_g, *lnf_b;
-    float* x; bf16 *q, *ctx, *ffn_act; float* logits; float* part;
+    const StepState* state; const int* unfinished; const int* page_table;
+    float* x; bf16 *q, *ctx; float* part;
+    const PhaseDesc* table;
     long long* trace;  // optional (tools/step_trace.py): SM clock stamps of CTA 0, 8 slots per phase (see the kernel body)
     unsigned* sync;    // [0] grid barrier counter, [32 ..) per-item arrival counters; all zero between launches
-    MegaLayer layer[MG_MAX_LAYERS];
 };
 
 __device__ __forceinline__ uint4 ldg_nc16(const void* p) {   // read-only for the whole kernel (weights, cross K/V)
@@ -128,196 +134,109 @@ __device__ __forceinline__ void grid_wait(unsigned* counter, unsigned& epoch) {
 }
 
 // ---- activation staging: the (normalised) rows of all M utterances as bf16 in shared memory, row stride K + MG_ACT_PAD
-// LayerNorm staging, one warp per row (rows m = warp, warp + 8): the 24 loads of a row (x, gamma, beta: 8 float4 each per lane
-// at d = 1024) are all issued before the first use - one round trip - and the statistics need only warp shuffles.  The phases
-// are latency-bound instruction streams (2 warps per scheduler): what counts is the number of instructions per warp on the
-// critical path.  (First version: guarded per-element loop, ptxas serialised the gamma / beta loads into 8 dependent round
-// trips; second version: every thread touched every row - 1300 instructions per warp, 6.4 K cycles, profiles/r01_step_trace*.)
-// Rows come from the fp32 residual stream, or (first layer) straight from the embedding tables: x = E[token] + P[position]
-// with token = ids[m, cur_len - 1] (model.py:423-425); CTA 0 then also writes the residual stream.
-template <bool kFull>   // kFull: d == 1024, every lane owns 8 float4 of the row (no predicates)
-__device__ __forceinline__ void stage_layernorm(const MegaParams& p, bf16* act_s, const float* __restrict__ gamma,
-                                                const float* __restrict__ beta, bool embed, int pos) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int d = p.d, nvec = d >> 2, astride = d + MG_ACT_PAD;
+// ---- activation staging: the (normalised) rows of all M utterances as bf16 in shared memory, row stride K + MG_ACT_PAD
+// LayerNorm: a row is split over the whole CTA (thread t owns float4 t of every row, d <= 1024), the loads of all rows plus
+// gamma / beta are issued together - one round trip - and the statistics go through shared memory; per row that is ~60
+// instructions per warp, and only the rows that exist are computed.  (Earlier versions, profiles/r01_step_trace_*.md: one warp
+// per row with a guarded per-element loop - ptxas serialised the gamma / beta loads into 8 dependent round trips; every thread
+// computing all 8 rows - 1300 instructions per warp; one warp per row with 24 batched loads - 750 instructions on ONE warp.)
+// Rows come from the fp32 residual stream; the embedding of the token that is fed (x = E[token] + P[position], model.py:423-425)
+// was written there by the previous step's greedy kernel (greedy.cu, GreedyArgs::embed_x) or by decode_begin.
+template <int NM>
+__device__ __noinline__ void stage_layernorm(const MegaParams& p, bf16* act_s, float* red_s, const float* __restrict__ gamma,
+                                                const float* __restrict__ beta) {
+    constexpr int MR = 8 * NM;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int d = p.d, nvec = d >> 2, astride = d + MG_ACT_PAD, M = p.M;
+    const bool on = tid < nvec;
     const float inv_d = 1.0f / (float)d;
-    for (int m = warp; m < p.M; m += MG_WARPS) {
-        float4 v[8];
-        if (embed) {
-            const int tok = p.tokens[(size_t)m * p.tokens_stride + pos];
-            const uint2* erow = reinterpret_cast<const uint2*>(p.emb + (size_t)tok * d);
-            const uint2* prow = reinterpret_cast<const uint2*>(p.pos + (size_t)pos * d);
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = g4;
+    if (on) {
+        g4 = __ldg(reinterpret_cast<const float4*>(gamma) + tid);
+        b4 = __ldg(reinterpret_cast<const float4*>(beta) + tid);
+    }
+    float4 v[MR];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int idx = lane + 32 * i;
-                const uint2 e = (kFull || idx < nvec) ? __ldg(erow + idx) : make_uint2(0u, 0u);
-                const uint2 q = (kFull || idx < nvec) ? __ldg(prow + idx) : make_uint2(0u, 0u);
-                v[i].x = __uint_as_float(e.x << 16) + __uint_as_float(q.x << 16);
-                v[i].y = __uint_as_float(e.x & 0xffff0000u) + __uint_as_float(q.x & 0xffff0000u);
-                v[i].z = __uint_as_float(e.y << 16) + __uint_as_float(q.y << 16);
-                v[i].w = __uint_as_float(e.y & 0xffff0000u) + __uint_as_float(q.y & 0xffff0000u);
-            }
-        } else {
+    for (int m = 0; m < MR; ++m) {
+        v[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on && m < M) v[m] = ldg_cg_f4(p.x + (size_t)m * d + tid * 4);
+    }
+    float* rs = red_s;                  // [MR][8] partial sums, then [MR][8] partial sums of squares
+    float* rq = red_s + MR * MG_WARPS;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int idx = lane + 32 * i;
-                v[i] = (kFull || idx < nvec) ? ldg_cg_f4(p.x + (size_t)m * d + idx * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+    for (int m = 0; m < MR; ++m) {
+        if (m < M) {                    // CTA-uniform
+            const float s = warp_sum((v[m].x + v[m].y) + (v[m].z + v[m].w));     // threads past the row hold zeros
+            if (lane == 0) rs[m * MG_WARPS + warp] = s;
         }
-        float s = 0.f;
+    }
+    __syncthreads();
+    float mean[MR];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);      // lanes past the row hold zeros
-        const float mean = warp_sum(s) * inv_d;
-        float ss = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (kFull || lane + 32 * i < nvec) {
-                const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
-                ss += (a * a + b * b) + (c * c + e * e);
-            }
+    for (int m = 0; m < MR; ++m) {
+        if (m < M) {
+            const float4 a = *reinterpret_cast<const float4*>(rs + m * MG_WARPS), b = *reinterpret_cast<const float4*>(rs + m * MG_WARPS + 4);
+            mean[m] = (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) * inv_d;
+            const float c0 = v[m].x - mean[m], c1 = v[m].y - mean[m], c2 = v[m].z - mean[m], c3 = v[m].w - mean[m];
+            const float ss = warp_sum(on ? (c0 * c0 + c1 * c1) + (c2 * c2 + c3 * c3) : 0.f);
+            if (lane == 0) rq[m * MG_WARPS + warp] = ss;
         }
-        const float rstd = rsqrtf(warp_sum(ss) * inv_d + 1e-5f);
-        // gamma / beta were requested into L2 before the grid barrier: two half-batches of 8 loads (an L2 round trip each) keep
-        // the register peak at v[8] + 8 float4 next to the weight tile that is already in flight
+    }
+    __syncthreads();
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float4 g4[4], b4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int idx = lane + 32 * (half * 4 + j);
-                g4[j] = (kFull || idx < nvec) ? __ldg(reinterpret_cast<const float4*>(gamma) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-                b4[j] = (kFull || idx < nvec) ? __ldg(reinterpret_cast<const float4*>(beta) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = half * 4 + j, idx = lane + 32 * i;
-                if (kFull || idx < nvec) {
-                    if (embed && blockIdx.x == 0) *reinterpret_cast<float4*>(p.x + (size_t)m * d + idx * 4) = v[i];
-                    __nv_bfloat162 p0 = __floats2bfloat162_rn((v[i].x - mean) * rstd * g4[j].x + b4[j].x, (v[i].y - mean) * rstd * g4[j].y + b4[j].y);
-                    __nv_bfloat162 p1 = __floats2bfloat162_rn((v[i].z - mean) * rstd * g4[j].z + b4[j].z, (v[i].w - mean) * rstd * g4[j].w + b4[j].w);
-                    uint2 u;
-                    u.x = *reinterpret_cast<uint32_t*>(&p0);
-                    u.y = *reinterpret_cast<uint32_t*>(&p1);
-                    *reinterpret_cast<uint2*>(act_s + (size_t)m * astride + idx * 4) = u;
-                }
+    for (int m = 0; m < MR; ++m) {
+        if (m < M) {
+            const float4 a = *reinterpret_cast<const float4*>(rq + m * MG_WARPS), b = *reinterpret_cast<const float4*>(rq + m * MG_WARPS + 4);
+            const float rstd = rsqrtf((((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) * inv_d + 1e-5f);
+            if (on) {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn((v[m].x - mean[m]) * rstd * g4.x + b4.x, (v[m].y - mean[m]) * rstd * g4.y + b4.y);
+                __nv_bfloat162 p1 = __floats2bfloat162_rn((v[m].z - mean[m]) * rstd * g4.z + b4.z, (v[m].w - mean[m]) * rstd * g4.w + b4.w);
+                uint2 u;
+                u.x = *reinterpret_cast<uint32_t*>(&p0);
+                u.y = *reinterpret_cast<uint32_t*>(&p1);
+                *reinterpret_cast<uint2*>(act_s + (size_t)m * astride + tid * 4) = u;
             }
         }
     }
 }
 
-// bf16 rows of the previous phase -> shared memory; 8 independent 16-byte requests per thread and trip
-__device__ __forceinline__ void stage_copy(bf16* act_s, const bf16* src, int M, int K) {
+// bf16 rows of the previous phase -> shared memory; the requests of a thread are issued together (no clamped duplicates:
+// 148 SMs x 256 threads asking for one line serialise in its L2 slice)
+__device__ __noinline__ void stage_copy(bf16* act_s, const bf16* src, int M, int K, unsigned vpr_rcp) {
     const int vpr = K >> 3, astride = K + MG_ACT_PAD, total = M * vpr;
     for (int base = 0; base < total; base += MG_THREADS * 8) {
         uint4 r[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int i = base + u * MG_THREADS + (int)threadIdx.x;   // no clamped duplicates: 148 SMs x 256 threads asking for one
-            r[u] = i < total ? ldg_cg16(src + (size_t)i * 8) : make_uint4(0, 0, 0, 0);   // line serialise in its L2 slice
+            const int i = base + u * MG_THREADS + (int)threadIdx.x;
+            r[u] = make_uint4(0, 0, 0, 0);
+            if (i < total) r[u] = ldg_cg16(src + (size_t)i * 8);      // rows are contiguous: element offset = i * 8
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = base + u * MG_THREADS + (int)threadIdx.x;
             if (i < total) {
-                const int m = i / vpr, j = i - m * vpr;
+                const int m = (int)__umulhi((unsigned)i, vpr_rcp), j = i - m * vpr;   // vpr_rcp = ceil(2^32 / vpr), exact for i < 2^16
                 *reinterpret_cast<uint4*>(act_s + (size_t)m * astride + j * 8) = r[u];
             }
         }
     }
 }
 
-// ---- geometry of one linear layer on this CTA / warp
-struct GemvGeom {
-    int rt_shift, rt, tpr, tl, ks_id, c0, c1, cps, nsc, rounds;
-    __device__ __forceinline__ GemvGeom(const GemvCfg& cfg) {
-        const int warp = threadIdx.x >> 5;
-        rt_shift = cfg.rows16 ? 4 : 3;
-        rt = 1 << rt_shift;
-        tpr = cfg.tpr;
-        tl = warp >> cfg.ks_shift;
-        ks_id = warp & (cfg.ks - 1);
-        c0 = (ks_id * cfg.C) >> cfg.ks_shift;
-        c1 = ((ks_id + 1) * cfg.C) >> cfg.ks_shift;
-        cps = cfg.cps;
-        nsc = cfg.nsc;
-        rounds = cfg.rounds_base + ((int)blockIdx.x * tpr < cfg.rounds_rem ? 1 : 0);
-    }
-    __device__ __forceinline__ int tile_of(int r, int t_local) const { return (r * (int)gridDim.x + (int)blockIdx.x) * tpr + t_local; }
-};
-
-// One linear layer of the step, described at run time.  The kernel body is a small interpreter over these descriptors with ONE
-// copy of the linear-layer code and one of each attention flavour: the whole step has to stay inside the instruction cache
-// (a first version that inlined the eight phases of a layer was 20 K instructions per layer iteration and ran 1.6x SLOWER
-// than the multi-kernel path: every phase was an instruction-cache miss streak).
-enum { ST_LN_X = 0, ST_LN_EMBED = 1, ST_COPY = 2 };
-enum { EP_QKV = 0, EP_RESIDUAL = 1, EP_BF16 = 2, EP_GELU_BF16 = 3, EP_F32 = 4 };
-struct LinearPhase {
-    const bf16* W; const float* bias; int N, K; GemvCfg cfg;
-    int stage; const float *gamma, *beta; const bf16* src;      // LayerNorm parameters / bf16 rows to copy
-    int epi; bf16* out_bf16; float* out_f32; bf16 *k_pages, *v_pages;
-};
-
-// phase k of layer l: 0 LN1+qkv, 2 out-proj, 3 LN2+cross-q, 5 cross-out, 6 LN3+fc1, 7 fc2, 8 final LN + LM head
-__device__ __forceinline__ void make_linear_phase(const MegaParams& p, int l, int k, LinearPhase& o) {
-    const MegaLayer& L = p.layer[l < p.n_layers ? l : 0];
-    o.src = nullptr; o.gamma = nullptr; o.beta = nullptr; o.out_bf16 = nullptr; o.out_f32 = nullptr; o.k_pages = nullptr; o.v_pages = nullptr;
-    o.K = p.d; o.N = p.d; o.cfg = p.c_dd; o.stage = ST_LN_X; o.epi = EP_RESIDUAL;
-    switch (k) {
-        case 0:
-            o.W = L.qkv_w; o.bias = L.qkv_b; o.N = 3 * p.d; o.cfg = p.c_qkv; o.stage = l == 0 ? ST_LN_EMBED : ST_LN_X;
-            o.gamma = L.ln1_g; o.beta = L.ln1_b; o.epi = EP_QKV; o.out_bf16 = p.q; o.k_pages = L.self_k; o.v_pages = L.self_v;
-            break;
-        case 2: o.W = L.out_w; o.bias = L.out_b; o.stage = ST_COPY; o.src = p.ctx; break;
-        case 3:
-            o.W = L.cq_w; o.bias = L.cq_b; o.gamma = L.ln2_g; o.beta = L.ln2_b; o.epi = EP_BF16; o.out_bf16 = p.q;
-            break;
-        case 5: o.W = L.cout_w; o.bias = L.cout_b; o.stage = ST_COPY; o.src = p.ctx; break;
-        case 6:
-            o.W = L.fc1_w; o.bias = L.fc1_b; o.N = p.ffn; o.cfg = p.c_fc1; o.gamma = L.ln3_g; o.beta = L.ln3_b;
-            o.epi = EP_GELU_BF16; o.out_bf16 = p.ffn_act;
-            break;
-        case 7: o.W = L.fc2_w; o.bias = L.fc2_b; o.K = p.ffn; o.cfg = p.c_fc2; o.stage = ST_COPY; o.src = p.ffn_act; break;
-        default:
-            o.W = p.emb; o.bias = nullptr; o.N = p.vocab; o.cfg = p.c_head; o.gamma = p.lnf_g; o.beta = p.lnf_b;
-            o.epi = EP_F32; o.out_f32 = p.logits;
-            break;
-    }
-}
-
-// request what the next linear layer reads first into L2: this warp's first weight tile, the LayerNorm parameters, the bias
-// of the tile (issued between the arrival at the grid barrier and the wait: none of it depends on the other CTAs)
-__device__ __forceinline__ void prefetch_linear(const MegaParams& p, const LinearPhase& ph) {
-    const GemvGeom gm(ph.cfg);
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (ph.gamma != nullptr) {
-        const int lines = p.d >> 5;                   // 128-byte lines per fp32 vector of d elements (<= 32)
-        if (tid < lines) prefetch_l2(ph.gamma + tid * 32);
-        else if (tid < 2 * lines) prefetch_l2(ph.beta + (tid - lines) * 32);
-    }
-    if (gm.rounds == 0) return;
-    const int n0 = gm.tile_of(0, gm.tl) << gm.rt_shift;
-    if (ph.bias != nullptr && lane == 31) prefetch_l2(ph.bias + min(n0, ph.N - 1));
-    const int lines = ((gm.c1 - gm.c0) * 64 + 127) >> 7;      // <= 32 for K <= 4096
-    if (lane < lines) {
-        const bf16* base = ph.W + gm.c0 * 32 + lane * 64;
-        for (int r = 0; r < gm.rt; ++r) prefetch_l2(base + (size_t)min(n0 + r, ph.N - 1) * ph.K);
-    }
-}
-
 // called exactly once per output element (n, m) by exactly one thread of the grid
-__device__ __forceinline__ void linear_epilogue(const MegaParams& p, const LinearPhase& ph, int pos, int n, int m, float v) {
-    if (n >= ph.N || m >= p.M) return;
-    if (ph.bias != nullptr) v += __ldg(ph.bias + n);
+__device__ __forceinline__ void linear_epilogue(const MegaParams& p, const PhaseDesc& D, int pos, int n, int m, float v) {
+    if (n >= D.N || m >= p.M) return;
+    if (D.bias != nullptr) v += __ldg(D.bias + n);
     const int d = p.d;
-    switch (ph.epi) {
+    switch (D.epi) {
         case EP_QKV: {   // q -> activation buffer; k / v rows straight into the paged cache at slot cur_len - 1
             const int which = (n >= d ? 1 : 0) + (n >= 2 * d ? 1 : 0), c = n - which * d;
             if (which == 0) {
-                ph.out_bf16[(size_t)m * d + c] = __float2bfloat16_rn(v);
+                D.out_bf16[(size_t)m * d + c] = __float2bfloat16_rn(v);
             } else {
                 const int page = p.page_table[(size_t)m * p.pages_per_seq + (pos >> 6)];
                 const size_t off = (((size_t)page * p.H + (c >> 6)) * 64 + (pos & 63)) * 64 + (c & 63);
-                (which == 1 ? ph.k_pages : ph.v_pages)[off] = __float2bfloat16_rn(v);
+                (which == 1 ? D.k_pages : D.v_pages)[off] = __float2bfloat16_rn(v);
             }
             break;
         }
@@ -326,67 +245,64 @@ __device__ __forceinline__ void linear_epilogue(const MegaParams& p, const Linea
             *xp = ldg_cg_f(xp) + v;
             break;
         }
-        case EP_BF16: ph.out_bf16[(size_t)m * ph.N + n] = __float2bfloat16_rn(v); break;
-        case EP_GELU_BF16: ph.out_bf16[(size_t)m * ph.N + n] = __float2bfloat16_rn(gelu_erf_fast(v)); break;
-        default: ph.out_f32[(size_t)m * ph.N + n] = v; break;
+        case EP_BF16: D.out_bf16[(size_t)m * D.N + n] = __float2bfloat16_rn(v); break;
+        case EP_GELU_BF16: D.out_bf16[(size_t)m * D.N + n] = __float2bfloat16_rn(gelu_erf_fast(v)); break;
+        default: D.out_f32[(size_t)m * D.N + n] = v; break;
     }
 }
 
-// out[m, n] = epilogue( sum_k act[m, k] * W[n, k] ) for all n < N, m < 8 * NM
-template <int NM>
-__device__ __forceinline__ void linear_phase(const MegaParams& p, const LinearPhase& ph, int pos, uint8_t* smem, long long* tr) {
+// out[m, n] = epilogue( sum_k act[m, k] * W[n, k] ) for all n < N, m < 8 * NM.
+// KS warps split K for one tile of RT = 8 / 16 weight rows; a CTA works on 8 / KS tiles per round; tiles (r * grid + cta) * TPR + ..
+template <int NM, int KS, bool R16>
+__device__ __forceinline__ void linear_phase(const MegaParams& p, const PhaseDesc& D, int pos, uint8_t* smem, long long* tr) {
+    constexpr int TPR = MG_WARPS / KS, RT_SHIFT = R16 ? 4 : 3, RT = 1 << RT_SHIFT, CPS = R16 ? 4 : 8;
     float* red_s = reinterpret_cast<float*>(smem);
     bf16* act_s = reinterpret_cast<bf16*>(smem + MG_RED_BYTES);
-    const bf16* __restrict__ W = ph.W;
-    const int N = ph.N, K = ph.K;
-    const GemvCfg cfg = ph.cfg;
-    const int astride = K + MG_ACT_PAD;
+    const bf16* __restrict__ W = D.W;
+    const int N = D.N, K = D.K, C = K >> 5, astride = K + MG_ACT_PAD, nsc = D.nsc;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
-    const GemvGeom gm(cfg);
-    const int total = gm.rounds * gm.nsc;
-    const bool rows16 = cfg.rows16 != 0;
+    const int tl = warp / KS, ks_id = warp % KS;
+    const int c0 = (ks_id * C) / KS, c1 = ((ks_id + 1) * C) / KS;
+    const int rounds = D.rounds_base + ((int)blockIdx.x * TPR < D.rounds_rem ? 1 : 0);
+    const int total = rounds * nsc;
+    auto tile_of = [&](int r, int t_local) { return (r * (int)gridDim.x + (int)blockIdx.x) * TPR + t_local; };
 
     // (r, sc) = (round, super-chunk) of the tile being requested / computed; advanced incrementally, no divisions
-    auto issue = [&](int idx, int r, int sc, uint4(&buf)[8]) __attribute__((always_inline)) {
-        const int n0 = gm.tile_of(r, gm.tl) << gm.rt_shift;
+    auto issue = [&](int r, int sc, uint4(&buf)[8]) __attribute__((always_inline)) {
+        const int n0 = tile_of(r, tl) << RT_SHIFT;
         const bf16* pa = W + (size_t)min(n0 + g, N - 1) * K + tq * 8;
-        if (rows16) {
+        if constexpr (R16) {
             const bf16* pb = W + (size_t)min(n0 + g + 8, N - 1) * K + tq * 8;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int chunk = gm.c0 + sc * 4 + j;
-                const bool in = chunk < gm.c1;
-                buf[2 * j] = in ? ldg_nc16(pa + chunk * 32) : make_uint4(0, 0, 0, 0);
-                buf[2 * j + 1] = in ? ldg_nc16(pb + chunk * 32) : make_uint4(0, 0, 0, 0);
+                const int chunk = c0 + sc * 4 + j;
+                buf[2 * j] = make_uint4(0, 0, 0, 0);
+                buf[2 * j + 1] = make_uint4(0, 0, 0, 0);
+                if (chunk < c1) {
+                    buf[2 * j] = ldg_nc16(pa + chunk * 32);
+                    buf[2 * j + 1] = ldg_nc16(pb + chunk * 32);
+                }
             }
         } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int chunk = gm.c0 + sc * 8 + j;
-                buf[j] = chunk < gm.c1 ? ldg_nc16(pa + chunk * 32) : make_uint4(0, 0, 0, 0);
+                const int chunk = c0 + sc * 8 + j;
+                buf[j] = make_uint4(0, 0, 0, 0);
+                if (chunk < c1) buf[j] = ldg_nc16(pa + chunk * 32);
             }
-        }
-        if (idx + 3 < total) {   // keep the stream ahead of the two register buffers: one L2 prefetch per lane, 3 super-chunks on
-            int r3 = r, sc3 = sc + 3;
-            while (sc3 >= gm.nsc) { sc3 -= gm.nsc; ++r3; }
-            const int n3 = gm.tile_of(r3, gm.tl) << gm.rt_shift;
-            const int row = rows16 ? lane >> 1 : lane >> 2, line = rows16 ? lane & 1 : lane & 3;   // 256 / 512 bytes per row
-            const int chunk = gm.c0 + sc3 * gm.cps + line * 2;
-            if (chunk < gm.c1) prefetch_l2(W + (size_t)min(n3 + row, N - 1) * K + chunk * 32);
         }
     };
 
     float acc[NM][4];
     auto finish = [&](int r) __attribute__((always_inline)) {
-        const int n0 = gm.tile_of(r, gm.tl) << gm.rt_shift;
-        if (cfg.ks == 1) {
+        if constexpr (KS == 1) {
+            const int n0 = tile_of(r, tl) << RT_SHIFT;
 #pragma unroll
             for (int mb = 0; mb < NM; ++mb) {
-                linear_epilogue(p, ph, pos, n0 + g, mb * 8 + 2 * tq, acc[mb][0]);
-                linear_epilogue(p, ph, pos, n0 + g, mb * 8 + 2 * tq + 1, acc[mb][1]);
-                if (rows16) {
-                    linear_epilogue(p, ph, pos, n0 + g + 8, mb * 8 + 2 * tq, acc[mb][2]);
-                    linear_epilogue(p, ph, pos, n0 + g + 8, mb * 8 + 2 * tq + 1, acc[mb][3]);
+#pragma unroll 1
+                for (int e = 0; e < (R16 ? 4 : 2); ++e) {   // rolled: one copy of the epilogue code
+                    const float v = e == 0 ? acc[mb][0] : e == 1 ? acc[mb][1] : e == 2 ? acc[mb][2] : acc[mb][3];
+                    linear_epilogue(p, D, pos, n0 + g + (e >> 1) * 8, mb * 8 + 2 * tq + (e & 1), v);
                 }
             }
         } else {
@@ -396,20 +312,24 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const LinearPh
             for (int mb = 0; mb < NM; ++mb) {
                 rw[(mb * 8 + 2 * tq) * MG_RS + g] = acc[mb][0];
                 rw[(mb * 8 + 2 * tq + 1) * MG_RS + g] = acc[mb][1];
-                rw[(mb * 8 + 2 * tq) * MG_RS + g + 8] = acc[mb][2];
-                rw[(mb * 8 + 2 * tq + 1) * MG_RS + g + 8] = acc[mb][3];
+                if constexpr (R16) {
+                    rw[(mb * 8 + 2 * tq) * MG_RS + g + 8] = acc[mb][2];
+                    rw[(mb * 8 + 2 * tq + 1) * MG_RS + g + 8] = acc[mb][3];
+                }
             }
             __syncthreads();
-            const int m_cnt = 8 * NM;
-            const int outs = (gm.tpr * m_cnt) << gm.rt_shift;
-            for (int o = tid; o < outs; o += MG_THREADS) {
-                const int n_l = o & (gm.rt - 1);
-                const int rest = o >> gm.rt_shift;
-                const int m = rest % m_cnt, t2 = rest / m_cnt;
-                const float* rr = red_s + ((r & 1) * MG_WARPS + t2 * cfg.ks) * WSTRIDE + m * MG_RS + n_l;
-                float v = 0.f;
-                for (int k = 0; k < cfg.ks; ++k) v += rr[k * WSTRIDE];     // fixed order: deterministic
-                linear_epilogue(p, ph, pos, (gm.tile_of(r, t2) << gm.rt_shift) + n_l, m, v);
+            constexpr int M_CNT = 8 * NM, OUTS = TPR * M_CNT * RT;
+#pragma unroll
+            for (int o0 = 0; o0 < OUTS; o0 += MG_THREADS) {
+                const int o = o0 + tid;
+                if (OUTS % MG_THREADS == 0 || o < OUTS) {
+                    const int n_l = o & (RT - 1), rest = o >> RT_SHIFT, m = rest % M_CNT, t2 = rest / M_CNT;
+                    const float* rr = red_s + ((r & 1) * MG_WARPS + t2 * KS) * WSTRIDE + m * MG_RS + n_l;
+                    float v = 0.f;
+#pragma unroll
+                    for (int k = 0; k < KS; ++k) v += rr[k * WSTRIDE];     // fixed order: deterministic
+                    linear_epilogue(p, D, pos, (tile_of(r, t2) << RT_SHIFT) + n_l, m, v);
+                }
             }
         }
     };
@@ -422,43 +342,32 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const LinearPh
         }
         const bf16* arow = act_s + (size_t)g * astride + tq * 8;
         // K is permuted identically in both operands: lane tq supplies elements [8 tq, 8 tq + 8) of every 32-element chunk
-        if (rows16) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int chunk = gm.c0 + sc * 4 + j;
-                if (chunk < gm.c1) {   // warp-uniform
+        for (int j = 0; j < CPS; ++j) {
+            const int chunk = c0 + sc * CPS + j;
+            if (chunk < c1) {   // warp-uniform
 #pragma unroll
-                    for (int mb = 0; mb < NM; ++mb) {
-                        const uint4 a = *reinterpret_cast<const uint4*>(arow + (size_t)mb * 8 * astride + chunk * 32);
+                for (int mb = 0; mb < NM; ++mb) {
+                    const uint4 a = *reinterpret_cast<const uint4*>(arow + (size_t)mb * 8 * astride + chunk * 32);
+                    if constexpr (R16) {
                         mma_16816(acc[mb], buf[2 * j].x, buf[2 * j + 1].x, buf[2 * j].y, buf[2 * j + 1].y, a.x, a.y);
                         mma_16816(acc[mb], buf[2 * j].z, buf[2 * j + 1].z, buf[2 * j].w, buf[2 * j + 1].w, a.z, a.w);
-                    }
-                }
-            }
-        } else {               // 8-row tiles: MMA rows 8..15 are zero
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int chunk = gm.c0 + sc * 8 + j;
-                if (chunk < gm.c1) {
-#pragma unroll
-                    for (int mb = 0; mb < NM; ++mb) {
-                        const uint4 a = *reinterpret_cast<const uint4*>(arow + (size_t)mb * 8 * astride + chunk * 32);
+                    } else {       // 8-row tiles: MMA rows 8..15 are zero
                         mma_16816(acc[mb], buf[j].x, 0u, buf[j].y, 0u, a.x, a.y);
                         mma_16816(acc[mb], buf[j].z, 0u, buf[j].w, 0u, a.z, a.w);
                     }
                 }
             }
         }
-        if (sc == gm.nsc - 1) finish(r);
+        if (sc == nsc - 1) finish(r);
     };
 
     uint4 cur[8], nxt[8];
     if (total > 0) {
-        issue(0, 0, 0, cur);     // in flight while the activations are staged
+        issue(0, 0, cur);     // in flight while the activations are staged
         if (tr != nullptr) tr[1] = clock64();
-        if (ph.stage == ST_COPY) stage_copy(act_s, ph.src, p.M, K);
-        else if (p.d == 1024) stage_layernorm<true>(p, act_s, ph.gamma, ph.beta, ph.stage == ST_LN_EMBED, pos);
-        else stage_layernorm<false>(p, act_s, ph.gamma, ph.beta, ph.stage == ST_LN_EMBED, pos);
+        if (D.stage == ST_COPY) stage_copy(act_s, D.src, p.M, K, D.vpr_rcp);
+        else stage_layernorm<NM>(p, act_s, red_s, D.gamma, D.beta);
     }
     if (tr != nullptr) tr[2] = clock64();
     __syncthreads();
@@ -467,8 +376,8 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const LinearPh
 #pragma unroll 1
     for (int idx = 0; idx < total; ++idx) {   // trip counts are CTA-uniform (finish() contains a block barrier)
         int r1 = r, sc1 = sc + 1;
-        if (sc1 == gm.nsc) { sc1 = 0; ++r1; }
-        if (idx + 1 < total) issue(idx + 1, r1, sc1, nxt);
+        if (sc1 == nsc) { sc1 = 0; ++r1; }
+        if (idx + 1 < total) issue(r1, sc1, nxt);
         compute(r, sc, cur);
 #pragma unroll
         for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
@@ -506,22 +415,14 @@ __device__ __forceinline__ void attention_phase(const MegaParams& p, const bool 
         float m_run = -INFINITY, l_run = 0.f, acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        // software pipeline: the 16 requests per lane of batch i + 1 are in flight while batch i is reduced (one CTA per SM
-        // and 8 warps in lock step: without it the SM alternates between waiting for HBM and computing, 13 B/clk)
-        auto issue = [&](int sb, uint4(&kr)[MG_ATT_UNROLL], uint4(&vr)[MG_ATT_UNROLL]) __attribute__((always_inline)) {
+        for (int sb = s_beg + warp * 4; sb < s_end; sb += 32 * MG_ATT_UNROLL) {   // warp-uniform trip count
+            uint4 kr[MG_ATT_UNROLL], vr[MG_ATT_UNROLL];
 #pragma unroll
             for (int u = 0; u < MG_ATT_UNROLL; ++u) {
                 const size_t off = row_off(min(sb + grp + u * 32, s_end - 1));
                 kr[u] = ldg_cg16(kbase + off);          // L2-coherent: the newest self-attention row was written by another CTA
                 vr[u] = ldg_cg16(vbase + off);          // in the previous phase (cross K/V are read-only; same L1 bypass)
             }
-        };
-        uint4 kr[MG_ATT_UNROLL], vr[MG_ATT_UNROLL], kn[MG_ATT_UNROLL], vn[MG_ATT_UNROLL];
-        const int sb0 = s_beg + warp * 4;
-        if (sb0 < s_end) issue(sb0, kr, vr);
-        for (int sb = sb0; sb < s_end; sb += 32 * MG_ATT_UNROLL) {   // warp-uniform trip count
-            const bool more = sb + 32 * MG_ATT_UNROLL < s_end;
-            if (more) issue(sb + 32 * MG_ATT_UNROLL, kn, vn);
             float sc[MG_ATT_UNROLL], mb = -INFINITY;
 #pragma unroll
             for (int u = 0; u < MG_ATT_UNROLL; ++u) {
@@ -552,10 +453,6 @@ __device__ __forceinline__ void attention_phase(const MegaParams& p, const bool 
                 for (int i = 0; i < 8; ++i) acc[i] = fmaf(pr, vf[i], acc[i]);
             }
             m_run = m_new;
-            if (more) {
-#pragma unroll
-                for (int u = 0; u < MG_ATT_UNROLL; ++u) { kr[u] = kn[u]; vr[u] = vn[u]; }
-            }
         }
 #pragma unroll
         for (int o = 8; o < 32; o <<= 1) {      // merge the four key groups of the warp
@@ -634,7 +531,34 @@ __device__ __forceinline__ void attention_phase(const MegaParams& p, const bool 
     }
 }
 
-// request the first cross-attention unit of this CTA into L2 (before the barrier in front of the phase)
+// ---- requests for what the NEXT phase reads first, issued between the arrival at the grid barrier and the wait (none of it
+// depends on the other CTAs): the first weight tile of this warp, LayerNorm parameters, bias; the first attention unit
+__device__ __forceinline__ void prefetch_linear(const MegaParams& p, const PhaseDesc* nd, int kind) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bf16* W = nd->W;
+    const float* gamma = nd->gamma;
+    const float* beta = nd->beta;
+    const float* bias = nd->bias;
+    const int N = nd->N, K = nd->K, C = K >> 5;
+    if (gamma != nullptr) {
+        const int lines = p.d >> 5;                   // 128-byte lines per fp32 vector of d elements (<= 32)
+        if (tid < lines) prefetch_l2(gamma + tid * 32);
+        else if (tid < 2 * lines) prefetch_l2(beta + (tid - lines) * 32);
+    }
+    const bool head = kind == PH_HEAD;
+    const int ks_shift = head ? 0 : 3, rt = head ? 16 : 8, tpr = MG_WARPS >> ks_shift;
+    const int tl = warp >> ks_shift, ks_id = warp & ((1 << ks_shift) - 1);
+    const int c0 = (ks_id * C) >> ks_shift, c1 = ((ks_id + 1) * C) >> ks_shift;
+    const int n0 = ((int)blockIdx.x * tpr + tl) * rt;
+    if (n0 >= N) return;
+    if (bias != nullptr && lane == 31) prefetch_l2(bias + n0);
+    const int lines = ((c1 - c0) * 64 + 127) >> 7;      // <= 32 for K <= 4096
+    if (lane < lines) {
+        const bf16* base = W + c0 * 32 + lane * 64;
+        for (int r = 0; r < rt; ++r) prefetch_l2(base + (size_t)min(n0 + r, N - 1) * K);
+    }
+}
+
 __device__ __forceinline__ void prefetch_cross(const MegaParams& p, const bf16* kbase, const bf16* vbase) {
     const int splits = p.cross_splits, units = p.M * p.H * splits;
     const int unit = blockIdx.x;
@@ -648,7 +572,7 @@ __device__ __forceinline__ void prefetch_cross(const MegaParams& p, const bf16* 
     }
 }
 
-// same for the first self-attention item of this CTA (pages of utterance b, head h; the newest row is still being written)
+// pages of utterance b, head h (the newest row is still being written)
 __device__ __forceinline__ void prefetch_self(const MegaParams& p, const bf16* kbase, const bf16* vbase, int n_keys) {
     const int item = blockIdx.x;
     if (item >= p.M * p.H) return;
@@ -664,81 +588,52 @@ __device__ __forceinline__ void prefetch_self(const MegaParams& p, const bf16* k
 template <int NM>
 __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_mega_kernel(const __grid_constant__ MegaParams p) {
     extern __shared__ __align__(128) uint8_t mg_smem[];
+    __shared__ __align__(16) PhaseDesc sdesc[2];
     if (p.state->active == 0) return;          // the loop has stopped: grid-uniform, nobody touches the barrier
     const int cur_len = p.state->cur_len, pos = cur_len - 1;
+    const int tid = threadIdx.x;
     unsigned* bar = p.sync;
     unsigned* item_cnt = p.sync + 32;
     unsigned epoch = 0;
-    const int n_phases = 8 * p.n_layers + 1;   // 8 per layer + final LayerNorm / LM head
-    long long* const trace = (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) ? p.trace : nullptr;
+    const int n_phases = p.n_phases;           // 8 per layer + final LayerNorm / LM head
+    long long* const trace = (p.trace != nullptr && blockIdx.x == 0 && tid == 0) ? p.trace : nullptr;
+    if (tid < 16) reinterpret_cast<unsigned long long*>(&sdesc[0])[tid] = reinterpret_cast<const unsigned long long*>(p.table)[tid];
+    __syncthreads();
     if (trace != nullptr) trace[0] = clock64();
 #pragma unroll 1
     for (int ph = 0; ph < n_phases; ++ph) {
-        const int l = ph >> 3, k = (ph == n_phases - 1) ? 8 : (ph & 7);
-        if (k == 1) {          // cached self-attention over cur_len keys (the newest row was appended by phase 0's epilogue)
-            attention_phase(p, true, p.layer[l].self_k, p.layer[l].self_v, cur_len, 1, mg_smem, item_cnt);
-        } else if (k == 4) {   // cross-attention over the encoder K/V projected once per utterance
-            attention_phase(p, false, p.layer[l].cross_k, p.layer[l].cross_v, p.n_ctx, p.cross_splits, mg_smem, item_cnt);
+        const PhaseDesc& D = sdesc[ph & 1];
+        const int kind = D.kind;
+        if (kind == PH_LINEAR) {
+            linear_phase<NM, MG_LAYER_KS, false>(p, D, pos, mg_smem, trace != nullptr ? trace + 8 * ph : nullptr);
+        } else if (kind == PH_HEAD) {
+            linear_phase<NM, MG_HEAD_KS, true>(p, D, pos, mg_smem, trace != nullptr ? trace + 8 * ph : nullptr);
         } else {
-            LinearPhase lp;
-            make_linear_phase(p, l, k, lp);
-            linear_phase<NM>(p, lp, pos, mg_smem, trace != nullptr ? trace + 8 * ph : nullptr);
+            // cached self-attention over cur_len keys (newest row appended by the qkv epilogue) / cross-attention over the encoder
+            // K/V projected once per utterance; ONE call site = one copy of the code
+            const bool self = kind == PH_SELF_ATTN;
+            attention_phase(p, self, D.k_pages, D.v_pages, self ? cur_len : p.n_ctx, self ? 1 : p.cross_splits, mg_smem, item_cnt);
         }
         if (trace != nullptr) trace[8 * ph + 4] = clock64();
         if (ph + 1 == n_phases) break;
-        // arrive at the grid barrier, request what the next phase reads first, then wait for the other CTAs
+        // arrive at the grid barrier, fetch the next descriptor and request what the next phase reads first, then wait
         grid_arrive(bar);
-        const int l2 = (ph + 1) >> 3, k2 = (ph + 2 == n_phases) ? 8 : ((ph + 1) & 7);
-        if (k2 == 4) {
-            prefetch_cross(p, p.layer[l2].cross_k, p.layer[l2].cross_v);
-        } else if (k2 == 1) {
-            prefetch_self(p, p.layer[l2].self_k, p.layer[l2].self_v, cur_len);
-        } else {
-            LinearPhase np;
-            make_linear_phase(p, l2, k2, np);
-            prefetch_linear(p, np);
-        }
+        const PhaseDesc* nd = p.table + ph + 1;
+        if (tid < 16) reinterpret_cast<unsigned long long*>(&sdesc[(ph + 1) & 1])[tid] = reinterpret_cast<const unsigned long long*>(nd)[tid];
+        const int k2 = nd->kind;
+        if (k2 == PH_CROSS_ATTN) prefetch_cross(p, nd->k_pages, nd->v_pages);
+        else if (k2 == PH_SELF_ATTN) prefetch_self(p, nd->k_pages, nd->v_pages, cur_len);
+        else prefetch_linear(p, nd, k2);
         if (trace != nullptr) trace[8 * ph + 5] = clock64();
         grid_wait(bar, epoch);
         if (trace != nullptr) trace[8 * ph + 8] = clock64();   // = slot 0 of the next phase
     }
     // leave the barrier counter at zero for the next launch: the last CTA to get here resets it (nobody polls it any more)
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         const unsigned old = atomicAdd(bar, 1u);
         if (old == epoch + gridDim.x - 1) atomicExch(bar, 0u);
     }
-}
-
-
-// rounds x (serial 16-byte loads per lane + fixed per-round cost): smallest wins, ties go to fewer K splits
-GemvCfg pick_gemv_cfg(int N, int K, int grid) {
-    GemvCfg best{};
-    double best_cost = 1e30;
-    const int C = K / 32;
-    for (int rows16 = 1; rows16 >= 0; --rows16) {
-        for (int ks = 1, shift = 0; ks <= 8; ks *= 2, ++shift) {
-            if (C < ks) break;
-            const int rt = rows16 ? 16 : 8, tpr = MG_WARPS / ks;
-            const int n_tiles = (N + rt - 1) / rt;
-            const int stride = grid * tpr;
-            const int rounds = (n_tiles + stride - 1) / stride;
-            const double cost = rounds * ((double)((C + ks - 1) / ks) * (rows16 ? 1.0 : 0.5) + 2.0);
-            if (cost < best_cost - 1e-9) {
-                best_cost = cost;
-                GemvCfg c{};
-                c.ks = ks; c.ks_shift = shift; c.rows16 = rows16; c.C = C;
-                c.cps = rows16 ? 4 : 8;
-                c.nsc = ((C + ks - 1) / ks + c.cps - 1) / c.cps;
-                c.n_tiles = n_tiles; c.tpr = tpr;
-                // CTA c owns tiles (r * grid + c) * tpr + [0, tpr): it has a round r iff (r * grid + c) * tpr < n_tiles
-                c.rounds_base = n_tiles / stride;
-                c.rounds_rem = n_tiles % stride;
-                best = c;
-            }
-        }
-    }
-    return best;
 }
 
 int pick_cross_splits(int items, int n_keys, int grid) {
@@ -754,6 +649,16 @@ int pick_cross_splits(int items, int n_keys, int grid) {
 }
 
 size_t mega_smem_bytes(int nm, int ffn) { return (size_t)MG_RED_BYTES + (size_t)8 * nm * (ffn + MG_ACT_PAD) * sizeof(bf16); }
+
+void fill_geometry(PhaseDesc& o, int ks, bool rows16, int grid) {
+    const int rt = rows16 ? 16 : 8, cps = rows16 ? 4 : 8, tpr = MG_WARPS / ks, C = o.K / 32;
+    const int n_tiles = (o.N + rt - 1) / rt, stride = grid * tpr;
+    o.nsc = ((C + ks - 1) / ks + cps - 1) / cps;
+    // CTA c owns tiles (r * grid + c) * tpr + [0, tpr): it has a round r iff (r * grid + c) * tpr < n_tiles
+    o.rounds_base = n_tiles / stride;
+    o.rounds_rem = n_tiles % stride;
+    o.vpr_rcp = (unsigned)((0x100000000ull + (unsigned)(o.K / 8) - 1) / (unsigned)(o.K / 8));
+}
 }  // namespace
 
 long long*& step_trace_ptr() {
@@ -766,24 +671,64 @@ size_t mega_part_bytes(int max_batch, int heads) {
     return (size_t)std::min(max_batch, 16) * heads * MG_MAX_SPLITS * MG_PART * sizeof(float);
 }
 size_t mega_sync_bytes(int max_batch, int heads) { return (size_t)(32 + std::min(max_batch, 16) * heads) * sizeof(unsigned); }
+size_t mega_table_bytes(int dec_layers) { return (size_t)(8 * dec_layers + 1) * sizeof(PhaseDesc); }
 
 bool Session::mega_supported() const {
     const ModelConfig& g = m->cfg;
-    return m->dtype == BF16 && batch >= 1 && batch <= 16 && g.d_model % 64 == 0 && g.d_model <= 1024 && g.n_heads * 64 == g.d_model &&
-           g.ffn % 64 == 0 && g.dec_layers <= MG_MAX_LAYERS && g.vocab % 4 == 0 && pages_per_seq <= 32 &&
-           mega_smem_bytes(batch <= 8 ? 1 : 2, g.ffn) <= 220 * 1024;
+    return mega_table != nullptr && m->dtype == BF16 && batch >= 1 && batch <= 16 && g.d_model % 64 == 0 && g.d_model <= 1024 &&
+           g.n_heads * 64 == g.d_model && g.ffn % 64 == 0 && g.ffn <= 4096 && g.dec_layers <= MG_MAX_LAYERS && g.vocab % 4 == 0 &&
+           pages_per_seq <= 32 && mega_smem_bytes(batch <= 8 ? 1 : 2, g.ffn) <= 200 * 1024;
+}
+
+// the phase table of this session: every pointer and every division resolved once (called by the Session constructor)
+void Session::build_mega_table() {
+    const ModelConfig& g = m->cfg;
+    mega_grid = 0;
+    if (m->dtype != BF16 || mega_table == nullptr) return;
+    int dev = 0;
+    WB_CHECK_CUDA(cudaGetDevice(&dev));
+    WB_CHECK_CUDA(cudaDeviceGetAttribute(&mega_grid, cudaDevAttrMultiProcessorCount, dev));
+    const int d = g.d_model;
+    std::vector<PhaseDesc> t((size_t)8 * g.dec_layers + 1);
+    const size_t per_kv = (size_t)max_batch * g.n_heads * g.n_ctx * 64;
+    auto linear = [&](PhaseDesc& o, const Linear& l, int stage, const LNorm* ln, const void* src, int epi, void* out_bf16) {
+        std::memset(&o, 0, sizeof(o));
+        o.kind = PH_LINEAR; o.W = (const bf16*)l.w; o.bias = l.b; o.N = l.n; o.K = l.k; o.stage = stage; o.epi = epi;
+        if (ln != nullptr) { o.gamma = ln->g; o.beta = ln->b; }
+        o.src = (const bf16*)src; o.out_bf16 = (bf16*)out_bf16;
+        fill_geometry(o, MG_LAYER_KS, false, mega_grid);
+    };
+    for (int l = 0; l < g.dec_layers; ++l) {
+        const DecLayer& L = m->dec[l];
+        PhaseDesc* o = &t[(size_t)8 * l];
+        bf16* sk = (bf16*)self_k + (size_t)l * self_layer_elems();
+        bf16* sv = (bf16*)self_v + (size_t)l * self_layer_elems();
+        bf16* ck = (bf16*)cross + (size_t)l * cross_layer_elems();
+        linear(o[0], L.qkv, ST_LN_X, &L.ln1, nullptr, EP_QKV, dq);
+        o[0].k_pages = sk; o[0].v_pages = sv;
+        std::memset(&o[1], 0, sizeof(PhaseDesc));
+        o[1].kind = PH_SELF_ATTN; o[1].k_pages = sk; o[1].v_pages = sv;
+        linear(o[2], L.out, ST_COPY, nullptr, datt, EP_RESIDUAL, nullptr);
+        linear(o[3], L.cq, ST_LN_X, &L.ln2, nullptr, EP_BF16, dq);
+        std::memset(&o[4], 0, sizeof(PhaseDesc));
+        o[4].kind = PH_CROSS_ATTN; o[4].k_pages = ck; o[4].v_pages = ck + per_kv;
+        linear(o[5], L.cout, ST_COPY, nullptr, datt, EP_RESIDUAL, nullptr);
+        linear(o[6], L.fc1, ST_LN_X, &L.ln3, nullptr, EP_GELU_BF16, dffn);
+        linear(o[7], L.fc2, ST_COPY, nullptr, dffn, EP_RESIDUAL, nullptr);
+    }
+    PhaseDesc& h = t.back();   // final LayerNorm + LM head (weights shared with the embedding table, no bias) -> fp32 logits
+    std::memset(&h, 0, sizeof(h));
+    h.kind = PH_HEAD; h.W = (const bf16*)m->emb; h.N = g.vocab; h.K = d; h.stage = ST_LN_X; h.epi = EP_F32;
+    h.gamma = m->dec_ln.g; h.beta = m->dec_ln.b; h.out_f32 = logits;
+    fill_geometry(h, MG_HEAD_KS, true, mega_grid);
+    WB_CHECK_CUDA(cudaMemcpy(mega_table, t.data(), t.size() * sizeof(PhaseDesc), cudaMemcpyHostToDevice));
 }
 
 // one token for the whole batch in ONE cooperative launch (the logits processors / argmax kernel follows, decode_step)
 void Session::decode_step_mega(cudaStream_t st) {
     const ModelConfig& g = m->cfg;
-    const int d = g.d_model, B = batch;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        WB_CHECK_CUDA(cudaGetDevice(&dev));
-        WB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int B = batch;
+    WB_REQUIRE(mega_grid > 0, "whole-step kernel: no phase table");
     const int nm = B <= 8 ? 1 : 2;
     const size_t smem = mega_smem_bytes(nm, g.ffn);
     auto kernel = nm == 1 ? decode_step_mega_kernel<1> : decode_step_mega_kernel<2>;
@@ -795,37 +740,18 @@ void Session::decode_step_mega(cudaStream_t st) {
     int per_sm = 0;
     WB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, MG_THREADS, smem));
     WB_REQUIRE(per_sm >= 1, "whole-step kernel does not fit on an SM");
-    const int grid = sms;
 
     MegaParams p{};
-    p.M = B; p.d = d; p.H = g.n_heads; p.ffn = g.ffn; p.vocab = g.vocab; p.n_layers = g.dec_layers; p.n_ctx = g.n_ctx;
-    p.cross_splits = pick_cross_splits(B * g.n_heads, g.n_ctx, grid);
-    p.pages_per_seq = pages_per_seq; p.tokens_stride = g.max_tgt;
+    p.M = B; p.d = g.d_model; p.H = g.n_heads; p.ffn = g.ffn; p.vocab = g.vocab; p.n_phases = 8 * g.dec_layers + 1; p.n_ctx = g.n_ctx;
+    p.cross_splits = pick_cross_splits(B * g.n_heads, g.n_ctx, mega_grid);
+    p.pages_per_seq = pages_per_seq;
     p.cross_bstride = (long long)g.n_heads * g.n_ctx * 64;
-    p.c_qkv = pick_gemv_cfg(3 * d, d, grid);
-    p.c_dd = pick_gemv_cfg(d, d, grid);
-    p.c_fc1 = pick_gemv_cfg(g.ffn, d, grid);
-    p.c_fc2 = pick_gemv_cfg(d, g.ffn, grid);
-    p.c_head = pick_gemv_cfg(g.vocab, d, grid);
-    p.tokens = tokens; p.state = state; p.unfinished = unfinished; p.page_table = page_table;
-    p.emb = (const bf16*)m->emb; p.pos = (const bf16*)m->dec_pos; p.lnf_g = m->dec_ln.g; p.lnf_b = m->dec_ln.b;
-    p.x = dx; p.q = (bf16*)dq; p.ctx = (bf16*)datt; p.ffn_act = (bf16*)dffn; p.logits = logits;
+    p.state = state; p.unfinished = unfinished; p.page_table = page_table;
+    p.x = dx; p.q = (bf16*)dq; p.ctx = (bf16*)datt;
     p.part = mega_part; p.sync = mega_sync; p.trace = step_trace_ptr();
-    const size_t per_kv = (size_t)max_batch * g.n_heads * g.n_ctx * 64;
-    for (int l = 0; l < g.dec_layers; ++l) {
-        const DecLayer& L = m->dec[l];
-        MegaLayer& o = p.layer[l];
-        o.ln1_g = L.ln1.g; o.ln1_b = L.ln1.b; o.ln2_g = L.ln2.g; o.ln2_b = L.ln2.b; o.ln3_g = L.ln3.g; o.ln3_b = L.ln3.b;
-        o.qkv_w = (const bf16*)L.qkv.w; o.out_w = (const bf16*)L.out.w; o.cq_w = (const bf16*)L.cq.w;
-        o.cout_w = (const bf16*)L.cout.w; o.fc1_w = (const bf16*)L.fc1.w; o.fc2_w = (const bf16*)L.fc2.w;
-        o.qkv_b = L.qkv.b; o.out_b = L.out.b; o.cq_b = L.cq.b; o.cout_b = L.cout.b; o.fc1_b = L.fc1.b; o.fc2_b = L.fc2.b;
-        o.self_k = (bf16*)self_k + (size_t)l * self_layer_elems();
-        o.self_v = (bf16*)self_v + (size_t)l * self_layer_elems();
-        o.cross_k = (const bf16*)cross + (size_t)l * cross_layer_elems();
-        o.cross_v = o.cross_k + per_kv;
-    }
+    p.table = reinterpret_cast<const PhaseDesc*>(mega_table);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
+    cfg.gridDim = dim3(mega_grid);
     cfg.blockDim = dim3(MG_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;

@@ -121,6 +121,9 @@ struct GreedyArgs {
     int* unfinished = nullptr;                      // [B]
     StepState* state = nullptr;
     const int* forced_tokens = nullptr;         // teacher forcing (tests): take ids[b, n] from here instead of argmax
+    // optional (whole-step decoder kernel): also write the embedding of the chosen token, the input of the next step,
+    // x[b, :] = E[tok, :] + P[len, :] (fp32 [B, d]; bf16 tables, d % 8 == 0)
+    float* embed_x = nullptr; const void* embed_table = nullptr; const void* embed_pos = nullptr; int embed_d = 0;
 };
 void greedy_step(const GreedyArgs& a, cudaStream_t stream);
 void greedy_init(int* tokens, int tokens_stride, int* unfinished, StepState* state, int B, int start_token,

@@ -84,10 +84,11 @@ struct Buffers {
     void* dffn = nullptr; float* logits = nullptr;
     int* tokens = nullptr; int* unfinished = nullptr; StepState* state = nullptr;
     // whole-step kernel (step_mega.cu): attention partials of split items, grid-barrier / per-item arrival counters
-    float* mega_part = nullptr; unsigned* mega_sync = nullptr;
+    float* mega_part = nullptr; unsigned* mega_sync = nullptr; void* mega_table = nullptr;
 };
 size_t mega_part_bytes(int max_batch, int heads);
 size_t mega_sync_bytes(int max_batch, int heads);
+size_t mega_table_bytes(int dec_layers);
 
 struct Session : Buffers {
     Model* m;
@@ -135,6 +136,9 @@ struct Session : Buffers {
     void decode_step_small(cudaStream_t s);   // B <= 16, bf16: weight-streaming GEMV kernels with fused LayerNorm
     void decode_step_mega(cudaStream_t s);    // B <= 16, bf16: ONE persistent cooperative kernel per token (step_mega.cu)
     bool mega_supported() const;
+    bool use_mega() const;                    // this batch goes through the whole-step kernel
+    void build_mega_table();                  // phase descriptors of the whole-step kernel (constructor)
+    int mega_grid = 0;                        // CTAs of the whole-step kernel = SMs of the device the table was built for
     int decode_run(int max_steps, int check_every, cudaStream_t s);  // returns final length (syncs)
     void enqueue_step();                                             // one step on loop_stream (graph replay or eager)
     size_t cross_layer_elems() const;
