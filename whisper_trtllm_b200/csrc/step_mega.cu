@@ -134,28 +134,27 @@ __device__ __forceinline__ void grid_wait(unsigned* counter, unsigned& epoch) {
 }
 
 // ---- activation staging: the (normalised) rows of all M utterances as bf16 in shared memory, row stride K + MG_ACT_PAD
-// ---- activation staging: the (normalised) rows of all M utterances as bf16 in shared memory, row stride K + MG_ACT_PAD
-// LayerNorm: a row is split over the whole CTA (thread t owns float4 t of every row, d <= 1024), the loads of all rows plus
-// gamma / beta are issued together - one round trip - and the statistics go through shared memory; per row that is ~60
-// instructions per warp, and only the rows that exist are computed.  (Earlier versions, profiles/r01_step_trace_*.md: one warp
-// per row with a guarded per-element loop - ptxas serialised the gamma / beta loads into 8 dependent round trips; every thread
-// computing all 8 rows - 1300 instructions per warp; one warp per row with 24 batched loads - 750 instructions on ONE warp.)
 // Rows come from the fp32 residual stream; the embedding of the token that is fed (x = E[token] + P[position], model.py:423-425)
 // was written there by the previous step's greedy kernel (greedy.cu, GreedyArgs::embed_x) or by decode_begin.
-template <int NM>
-__device__ __noinline__ void stage_layernorm(const MegaParams& p, bf16* act_s, float* red_s, const float* __restrict__ gamma,
-                                                const float* __restrict__ beta) {
-    constexpr int MR = 8 * NM;
+// The phases are latency-bound instruction streams: what counts is the number of dependent instructions per warp.
+//  * M <= 2: a row is split over the whole CTA (thread t owns float4 t, d <= 1024): 3 loads per thread in one round trip, two
+//    block reductions, ~60 instructions per row and warp;
+//  * M > 2: one warp per row (rows warp, warp + 8), the 8 x-loads of a lane issued together, gamma / beta (requested into L2
+//    before the grid barrier) in two half-batches: no block barrier, the rows run in parallel on the 8 warps.
+// (Measured alternatives, profiles/r01_step_trace_*.md: guarded per-element loop - ptxas serialised the gamma / beta loads
+// into 8 dependent round trips, 6.4 K cycles; every thread computing all 8 / 16 rows - 4.2 K / 17 K cycles.)
+__device__ __forceinline__ void stage_layernorm_wide(const MegaParams& p, bf16* act_s, float* red_s, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta) {
+    constexpr int MR = 2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int d = p.d, nvec = d >> 2, astride = d + MG_ACT_PAD, M = p.M;
     const bool on = tid < nvec;
     const float inv_d = 1.0f / (float)d;
-    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = g4;
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = g4, v[MR];
     if (on) {
         g4 = __ldg(reinterpret_cast<const float4*>(gamma) + tid);
         b4 = __ldg(reinterpret_cast<const float4*>(beta) + tid);
     }
-    float4 v[MR];
 #pragma unroll
     for (int m = 0; m < MR; ++m) {
         v[m] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -165,36 +164,85 @@ __device__ __noinline__ void stage_layernorm(const MegaParams& p, bf16* act_s, f
     float* rq = red_s + MR * MG_WARPS;
 #pragma unroll
     for (int m = 0; m < MR; ++m) {
-        if (m < M) {                    // CTA-uniform
-            const float s = warp_sum((v[m].x + v[m].y) + (v[m].z + v[m].w));     // threads past the row hold zeros
-            if (lane == 0) rs[m * MG_WARPS + warp] = s;
-        }
+        const float s = warp_sum((v[m].x + v[m].y) + (v[m].z + v[m].w));     // threads past the row hold zeros
+        if (lane == 0) rs[m * MG_WARPS + warp] = s;
     }
     __syncthreads();
     float mean[MR];
 #pragma unroll
     for (int m = 0; m < MR; ++m) {
-        if (m < M) {
-            const float4 a = *reinterpret_cast<const float4*>(rs + m * MG_WARPS), b = *reinterpret_cast<const float4*>(rs + m * MG_WARPS + 4);
-            mean[m] = (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) * inv_d;
-            const float c0 = v[m].x - mean[m], c1 = v[m].y - mean[m], c2 = v[m].z - mean[m], c3 = v[m].w - mean[m];
-            const float ss = warp_sum(on ? (c0 * c0 + c1 * c1) + (c2 * c2 + c3 * c3) : 0.f);
-            if (lane == 0) rq[m * MG_WARPS + warp] = ss;
-        }
+        const float4 a = *reinterpret_cast<const float4*>(rs + m * MG_WARPS), b = *reinterpret_cast<const float4*>(rs + m * MG_WARPS + 4);
+        mean[m] = (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) * inv_d;
+        const float c0 = v[m].x - mean[m], c1 = v[m].y - mean[m], c2 = v[m].z - mean[m], c3 = v[m].w - mean[m];
+        const float ss = warp_sum(on ? (c0 * c0 + c1 * c1) + (c2 * c2 + c3 * c3) : 0.f);
+        if (lane == 0) rq[m * MG_WARPS + warp] = ss;
     }
     __syncthreads();
 #pragma unroll
     for (int m = 0; m < MR; ++m) {
-        if (m < M) {
-            const float4 a = *reinterpret_cast<const float4*>(rq + m * MG_WARPS), b = *reinterpret_cast<const float4*>(rq + m * MG_WARPS + 4);
-            const float rstd = rsqrtf((((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) * inv_d + 1e-5f);
-            if (on) {
-                __nv_bfloat162 p0 = __floats2bfloat162_rn((v[m].x - mean[m]) * rstd * g4.x + b4.x, (v[m].y - mean[m]) * rstd * g4.y + b4.y);
-                __nv_bfloat162 p1 = __floats2bfloat162_rn((v[m].z - mean[m]) * rstd * g4.z + b4.z, (v[m].w - mean[m]) * rstd * g4.w + b4.w);
-                uint2 u;
-                u.x = *reinterpret_cast<uint32_t*>(&p0);
-                u.y = *reinterpret_cast<uint32_t*>(&p1);
-                *reinterpret_cast<uint2*>(act_s + (size_t)m * astride + tid * 4) = u;
+        const float4 a = *reinterpret_cast<const float4*>(rq + m * MG_WARPS), b = *reinterpret_cast<const float4*>(rq + m * MG_WARPS + 4);
+        const float rstd = rsqrtf((((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) * inv_d + 1e-5f);
+        if (on && m < M) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn((v[m].x - mean[m]) * rstd * g4.x + b4.x, (v[m].y - mean[m]) * rstd * g4.y + b4.y);
+            __nv_bfloat162 p1 = __floats2bfloat162_rn((v[m].z - mean[m]) * rstd * g4.z + b4.z, (v[m].w - mean[m]) * rstd * g4.w + b4.w);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&p0);
+            u.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(act_s + (size_t)m * astride + tid * 4) = u;
+        }
+    }
+}
+
+__device__ __forceinline__ void stage_layernorm_rows(const MegaParams& p, bf16* act_s, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = p.d, nvec = d >> 2, astride = d + MG_ACT_PAD;
+    const float inv_d = 1.0f / (float)d;
+    for (int m = warp; m < p.M; m += MG_WARPS) {
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = lane + 32 * i;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < nvec) v[i] = ldg_cg_f4(p.x + (size_t)m * d + idx * 4);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);      // lanes past the row hold zeros
+        const float mean = warp_sum(s) * inv_d;
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (lane + 32 * i < nvec) {
+                const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+                ss += (a * a + b * b) + (c * c + e * e);
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(ss) * inv_d + 1e-5f);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float4 g4[4], b4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = lane + 32 * (half * 4 + j);
+                g4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                b4[j] = g4[j];
+                if (idx < nvec) {
+                    g4[j] = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
+                    b4[j] = __ldg(reinterpret_cast<const float4*>(beta) + idx);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = half * 4 + j, idx = lane + 32 * i;
+                if (idx < nvec) {
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn((v[i].x - mean) * rstd * g4[j].x + b4[j].x, (v[i].y - mean) * rstd * g4[j].y + b4[j].y);
+                    __nv_bfloat162 p1 = __floats2bfloat162_rn((v[i].z - mean) * rstd * g4[j].z + b4[j].z, (v[i].w - mean) * rstd * g4[j].w + b4[j].w);
+                    uint2 u;
+                    u.x = *reinterpret_cast<uint32_t*>(&p0);
+                    u.y = *reinterpret_cast<uint32_t*>(&p1);
+                    *reinterpret_cast<uint2*>(act_s + (size_t)m * astride + idx * 4) = u;
+                }
             }
         }
     }
@@ -202,7 +250,7 @@ __device__ __noinline__ void stage_layernorm(const MegaParams& p, bf16* act_s, f
 
 // bf16 rows of the previous phase -> shared memory; the requests of a thread are issued together (no clamped duplicates:
 // 148 SMs x 256 threads asking for one line serialise in its L2 slice)
-__device__ __noinline__ void stage_copy(bf16* act_s, const bf16* src, int M, int K, unsigned vpr_rcp) {
+__device__ __forceinline__ void stage_copy(bf16* act_s, const bf16* src, int M, int K, unsigned vpr_rcp) {
     const int vpr = K >> 3, astride = K + MG_ACT_PAD, total = M * vpr;
     for (int base = 0; base < total; base += MG_THREADS * 8) {
         uint4 r[8];
@@ -224,9 +272,12 @@ __device__ __noinline__ void stage_copy(bf16* act_s, const bf16* src, int M, int
 }
 
 // called exactly once per output element (n, m) by exactly one thread of the grid
-__device__ __forceinline__ void linear_epilogue(const MegaParams& p, const PhaseDesc& D, int pos, int n, int m, float v) {
+// kPre: `pre` already holds bias[n] (+ x[m, n] for the residual epilogue), loaded while the weights were in flight
+template <bool kPre>
+__device__ __forceinline__ void linear_epilogue(const MegaParams& p, const PhaseDesc& D, int pos, int n, int m, float v, float pre) {
     if (n >= D.N || m >= p.M) return;
-    if (D.bias != nullptr) v += __ldg(D.bias + n);
+    if (kPre) v += pre;
+    else if (D.bias != nullptr) v += __ldg(D.bias + n);
     const int d = p.d;
     switch (D.epi) {
         case EP_QKV: {   // q -> activation buffer; k / v rows straight into the paged cache at slot cur_len - 1
@@ -242,7 +293,7 @@ __device__ __forceinline__ void linear_epilogue(const MegaParams& p, const Phase
         }
         case EP_RESIDUAL: {   // fp32 residual stream, updated in place: this thread owns (m, n)
             float* xp = p.x + (size_t)m * d + n;
-            *xp = ldg_cg_f(xp) + v;
+            *xp = kPre ? v : ldg_cg_f(xp) + v;
             break;
         }
         case EP_BF16: D.out_bf16[(size_t)m * D.N + n] = __float2bfloat16_rn(v); break;
@@ -293,6 +344,24 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const PhaseDes
         }
     };
 
+    // K-split tiles: thread o < OUTS owns output element (n_l, m) of tile t2 in every round; its bias (and the residual it adds
+    // to) are loaded when the round's weights are requested, not after the reduction
+    constexpr int M_CNT = 8 * NM, OUTS = KS == 1 ? 0 : TPR * M_CNT * RT;
+    static_assert(OUTS <= MG_THREADS, "one output element per thread");
+    const int o_nl = tid & (RT - 1), o_m = (tid >> RT_SHIFT) % M_CNT, o_t2 = (tid >> RT_SHIFT) / M_CNT;
+    float pre_cur = 0.f, pre_nxt = 0.f;
+    auto preload = [&](int r) -> float {
+        float v = 0.f;
+        if (tid < OUTS) {
+            const int n = (tile_of(r, o_t2) << RT_SHIFT) + o_nl;
+            if (n < N && o_m < p.M) {
+                if (D.bias != nullptr) v = __ldg(D.bias + n);
+                if (D.epi == EP_RESIDUAL) v += ldg_cg_f(p.x + (size_t)o_m * p.d + n);
+            }
+        }
+        return v;
+    };
+
     float acc[NM][4];
     auto finish = [&](int r) __attribute__((always_inline)) {
         if constexpr (KS == 1) {
@@ -302,7 +371,7 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const PhaseDes
 #pragma unroll 1
                 for (int e = 0; e < (R16 ? 4 : 2); ++e) {   // rolled: one copy of the epilogue code
                     const float v = e == 0 ? acc[mb][0] : e == 1 ? acc[mb][1] : e == 2 ? acc[mb][2] : acc[mb][3];
-                    linear_epilogue(p, D, pos, n0 + g + (e >> 1) * 8, mb * 8 + 2 * tq + (e & 1), v);
+                    linear_epilogue<false>(p, D, pos, n0 + g + (e >> 1) * 8, mb * 8 + 2 * tq + (e & 1), v, 0.f);
                 }
             }
         } else {
@@ -318,18 +387,12 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const PhaseDes
                 }
             }
             __syncthreads();
-            constexpr int M_CNT = 8 * NM, OUTS = TPR * M_CNT * RT;
+            if (tid < OUTS) {              // thread o finishes output (n_l, m) of tile t2 in every round
+                const float* rr = red_s + ((r & 1) * MG_WARPS + o_t2 * KS) * WSTRIDE + o_m * MG_RS + o_nl;
+                float v = 0.f;
 #pragma unroll
-            for (int o0 = 0; o0 < OUTS; o0 += MG_THREADS) {
-                const int o = o0 + tid;
-                if (OUTS % MG_THREADS == 0 || o < OUTS) {
-                    const int n_l = o & (RT - 1), rest = o >> RT_SHIFT, m = rest % M_CNT, t2 = rest / M_CNT;
-                    const float* rr = red_s + ((r & 1) * MG_WARPS + t2 * KS) * WSTRIDE + m * MG_RS + n_l;
-                    float v = 0.f;
-#pragma unroll
-                    for (int k = 0; k < KS; ++k) v += rr[k * WSTRIDE];     // fixed order: deterministic
-                    linear_epilogue(p, D, pos, (tile_of(r, t2) << RT_SHIFT) + n_l, m, v);
-                }
+                for (int k = 0; k < KS; ++k) v += rr[k * WSTRIDE];     // fixed order: deterministic
+                linear_epilogue<true>(p, D, pos, (tile_of(r, o_t2) << RT_SHIFT) + o_nl, o_m, v, pre_cur);
             }
         }
     };
@@ -365,9 +428,11 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const PhaseDes
     uint4 cur[8], nxt[8];
     if (total > 0) {
         issue(0, 0, cur);     // in flight while the activations are staged
+        if constexpr (KS > 1) pre_cur = preload(0);
         if (tr != nullptr) tr[1] = clock64();
         if (D.stage == ST_COPY) stage_copy(act_s, D.src, p.M, K, D.vpr_rcp);
-        else stage_layernorm<NM>(p, act_s, red_s, D.gamma, D.beta);
+        else if (p.M <= 2) stage_layernorm_wide(p, act_s, red_s, D.gamma, D.beta);
+        else stage_layernorm_rows(p, act_s, D.gamma, D.beta);
     }
     if (tr != nullptr) tr[2] = clock64();
     __syncthreads();
@@ -377,10 +442,14 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const PhaseDes
     for (int idx = 0; idx < total; ++idx) {   // trip counts are CTA-uniform (finish() contains a block barrier)
         int r1 = r, sc1 = sc + 1;
         if (sc1 == nsc) { sc1 = 0; ++r1; }
-        if (idx + 1 < total) issue(r1, sc1, nxt);
+        if (idx + 1 < total) {
+            issue(r1, sc1, nxt);
+            if constexpr (KS > 1) { if (r1 != r) pre_nxt = preload(r1); }
+        }
         compute(r, sc, cur);
 #pragma unroll
         for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+        if (r1 != r) pre_cur = pre_nxt;
         r = r1;
         sc = sc1;
     }
@@ -608,11 +677,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_mega_kernel(const _
             linear_phase<NM, MG_LAYER_KS, false>(p, D, pos, mg_smem, trace != nullptr ? trace + 8 * ph : nullptr);
         } else if (kind == PH_HEAD) {
             linear_phase<NM, MG_HEAD_KS, true>(p, D, pos, mg_smem, trace != nullptr ? trace + 8 * ph : nullptr);
-        } else {
-            // cached self-attention over cur_len keys (newest row appended by the qkv epilogue) / cross-attention over the encoder
-            // K/V projected once per utterance; ONE call site = one copy of the code
-            const bool self = kind == PH_SELF_ATTN;
-            attention_phase(p, self, D.k_pages, D.v_pages, self ? cur_len : p.n_ctx, self ? 1 : p.cross_splits, mg_smem, item_cnt);
+        } else if (kind == PH_SELF_ATTN) {   // cached self-attention over cur_len keys (newest row appended by the qkv epilogue)
+            attention_phase(p, true, D.k_pages, D.v_pages, cur_len, 1, mg_smem, item_cnt);
+        } else {                             // cross-attention over the encoder K/V projected once per utterance
+            attention_phase(p, false, D.k_pages, D.v_pages, p.n_ctx, p.cross_splits, mg_smem, item_cnt);
         }
         if (trace != nullptr) trace[8 * ph + 4] = clock64();
         if (ph + 1 == n_phases) break;
