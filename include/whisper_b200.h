@@ -71,7 +71,7 @@ WB_API int wb_set_self_attention_warp_kernel(int variant);
  * (csrc/gemv.cu); 0 = the large-batch kernels.  Captured CUDA graphs keep the path they were captured with. */
 WB_API int wb_set_small_batch_path(int mode);
 /* measurement hook of the whole-step kernel: device buffer of 8 * (8 * decoder_layers + 2) int64; CTA 0 stores its SM clock
- * at 8 points of every phase: [0] start, [1] first weight tile requested, [2] activations staged, [3] block barrier passed,
+ * at 8 points of every phase: [0] start, [1] activations staged, [2] block barrier passed, [3] first weight tile requested,
  * [4] phase done, [5] arrived at the grid barrier + next phase prefetched, [8] = next [0] grid barrier passed
  * (tools/step_trace.py).  NULL (default) = off.  Decode-step graphs captured afterwards carry the pointer. */
 WB_API int wb_set_step_trace(void* device_buffer);

@@ -50,9 +50,9 @@ def main():
     mhz = float(os.popen("nvidia-smi --query-gpu=clocks.sm --format=csv,noheader,nounits -i 0").read().split()[0] or 0)
     print(f"# Whole-step kernel phase trace: {a.size} bf16, batch {a.batch}, length {a.length + 8}\n")
     print(f"step (CUDA events, graph replay) {step_us:.0f} us; kernel {total_cycles} SM cycles; nvidia-smi SM clock after the run {mhz:.0f} MHz\n")
-    print("Mean SM cycles of CTA 0 per phase kind (linear layers: request first weight tile -> stage activations (LayerNorm / copy) "
-          "-> block barrier -> weight stream + MMA + reduction + epilogue; then arrive + prefetch of the next phase -> wait for the grid).\n")
-    print("| phase | count | issue | stage | block barrier | stream + epilogue | work total | arrive + prefetch | grid wait | share of kernel |")
+    print("Mean SM cycles of CTA 0 per phase kind (linear layers: stage activations (LayerNorm / copy) -> block barrier -> request first "
+          "weight tile -> weight stream + MMA + reduction + epilogue; then arrive + prefetch of the next phase -> wait for the grid).\n")
+    print("| phase | count | stage | block barrier | first tile issue | stream + epilogue | work total | arrive + prefetch | grid wait | share of kernel |")
     print("|---|---|---|---|---|---|---|---|---|---|")
     acc = [[0] * 7 for _ in range(9)]
     count = [0] * 9

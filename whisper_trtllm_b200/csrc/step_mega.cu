@@ -36,10 +36,11 @@ constexpr int MG_ACT_PAD = 32;       // bf16 elements of padding per staged row 
 constexpr unsigned MG_SPIN_LIMIT = 1u << 26;
 constexpr int MG_ATT_UNROLL = 8;
 // linear layers of a decoder layer: tiles of 8 weight rows, K split over the 8 warps of the CTA (one tile per CTA and round);
-// LM head (51864 rows): tiles of 16 rows, one tile per warp, no K split
-constexpr int MG_HEAD_KS = 1, MG_LAYER_KS = 8;
+// wide ones (qkv, fc1 at d = 1024: more than two such rounds): tiles of 16 rows, K split over 4 warps, two tiles per CTA and
+// round - every round costs a block barrier and an epilogue; LM head (51864 rows): tiles of 16 rows, one per warp, no K split
+constexpr int MG_HEAD_KS = 1, MG_LAYER_KS = 8, MG_WIDE_KS = 4;
 
-enum { PH_LINEAR = 0, PH_SELF_ATTN = 1, PH_CROSS_ATTN = 2, PH_HEAD = 3 };
+enum { PH_LINEAR = 0, PH_SELF_ATTN = 1, PH_CROSS_ATTN = 2, PH_HEAD = 3, PH_LINEAR_WIDE = 4 };
 enum { ST_LN_X = 0, ST_COPY = 2 };
 enum { EP_QKV = 0, EP_RESIDUAL = 1, EP_BF16 = 2, EP_GELU_BF16 = 3, EP_F32 = 4 };
 
@@ -272,11 +273,12 @@ __device__ __forceinline__ void stage_copy(bf16* act_s, const bf16* src, int M, 
 }
 
 // called exactly once per output element (n, m) by exactly one thread of the grid
-// kPre: `pre` already holds bias[n] (+ x[m, n] for the residual epilogue), loaded while the weights were in flight
+// kPre: pre_b / pre_x already hold bias[n] / x[m, n] (residual epilogue), loaded while the weights were in flight
 template <bool kPre>
-__device__ __forceinline__ void linear_epilogue(const MegaParams& p, const PhaseDesc& D, int pos, int n, int m, float v, float pre) {
+__device__ __forceinline__ void linear_epilogue(const MegaParams& p, const PhaseDesc& D, int pos, int n, int m, float v, float pre_b,
+                                                float pre_x) {
     if (n >= D.N || m >= p.M) return;
-    if (kPre) v += pre;
+    if (kPre) v += pre_b;
     else if (D.bias != nullptr) v += __ldg(D.bias + n);
     const int d = p.d;
     switch (D.epi) {
@@ -293,7 +295,7 @@ __device__ __forceinline__ void linear_epilogue(const MegaParams& p, const Phase
         }
         case EP_RESIDUAL: {   // fp32 residual stream, updated in place: this thread owns (m, n)
             float* xp = p.x + (size_t)m * d + n;
-            *xp = kPre ? v : ldg_cg_f(xp) + v;
+            *xp = (kPre ? pre_x : ldg_cg_f(xp)) + v;
             break;
         }
         case EP_BF16: D.out_bf16[(size_t)m * D.N + n] = __float2bfloat16_rn(v); break;
@@ -302,7 +304,7 @@ __device__ __forceinline__ void linear_epilogue(const MegaParams& p, const Phase
     }
 }
 
-// out[m, n] = epilogue( sum_k act[m, k] * W[n, k] ) for all n < N, m < 8 * NM.
+// out[m, n] = epilogue( sum_k act[m, k] * W[n, k] ) for all n < N, m < 8 * NM; the activations are already staged.
 // KS warps split K for one tile of RT = 8 / 16 weight rows; a CTA works on 8 / KS tiles per round; tiles (r * grid + cta) * TPR + ..
 template <int NM, int KS, bool R16>
 __device__ __forceinline__ void linear_phase(const MegaParams& p, const PhaseDesc& D, int pos, uint8_t* smem, long long* tr) {
@@ -346,20 +348,26 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const PhaseDes
 
     // K-split tiles: thread o < OUTS owns output element (n_l, m) of tile t2 in every round; its bias (and the residual it adds
     // to) are loaded when the round's weights are requested, not after the reduction
-    constexpr int M_CNT = 8 * NM, OUTS = KS == 1 ? 0 : TPR * M_CNT * RT;
-    static_assert(OUTS <= MG_THREADS, "one output element per thread");
-    const int o_nl = tid & (RT - 1), o_m = (tid >> RT_SHIFT) % M_CNT, o_t2 = (tid >> RT_SHIFT) / M_CNT;
-    float pre_cur = 0.f, pre_nxt = 0.f;
-    auto preload = [&](int r) -> float {
-        float v = 0.f;
-        if (tid < OUTS) {
-            const int n = (tile_of(r, o_t2) << RT_SHIFT) + o_nl;
-            if (n < N && o_m < p.M) {
-                if (D.bias != nullptr) v = __ldg(D.bias + n);
-                if (D.epi == EP_RESIDUAL) v += ldg_cg_f(p.x + (size_t)o_m * p.d + n);
+    constexpr int M_CNT = 8 * NM, OUTS = KS == 1 ? 0 : TPR * M_CNT * RT, OPT = OUTS == 0 ? 1 : (OUTS + MG_THREADS - 1) / MG_THREADS;
+    // output element e of this thread: o = tid + e * 256 -> (n_l, m, t2)
+    auto out_nl = [&](int e) { return (tid + e * MG_THREADS) & (RT - 1); };
+    auto out_m = [&](int e) { return ((tid + e * MG_THREADS) >> RT_SHIFT) % M_CNT; };
+    auto out_t2 = [&](int e) { return ((tid + e * MG_THREADS) >> RT_SHIFT) / M_CNT; };
+    float2 pre_cur[OPT], pre_nxt[OPT];     // (bias, residual); no arithmetic until the epilogue
+#pragma unroll
+    for (int e = 0; e < OPT; ++e) pre_cur[e] = pre_nxt[e] = make_float2(0.f, 0.f);
+    auto preload = [&](int r, float2(&dst)[OPT]) __attribute__((always_inline)) {
+#pragma unroll
+        for (int e = 0; e < OPT; ++e) {
+            dst[e] = make_float2(0.f, 0.f);
+            if (tid + e * MG_THREADS < OUTS) {
+                const int n = (tile_of(r, out_t2(e)) << RT_SHIFT) + out_nl(e), m = out_m(e);
+                if (n < N && m < p.M) {
+                    if (D.bias != nullptr) dst[e].x = __ldg(D.bias + n);
+                    if (D.epi == EP_RESIDUAL) dst[e].y = ldg_cg_f(p.x + (size_t)m * p.d + n);
+                }
             }
         }
-        return v;
     };
 
     float acc[NM][4];
@@ -371,7 +379,7 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const PhaseDes
 #pragma unroll 1
                 for (int e = 0; e < (R16 ? 4 : 2); ++e) {   // rolled: one copy of the epilogue code
                     const float v = e == 0 ? acc[mb][0] : e == 1 ? acc[mb][1] : e == 2 ? acc[mb][2] : acc[mb][3];
-                    linear_epilogue<false>(p, D, pos, n0 + g + (e >> 1) * 8, mb * 8 + 2 * tq + (e & 1), v, 0.f);
+                    linear_epilogue<false>(p, D, pos, n0 + g + (e >> 1) * 8, mb * 8 + 2 * tq + (e & 1), v, 0.f, 0.f);
                 }
             }
         } else {
@@ -387,12 +395,16 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const PhaseDes
                 }
             }
             __syncthreads();
-            if (tid < OUTS) {              // thread o finishes output (n_l, m) of tile t2 in every round
-                const float* rr = red_s + ((r & 1) * MG_WARPS + o_t2 * KS) * WSTRIDE + o_m * MG_RS + o_nl;
-                float v = 0.f;
 #pragma unroll
-                for (int k = 0; k < KS; ++k) v += rr[k * WSTRIDE];     // fixed order: deterministic
-                linear_epilogue<true>(p, D, pos, (tile_of(r, o_t2) << RT_SHIFT) + o_nl, o_m, v, pre_cur);
+            for (int e = 0; e < OPT; ++e) {
+                if (tid + e * MG_THREADS < OUTS) {
+                    const int t2 = out_t2(e), m = out_m(e), n_l = out_nl(e);
+                    const float* rr = red_s + ((r & 1) * MG_WARPS + t2 * KS) * WSTRIDE + m * MG_RS + n_l;
+                    float v = 0.f;
+#pragma unroll
+                    for (int k = 0; k < KS; ++k) v += rr[k * WSTRIDE];     // fixed order: deterministic
+                    linear_epilogue<true>(p, D, pos, (tile_of(r, t2) << RT_SHIFT) + n_l, m, v, pre_cur[e].x, pre_cur[e].y);
+                }
             }
         }
     };
@@ -427,15 +439,9 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const PhaseDes
 
     uint4 cur[8], nxt[8];
     if (total > 0) {
-        issue(0, 0, cur);     // in flight while the activations are staged
-        if constexpr (KS > 1) pre_cur = preload(0);
-        if (tr != nullptr) tr[1] = clock64();
-        if (D.stage == ST_COPY) stage_copy(act_s, D.src, p.M, K, D.vpr_rcp);
-        else if (p.M <= 2) stage_layernorm_wide(p, act_s, red_s, D.gamma, D.beta);
-        else stage_layernorm_rows(p, act_s, D.gamma, D.beta);
+        issue(0, 0, cur);
+        if constexpr (KS > 1) preload(0, pre_cur);
     }
-    if (tr != nullptr) tr[2] = clock64();
-    __syncthreads();
     if (tr != nullptr) tr[3] = clock64();
     int r = 0, sc = 0;
 #pragma unroll 1
@@ -444,12 +450,15 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const PhaseDes
         if (sc1 == nsc) { sc1 = 0; ++r1; }
         if (idx + 1 < total) {
             issue(r1, sc1, nxt);
-            if constexpr (KS > 1) { if (r1 != r) pre_nxt = preload(r1); }
+            if constexpr (KS > 1) { if (r1 != r) preload(r1, pre_nxt); }
         }
         compute(r, sc, cur);
 #pragma unroll
         for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-        if (r1 != r) pre_cur = pre_nxt;
+        if (r1 != r) {
+#pragma unroll
+            for (int e = 0; e < OPT; ++e) pre_cur[e] = pre_nxt[e];
+        }
         r = r1;
         sc = sc1;
     }
@@ -583,13 +592,20 @@ __device__ __forceinline__ void attention_phase(const MegaParams& p, const bool 
                     if (u * MG_THREADS + tid < n_f) pbuf[u * MG_THREADS + tid] = r[u];
                 __syncthreads();
                 if (tid < 64) {
-                    float mm = -INFINITY;
-                    for (int s = 0; s < splits; ++s) mm = fmaxf(mm, pbuf[s * MG_PART]);
+                    float ms[MG_MAX_SPLITS], mm = -INFINITY;
+#pragma unroll
+                    for (int s = 0; s < MG_MAX_SPLITS; ++s) {
+                        ms[s] = s < splits ? pbuf[s * MG_PART] : -INFINITY;
+                        mm = fmaxf(mm, ms[s]);
+                    }
                     float l = 0.f, o = 0.f;
-                    for (int s = 0; s < splits; ++s) {
-                        const float w = __expf(pbuf[s * MG_PART] - mm);
-                        l = fmaf(pbuf[s * MG_PART + 1], w, l);
-                        o = fmaf(pbuf[s * MG_PART + 8 + tid], w, o);
+#pragma unroll
+                    for (int s = 0; s < MG_MAX_SPLITS; ++s) {
+                        if (s < splits) {
+                            const float w = __expf(ms[s] - mm);
+                            l = fmaf(pbuf[s * MG_PART + 1], w, l);
+                            o = fmaf(pbuf[s * MG_PART + 8 + tid], w, o);
+                        }
                     }
                     p.ctx[(size_t)b * d + h * 64 + tid] = __float2bfloat16_rn(o / l);
                 }
@@ -614,8 +630,7 @@ __device__ __forceinline__ void prefetch_linear(const MegaParams& p, const Phase
         if (tid < lines) prefetch_l2(gamma + tid * 32);
         else if (tid < 2 * lines) prefetch_l2(beta + (tid - lines) * 32);
     }
-    const bool head = kind == PH_HEAD;
-    const int ks_shift = head ? 0 : 3, rt = head ? 16 : 8, tpr = MG_WARPS >> ks_shift;
+    const int ks_shift = kind == PH_HEAD ? 0 : kind == PH_LINEAR_WIDE ? 2 : 3, rt = kind == PH_LINEAR ? 8 : 16, tpr = MG_WARPS >> ks_shift;
     const int tl = warp >> ks_shift, ks_id = warp & ((1 << ks_shift) - 1);
     const int c0 = (ks_id * C) >> ks_shift, c1 = ((ks_id + 1) * C) >> ks_shift;
     const int n0 = ((int)blockIdx.x * tpr + tl) * rt;
@@ -673,8 +688,21 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_mega_kernel(const _
     for (int ph = 0; ph < n_phases; ++ph) {
         const PhaseDesc& D = sdesc[ph & 1];
         const int kind = D.kind;
+        if (kind != PH_SELF_ATTN && kind != PH_CROSS_ATTN) {
+            // activations of a linear layer -> shared memory (ONE copy of this code for the three tile geometries below; the
+            // first weight tile was requested into L2 before the grid barrier)
+            bf16* act_s = reinterpret_cast<bf16*>(mg_smem + MG_RED_BYTES);
+            if (D.stage == ST_COPY) stage_copy(act_s, D.src, p.M, D.K, D.vpr_rcp);
+            else if (p.M <= 2) stage_layernorm_wide(p, act_s, reinterpret_cast<float*>(mg_smem), D.gamma, D.beta);
+            else stage_layernorm_rows(p, act_s, D.gamma, D.beta);
+            if (trace != nullptr) trace[8 * ph + 1] = clock64();
+            __syncthreads();
+            if (trace != nullptr) trace[8 * ph + 2] = clock64();
+        }
         if (kind == PH_LINEAR) {
             linear_phase<NM, MG_LAYER_KS, false>(p, D, pos, mg_smem, trace != nullptr ? trace + 8 * ph : nullptr);
+        } else if (kind == PH_LINEAR_WIDE) {
+            linear_phase<NM, MG_WIDE_KS, true>(p, D, pos, mg_smem, trace != nullptr ? trace + 8 * ph : nullptr);
         } else if (kind == PH_HEAD) {
             linear_phase<NM, MG_HEAD_KS, true>(p, D, pos, mg_smem, trace != nullptr ? trace + 8 * ph : nullptr);
         } else if (kind == PH_SELF_ATTN) {   // cached self-attention over cur_len keys (newest row appended by the qkv epilogue)
@@ -764,7 +792,12 @@ void Session::build_mega_table() {
         o.kind = PH_LINEAR; o.W = (const bf16*)l.w; o.bias = l.b; o.N = l.n; o.K = l.k; o.stage = stage; o.epi = epi;
         if (ln != nullptr) { o.gamma = ln->g; o.beta = ln->b; }
         o.src = (const bf16*)src; o.out_bf16 = (bf16*)out_bf16;
-        fill_geometry(o, MG_LAYER_KS, false, mega_grid);
+        if ((l.n + 7) / 8 > 2 * mega_grid) {      // more than two rounds of 8-row tiles: 16-row tiles, two per CTA and round
+            o.kind = PH_LINEAR_WIDE;
+            fill_geometry(o, MG_WIDE_KS, true, mega_grid);
+        } else {
+            fill_geometry(o, MG_LAYER_KS, false, mega_grid);
+        }
     };
     for (int l = 0; l < g.dec_layers; ++l) {
         const DecLayer& L = m->dec[l];
