@@ -688,6 +688,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_mega_kernel(const _
     for (int ph = 0; ph < n_phases; ++ph) {
         const PhaseDesc& D = sdesc[ph & 1];
         const int kind = D.kind;
+        // the next descriptor is requested now and parked in a register: its round trip overlaps this phase's work
+        unsigned long long nd_word = 0ull;
+        if (tid < 16 && ph + 1 < n_phases) nd_word = __ldg(reinterpret_cast<const unsigned long long*>(p.table + ph + 1) + tid);
         if (kind != PH_SELF_ATTN && kind != PH_CROSS_ATTN) {
             // activations of a linear layer -> shared memory (ONE copy of this code for the three tile geometries below; the
             // first weight tile was requested into L2 before the grid barrier)
@@ -712,10 +715,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_mega_kernel(const _
         }
         if (trace != nullptr) trace[8 * ph + 4] = clock64();
         if (ph + 1 == n_phases) break;
-        // arrive at the grid barrier, fetch the next descriptor and request what the next phase reads first, then wait
-        grid_arrive(bar);
-        const PhaseDesc* nd = p.table + ph + 1;
-        if (tid < 16) reinterpret_cast<unsigned long long*>(&sdesc[(ph + 1) & 1])[tid] = reinterpret_cast<const unsigned long long*>(nd)[tid];
+        // arrive at the grid barrier, request what the next phase reads first, then wait
+        if (tid < 16) reinterpret_cast<unsigned long long*>(&sdesc[(ph + 1) & 1])[tid] = nd_word;
+        grid_arrive(bar);                         // (its block barrier publishes the descriptor to the CTA)
+        const PhaseDesc* nd = &sdesc[(ph + 1) & 1];
         const int k2 = nd->kind;
         if (k2 == PH_CROSS_ATTN) prefetch_cross(p, nd->k_pages, nd->v_pages);
         else if (k2 == PH_SELF_ATTN) prefetch_self(p, nd->k_pages, nd->v_pages, cur_len);
