@@ -198,6 +198,59 @@ def test_whole_step_kernel_matches_the_multi_kernel_path(size, B, steps):
         _abi.call("wb_set_small_batch_path", 2)
 
 
+def test_whole_step_kernel_edge_cases():
+    """Whole-step kernel with max_batch > batch (cache strides come from the session, not the batch), rows that hit EOS in the
+    middle (their attention items are skipped from then on) and other batch sizes on the same engine (the key-split
+    count changes with the batch, the step graph is re-captured): same ids and, for the rows still running, the same logits
+    as the multi-kernel path."""
+    from whisper_trtllm_b200 import _abi
+    steps = 23
+    cfg = synth.make_config("tiny.en", max_length=steps + 1)
+    sd = synth.make_weights(cfg, seed=33)
+    mel = synth.make_mel(7, seed=3)
+    ref_ids, _, _ = R.greedy(mel, sd, cfg, return_logits=True)
+    eos = cfg["eos_token_id"]
+    forced = ref_ids.clone()
+    forced[1, 6] = eos      # chosen by step 5: row 1 is finished from step 6 on
+    forced[4, 10] = eos     # chosen by step 9
+    try:
+        outs, subs = {}, {}
+        for mode in (0, 2):
+            _abi.call("wb_set_small_batch_path", mode)
+            eng = WhisperEngine(cfg, sd, dtype="bfloat16", max_batch=11, enc_chunk=4, device=DEV)
+            ids, lg = eng.generate(mel.to(DEV), forced_tokens=forced, dump_logits_steps=steps)
+            outs[mode] = (ids.cpu(), lg.float().cpu())
+            subs[mode] = {b: eng.generate(mel[:b].to(DEV)).cpu() for b in (1, 4, 2, 7)}
+            eng.close()
+        ids0, lg0 = outs[0]
+        ids2, lg2 = outs[2]
+        assert torch.equal(ids2, ids0)
+        assert torch.equal(ids2.long(), forced)     # teacher forcing overrides the pad-after-EOS substitution (tests only)
+        for s in range(steps):
+            alive = [r for r in range(7) if not ((r == 1 and s >= 6) or (r == 4 and s >= 10))]
+            assert torch.isfinite(lg2[s][alive]).all(), s
+            assert _rel(lg2[s][alive], lg0[s][alive]) < 1e-2, s
+        for b in (1, 4, 2, 7):
+            assert subs[2][b].shape == subs[0][b].shape
+            assert torch.equal(subs[2][b][:, :5], subs[0][b][:, :5]), b
+            assert float((subs[2][b] == subs[0][b]).float().mean()) >= 0.5, b
+        # free-running early stop of one row: the token row 0 emits at position 4 becomes EOS (= pad); the row is padded from
+        # then on while the others keep running (generation/utils.py:1506-1510)
+        eos_tok = int(subs[0][7][0, 4])
+        cfg3 = dict(cfg, eos_token_id=eos_tok, pad_token_id=eos_tok)
+        early = {}
+        for mode in (0, 2):
+            _abi.call("wb_set_small_batch_path", mode)
+            eng = WhisperEngine(cfg3, sd, dtype="bfloat16", max_batch=7, device=DEV)
+            early[mode] = eng.generate(mel.to(DEV)).cpu()
+            eng.close()
+        for mode in (0, 2):
+            assert early[mode].shape[1] == steps + 1 and (early[mode][0, 4:] == eos_tok).all(), mode
+        assert torch.equal(early[2][:, :5], early[0][:, :5])
+    finally:
+        _abi.call("wb_set_small_batch_path", 2)
+
+
 def test_multi_stream_sub_batches_give_the_same_tokens():
     """n_streams > 1: the batch is split into sub-sessions whose greedy loops are interleaved on separate streams
     (wb_decode_run_multi; bulk-ring cross-attention + lean decode GEMM so that their kernels can share an SM).  Rows are
