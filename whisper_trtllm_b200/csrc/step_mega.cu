@@ -304,10 +304,12 @@ __device__ __forceinline__ void linear_epilogue(const MegaParams& p, const Phase
     }
 }
 
-// out[m, n] = epilogue( sum_k act[m, k] * W[n, k] ) for all n < N, m < 8 * NM; the activations are already staged.
+// out[m, n] = epilogue( sum_k act[m, k] * W[n, k] ) for all n < N, m < 8 * NM; the activations are already staged and the
+// first weight tile is already in registers.
 // KS warps split K for one tile of RT = 8 / 16 weight rows; a CTA works on 8 / KS tiles per round; tiles (r * grid + cta) * TPR + ..
 template <int NM, int KS, bool R16>
-__device__ __forceinline__ void linear_phase(const MegaParams& p, const PhaseDesc& D, int pos, uint8_t* smem, long long* tr) {
+__device__ __forceinline__ void linear_phase(const MegaParams& p, const PhaseDesc& D, int pos, uint8_t* smem, long long* tr,
+                                             const uint4 (&first)[8]) {
     constexpr int TPR = MG_WARPS / KS, RT_SHIFT = R16 ? 4 : 3, RT = 1 << RT_SHIFT, CPS = R16 ? 4 : 8;
     float* red_s = reinterpret_cast<float*>(smem);
     bf16* act_s = reinterpret_cast<bf16*>(smem + MG_RED_BYTES);
@@ -437,9 +439,12 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const PhaseDes
         if (sc == nsc - 1) finish(r);
     };
 
+    // `first` = super-chunk 0 of round 0, requested before the grid barrier (prefetch_linear): it has been in flight during the
+    // wait and the staging
     uint4 cur[8], nxt[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cur[i] = first[i];
     if (total > 0) {
-        issue(0, 0, cur);
         if constexpr (KS > 1) preload(0, pre_cur);
     }
     if (tr != nullptr) tr[3] = clock64();
@@ -618,8 +623,8 @@ __device__ __forceinline__ void attention_phase(const MegaParams& p, const bool 
 
 // ---- requests for what the NEXT phase reads first, issued between the arrival at the grid barrier and the wait (none of it
 // depends on the other CTAs): the first weight tile of this warp, LayerNorm parameters, bias; the first attention unit
-__device__ __forceinline__ void prefetch_linear(const MegaParams& p, const PhaseDesc* nd, int kind) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+__device__ __forceinline__ void prefetch_linear(const MegaParams& p, const PhaseDesc* nd, int kind, uint4 (&first)[8]) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
     const bf16* W = nd->W;
     const float* gamma = nd->gamma;
     const float* beta = nd->beta;
@@ -630,16 +635,36 @@ __device__ __forceinline__ void prefetch_linear(const MegaParams& p, const Phase
         if (tid < lines) prefetch_l2(gamma + tid * 32);
         else if (tid < 2 * lines) prefetch_l2(beta + (tid - lines) * 32);
     }
-    const int ks_shift = kind == PH_HEAD ? 0 : kind == PH_LINEAR_WIDE ? 2 : 3, rt = kind == PH_LINEAR ? 8 : 16, tpr = MG_WARPS >> ks_shift;
+    const bool rows16 = kind != PH_LINEAR;
+    const int ks_shift = kind == PH_HEAD ? 0 : kind == PH_LINEAR_WIDE ? 2 : 3, rt = rows16 ? 16 : 8, tpr = MG_WARPS >> ks_shift;
     const int tl = warp >> ks_shift, ks_id = warp & ((1 << ks_shift) - 1);
     const int c0 = (ks_id * C) >> ks_shift, c1 = ((ks_id + 1) * C) >> ks_shift;
     const int n0 = ((int)blockIdx.x * tpr + tl) * rt;
-    if (n0 >= N) return;
-    if (bias != nullptr && lane == 31) prefetch_l2(bias + n0);
-    const int lines = ((c1 - c0) * 64 + 127) >> 7;      // <= 32 for K <= 4096
-    if (lane < lines) {
-        const bf16* base = W + c0 * 32 + lane * 64;
-        for (int r = 0; r < rt; ++r) prefetch_l2(base + (size_t)min(n0 + r, N - 1) * K);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) first[j] = make_uint4(0, 0, 0, 0);
+    if (nd->rounds_base == 0 && (int)blockIdx.x * tpr >= nd->rounds_rem) return;   // this CTA has no round in that phase
+    if (bias != nullptr && lane == 31 && n0 < N) prefetch_l2(bias + n0);
+    // super-chunk 0 of round 0 of this warp, straight into the registers linear_phase starts from (same layout as its issue())
+    const bf16* pa = W + (size_t)min(n0 + g, N - 1) * K + tq * 8;
+    if (rows16) {
+        const bf16* pb = W + (size_t)min(n0 + g + 8, N - 1) * K + tq * 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (c0 + j < c1) {
+                first[2 * j] = ldg_nc16(pa + (c0 + j) * 32);
+                first[2 * j + 1] = ldg_nc16(pb + (c0 + j) * 32);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (c0 + j < c1) first[j] = ldg_nc16(pa + (c0 + j) * 32);
+    }
+    // the second super-chunk (fc2, LM head) into L2
+    const int cps = rows16 ? 4 : 8;
+    if (c0 + cps < c1) {
+        const int row = rows16 ? lane >> 1 : lane >> 2, line = rows16 ? lane & 1 : lane & 3;
+        if (c0 + cps + line * 2 < c1) prefetch_l2(W + (size_t)min(n0 + row, N - 1) * K + (c0 + cps + line * 2) * 32);
     }
 }
 
@@ -683,6 +708,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_mega_kernel(const _
     long long* const trace = (p.trace != nullptr && blockIdx.x == 0 && tid == 0) ? p.trace : nullptr;
     if (tid < 16) reinterpret_cast<unsigned long long*>(&sdesc[0])[tid] = reinterpret_cast<const unsigned long long*>(p.table)[tid];
     __syncthreads();
+    uint4 first[8];                            // first weight tile of the next linear phase, requested before its grid barrier
+    prefetch_linear(p, &sdesc[0], sdesc[0].kind, first);
     if (trace != nullptr) trace[0] = clock64();
 #pragma unroll 1
     for (int ph = 0; ph < n_phases; ++ph) {
@@ -703,11 +730,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_mega_kernel(const _
             if (trace != nullptr) trace[8 * ph + 2] = clock64();
         }
         if (kind == PH_LINEAR) {
-            linear_phase<NM, MG_LAYER_KS, false>(p, D, pos, mg_smem, trace != nullptr ? trace + 8 * ph : nullptr);
+            linear_phase<NM, MG_LAYER_KS, false>(p, D, pos, mg_smem, trace != nullptr ? trace + 8 * ph : nullptr, first);
         } else if (kind == PH_LINEAR_WIDE) {
-            linear_phase<NM, MG_WIDE_KS, true>(p, D, pos, mg_smem, trace != nullptr ? trace + 8 * ph : nullptr);
+            linear_phase<NM, MG_WIDE_KS, true>(p, D, pos, mg_smem, trace != nullptr ? trace + 8 * ph : nullptr, first);
         } else if (kind == PH_HEAD) {
-            linear_phase<NM, MG_HEAD_KS, true>(p, D, pos, mg_smem, trace != nullptr ? trace + 8 * ph : nullptr);
+            linear_phase<NM, MG_HEAD_KS, true>(p, D, pos, mg_smem, trace != nullptr ? trace + 8 * ph : nullptr, first);
         } else if (kind == PH_SELF_ATTN) {   // cached self-attention over cur_len keys (newest row appended by the qkv epilogue)
             attention_phase(p, true, D.k_pages, D.v_pages, cur_len, 1, mg_smem, item_cnt);
         } else {                             // cross-attention over the encoder K/V projected once per utterance
@@ -720,9 +747,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_mega_kernel(const _
         grid_arrive(bar);                         // (its block barrier publishes the descriptor to the CTA)
         const PhaseDesc* nd = &sdesc[(ph + 1) & 1];
         const int k2 = nd->kind;
-        if (k2 == PH_CROSS_ATTN) prefetch_cross(p, nd->k_pages, nd->v_pages);
-        else if (k2 == PH_SELF_ATTN) prefetch_self(p, nd->k_pages, nd->v_pages, cur_len);
-        else prefetch_linear(p, nd, k2);
+        if (k2 == PH_CROSS_ATTN || k2 == PH_SELF_ATTN) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) first[j] = make_uint4(0, 0, 0, 0);      // dead across the attention phase
+            if (k2 == PH_CROSS_ATTN) prefetch_cross(p, nd->k_pages, nd->v_pages);
+            else prefetch_self(p, nd->k_pages, nd->v_pages, cur_len);
+        } else {
+            prefetch_linear(p, nd, k2, first);
+        }
         if (trace != nullptr) trace[8 * ph + 5] = clock64();
         grid_wait(bar, epoch);
         if (trace != nullptr) trace[8 * ph + 8] = clock64();   // = slot 0 of the next phase
