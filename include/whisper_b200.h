@@ -66,10 +66,10 @@ WB_API int wb_set_decode_attention_backend(int backend);
 /* paged self-attention kernel: 0 = one warp per (utterance, head) item (default, measured fastest), 1..4 = one CTA per item with
  * (threads, batch depth) = (128, 4) (128, 8) (64, 8) (256, 4), 5..6 = warp-kernel tuning variants */
 WB_API int wb_set_self_attention_warp_kernel(int variant);
-/* decode steps of <= 16 utterances (bf16): 2 (default) = ONE persistent cooperative kernel per token, phases separated by grid
- * barriers (csrc/step_mega.cu); 1 = weight-streaming GEMV kernels with the LayerNorm fused in front, 8 launches per layer
- * (csrc/gemv.cu); 0 = the large-batch kernels.  Captured CUDA graphs keep the path they were captured with. */
-WB_API int wb_set_small_batch_path(int mode);
+/* decode steps of <= 16 utterances (bf16) run as ONE persistent cooperative kernel per token, phases separated by grid barriers
+ * (csrc/step_mega.cu); default 1 = on, 0 = the multi-kernel step for every batch size (A/B measurements, parity tests).
+ * Captured CUDA graphs keep the path they were captured with. */
+WB_API int wb_set_small_batch_path(int enabled);
 /* measurement hook of the whole-step kernel: device buffer of 8 * (8 * decoder_layers + 2) int64; CTA 0 stores its SM clock
  * at 8 points of every phase: [0] start, [1] activations staged, [2] block barrier passed, [3] first weight tile requested,
  * [4] phase done, [5] arrived at the grid barrier + next phase prefetched, [8] = next [0] grid barrier passed

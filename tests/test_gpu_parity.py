@@ -174,7 +174,7 @@ def test_whole_step_kernel_matches_the_multi_kernel_path(size, B, steps):
     ref_ids, _, ref_logits = R.greedy(mel, sd, cfg, return_logits=True)
     try:
         lg, ids = {}, {}
-        for mode in (0, 2):
+        for mode in (0, 1):
             _abi.call("wb_set_small_batch_path", mode)
             eng = WhisperEngine(cfg, sd, dtype="bfloat16", max_batch=B, device=DEV)
             n0 = eng.launch_count()
@@ -183,19 +183,19 @@ def test_whole_step_kernel_matches_the_multi_kernel_path(size, B, steps):
             _, l = eng.generate(mel.to(DEV), forced_tokens=ref_ids, dump_logits_steps=steps)
             lg[mode] = l.float().cpu()
             eng.close()
-            if mode == 2:   # the step really is two launches (whole-step kernel + logits processors / argmax)
+            if mode == 1:   # the step really is two launches (whole-step kernel + logits processors / argmax)
                 assert launches <= 2 * steps + 60 + 12 * cfg["encoder_layers"], launches
-        assert lg[2].shape == lg[0].shape == (steps, B, cfg["vocab_size"])
-        assert torch.isfinite(lg[2]).all()
+        assert lg[1].shape == lg[0].shape == (steps, B, cfg["vocab_size"])
+        assert torch.isfinite(lg[1]).all()
         for s in range(steps):
-            assert _rel(lg[2][s], ref_logits[s]) < BF16_LOGIT_TOL, s
-            assert _rel(lg[2][s], lg[0][s]) < 1e-2, s
+            assert _rel(lg[1][s], ref_logits[s]) < BF16_LOGIT_TOL, s
+            assert _rel(lg[1][s], lg[0][s]) < 1e-2, s
         # free-running loops may part ways at a near-tie and never meet again: the first tokens must agree, most rows overall
-        assert ids[2].shape == ids[0].shape
-        assert torch.equal(ids[2][:, :4], ids[0][:, :4])
-        assert float((ids[2] == ids[0]).float().mean()) >= 0.5
+        assert ids[1].shape == ids[0].shape
+        assert torch.equal(ids[1][:, :4], ids[0][:, :4])
+        assert float((ids[1] == ids[0]).float().mean()) >= 0.5
     finally:
-        _abi.call("wb_set_small_batch_path", 2)
+        _abi.call("wb_set_small_batch_path", 1)
 
 
 def test_whole_step_kernel_edge_cases():
@@ -215,7 +215,7 @@ def test_whole_step_kernel_edge_cases():
     forced[4, 10] = eos     # chosen by step 9
     try:
         outs, subs = {}, {}
-        for mode in (0, 2):
+        for mode in (0, 1):
             _abi.call("wb_set_small_batch_path", mode)
             eng = WhisperEngine(cfg, sd, dtype="bfloat16", max_batch=11, enc_chunk=4, device=DEV)
             ids, lg = eng.generate(mel.to(DEV), forced_tokens=forced, dump_logits_steps=steps)
@@ -223,7 +223,7 @@ def test_whole_step_kernel_edge_cases():
             subs[mode] = {b: eng.generate(mel[:b].to(DEV)).cpu() for b in (1, 4, 2, 7)}
             eng.close()
         ids0, lg0 = outs[0]
-        ids2, lg2 = outs[2]
+        ids2, lg2 = outs[1]
         assert torch.equal(ids2, ids0)
         assert torch.equal(ids2.long(), forced)     # teacher forcing overrides the pad-after-EOS substitution (tests only)
         for s in range(steps):
@@ -231,24 +231,24 @@ def test_whole_step_kernel_edge_cases():
             assert torch.isfinite(lg2[s][alive]).all(), s
             assert _rel(lg2[s][alive], lg0[s][alive]) < 1e-2, s
         for b in (1, 4, 2, 7):
-            assert subs[2][b].shape == subs[0][b].shape
-            assert torch.equal(subs[2][b][:, :5], subs[0][b][:, :5]), b
-            assert float((subs[2][b] == subs[0][b]).float().mean()) >= 0.5, b
+            assert subs[1][b].shape == subs[0][b].shape
+            assert torch.equal(subs[1][b][:, :5], subs[0][b][:, :5]), b
+            assert float((subs[1][b] == subs[0][b]).float().mean()) >= 0.5, b
         # free-running early stop of one row: the token row 0 emits at position 4 becomes EOS (= pad); the row is padded from
         # then on while the others keep running (generation/utils.py:1506-1510)
         eos_tok = int(subs[0][7][0, 4])
         cfg3 = dict(cfg, eos_token_id=eos_tok, pad_token_id=eos_tok)
         early = {}
-        for mode in (0, 2):
+        for mode in (0, 1):
             _abi.call("wb_set_small_batch_path", mode)
             eng = WhisperEngine(cfg3, sd, dtype="bfloat16", max_batch=7, device=DEV)
             early[mode] = eng.generate(mel.to(DEV)).cpu()
             eng.close()
-        for mode in (0, 2):
+        for mode in (0, 1):
             assert early[mode].shape[1] > 5 and (early[mode][0, 4:] == eos_tok).all(), mode
-        assert torch.equal(early[2][:, :5], early[0][:, :5])
+        assert torch.equal(early[1][:, :5], early[0][:, :5])
     finally:
-        _abi.call("wb_set_small_batch_path", 2)
+        _abi.call("wb_set_small_batch_path", 1)
 
 
 def test_multi_stream_sub_batches_give_the_same_tokens():
@@ -366,10 +366,10 @@ def test_encoder_stem_matches_oracle(dtype, tol):
 
 
 def test_small_and_large_batch_decode_paths_agree():
-    """bf16 decode has three paths: B <= 16 -> ONE persistent cooperative kernel per token (csrc/step_mega.cu, mode 2, default) or
-    weight-streaming GEMV kernels with fused LayerNorm (csrc/gemv.cu, mode 1); otherwise tcgen05 GEMMs with split-K / deferred
-    reduction (mode 0).  All must match the fp32 oracle's teacher-forced logits within the stated bf16 tolerance, and each other
-    far more tightly (same rounding points, different summation order)."""
+    """bf16 decode has two paths: B <= 16 -> ONE persistent cooperative kernel per token (csrc/step_mega.cu, default); otherwise
+    (or with the switch off) tcgen05 GEMMs with split-K / deferred reduction, 11 kernels per layer.  Both must match the fp32
+    oracle's teacher-forced logits within the stated bf16 tolerance, and each other far more tightly (same rounding points,
+    different summation order)."""
     from whisper_trtllm_b200 import _abi
     cfg = synth.make_config("tiny.en", max_length=20)
     sd = synth.make_weights(cfg, seed=8)
@@ -377,24 +377,23 @@ def test_small_and_large_batch_decode_paths_agree():
     ref_ids, _, ref_logits = R.greedy(mel, sd, cfg, return_logits=True)
     steps = ref_ids.shape[1] - 1
     try:
-        # large path at B = 20 (> 16)
+        # multi-kernel path at B = 20 (> 16)
         eng = WhisperEngine(cfg, sd, dtype="bfloat16", max_batch=20, device=DEV)
         _, lg20 = eng.generate(mel.to(DEV), forced_tokens=ref_ids, dump_logits_steps=steps)
         for s in (0, 1, 5, steps - 1):
             assert _rel(lg20[s], ref_logits[s]) < BF16_LOGIT_TOL, s
-        # the same 6 rows through the small path and, with the switch off, through the large path
+        # the same 6 rows through the whole-step kernel and, with the switch off, through the multi-kernel path
         outs = {}
-        for flag in (2, 1, 0):
+        for flag in (1, 0):
             _abi.call("wb_set_small_batch_path", flag)
             e = WhisperEngine(cfg, sd, dtype="bfloat16", max_batch=6, device=DEV)
             _, lg = e.generate(mel[:6].to(DEV), forced_tokens=ref_ids[:6], dump_logits_steps=steps)
             outs[flag] = lg.clone()
             e.close()
         for s in (0, 1, 5, steps - 1):
-            for flag in (2, 1):
-                assert _rel(outs[flag][s], ref_logits[s][:6]) < BF16_LOGIT_TOL, (flag, s)
-                assert _rel(outs[flag][s], outs[0][s]) < 1e-2, (flag, s)
+            assert _rel(outs[1][s], ref_logits[s][:6]) < BF16_LOGIT_TOL, s
+            assert _rel(outs[1][s], outs[0][s]) < 1e-2, s
             assert _rel(outs[0][s], lg20[s][:6]) < 1e-2, s
         eng.close()
     finally:
-        _abi.call("wb_set_small_batch_path", 2)
+        _abi.call("wb_set_small_batch_path", 1)

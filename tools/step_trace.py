@@ -31,7 +31,7 @@ def main():
     L = cfg["decoder_layers"]
     n_phases = 8 * L + 1
     trace = torch.zeros(8 * (n_phases + 1), dtype=torch.int64, device=dev)
-    _abi.call("wb_set_small_batch_path", 2)
+    _abi.call("wb_set_small_batch_path", 1)
     _abi.call("wb_set_step_trace", ptr(trace))
     eng = WhisperEngine(cfg, sd, dtype="bf16", max_batch=a.batch, enc_chunk=min(a.batch, 32), device=dev)
     del sd

@@ -485,79 +485,22 @@ void Session::decode_begin(int B, cudaStream_t st) {
     if (use_mega()) decoder_embed(tokens, g.max_tgt, state, m->emb, m->dec_pos, m->dtype, dx, B, g.d_model, st);
 }
 
-// 0 = always the large-batch kernels, 1 = GEMV kernels (8 launches per layer), 2 = one persistent kernel per token (default)
-static int& small_batch_mode() {
-    static int mode = 2;
-    return mode;
+// small batches (B <= 16, bf16) run the whole decoder for one token in ONE persistent cooperative kernel (step_mega.cu); the
+// switch exists for A/B measurements and the parity tests (0 = always the multi-kernel step)
+static bool& whole_step_kernel_enabled() {
+    static bool on = true;
+    return on;
 }
-void set_small_batch_path(int mode) { small_batch_mode() = mode; }
+void set_small_batch_path(bool on) { whole_step_kernel_enabled() = on; }
 
-bool Session::use_mega() const {
-    const ModelConfig& g = m->cfg;
-    return small_batch_mode() == 2 && get_gemm_backend() == 0 && skinny_gemv_supported(batch, g.d_model, m->dtype) && mega_supported();
-}
-
-// B <= 16 (bf16): weight-streaming GEMV kernels with the LayerNorm fused in front, 8 launches per layer (gemv.cu)
-void Session::decode_step_small(cudaStream_t st) {
-    const ModelConfig& g = m->cfg;
-    const int d = g.d_model, dt = m->dtype, B = batch;
-    const int* active = &state->active;
-    auto lng = [&](const LNorm& n, const Linear& l, void* out, long long ldo, int odt, int act) {
-        ProfScope ps(this, PROF_DEC_GEMM, st);
-        ln_gemv(dx, n.g, n.b, 1e-5f, l.w, l.k, l.b, out, ldo, odt, B, l.n, d, act, active, st);
-    };
-    auto gres = [&](const void* a, long long lda, const Linear& l) {
-        ProfScope ps(this, PROF_DEC_GEMM, st);
-        gemv_residual(a, lda, l.w, l.k, l.b, dx, d, B, l.n, l.k, active, st);
-    };
-    decoder_embed(tokens, g.max_tgt, state, m->emb, m->dec_pos, dt, dx, B, d, st);
-    for (int l = 0; l < g.dec_layers; ++l) {
-        const DecLayer& L = m->dec[l];
-        lng(L.ln1, L.qkv, dqkv, 3 * d, dt, 0);
-        {
-            DecAttnArgs a;
-            a.dtype = dt; a.q = dqkv; a.q_stride = 3 * d; a.out = datt; a.out_stride = d; a.B = B; a.H = g.n_heads;
-            a.state = state; a.row_active = unfinished;
-            a.k_new = eoff(dqkv, d, dt); a.v_new = eoff(dqkv, 2 * d, dt); a.new_stride = 3 * d;
-            a.k_pages = eoff(self_k, (size_t)l * self_layer_elems(), dt);
-            a.v_pages = eoff(self_v, (size_t)l * self_layer_elems(), dt);
-            a.page_table = page_table; a.pages_per_seq = pages_per_seq; a.page_tokens = PAGE_TOKENS;
-            ProfScope ps(this, PROF_SELF_ATTN, st);
-            decode_attention(a, st);
-        }
-        gres(datt, d, L.out);
-        lng(L.ln2, L.cq, dq, d, dt, 0);
-        {
-            DecAttnArgs a;
-            a.dtype = dt; a.q = dq; a.q_stride = d; a.out = datt; a.out_stride = d; a.B = B; a.H = g.n_heads;
-            a.state = nullptr; a.n_keys = g.n_ctx; a.active = active; a.row_active = unfinished;
-            const size_t per_kv = (size_t)max_batch * g.n_heads * g.n_ctx * 64;
-            a.k = eoff(cross, (size_t)l * cross_layer_elems(), dt);
-            a.v = eoff(cross, (size_t)l * cross_layer_elems() + per_kv, dt);
-            a.kv_bstride = (long long)g.n_heads * g.n_ctx * 64; a.kv_hstride = (long long)g.n_ctx * 64;
-            ProfScope ps(this, PROF_CROSS_ATTN, st);
-            decode_attention(a, st);
-        }
-        gres(datt, d, L.cout);
-        lng(L.ln3, L.fc1, dffn, g.ffn, dt, 1);
-        gres(dffn, g.ffn, L.fc2);
-    }
-    {
-        // final LayerNorm + LM head (proj_out shares storage with embed_tokens, no bias) -> fp32 logits
-        ProfScope ps(this, PROF_LM_HEAD, st);
-        ln_gemv(dx, m->dec_ln.g, m->dec_ln.b, 1e-5f, m->emb, d, nullptr, logits, g.vocab, F32, B, g.vocab, d, 0, active, st);
-    }
-}
+bool Session::use_mega() const { return whole_step_kernel_enabled() && get_gemm_backend() == 0 && mega_supported(); }
 
 void Session::decode_step(cudaStream_t st) {
     WB_REQUIRE(batch > 0, "decode_begin was not called");
     const ModelConfig& g = m->cfg;
     const int d = g.d_model, dt = m->dtype, B = batch;
-    const bool small = small_batch_mode() != 0 && get_gemm_backend() == 0 && skinny_gemv_supported(B, d, dt) &&
-                       skinny_gemv_supported(B, g.ffn, dt) && d <= 1024;
     const bool mega = use_mega();
     if (mega) decode_step_mega(st);
-    else if (small) decode_step_small(st);
     else decode_step_large(st);
     // logits -> processors -> argmax -> EOS / length bookkeeping, common to both paths
     if (logits_dump != nullptr && steps_enqueued < logits_dump_steps)

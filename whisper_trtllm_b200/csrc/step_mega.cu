@@ -13,7 +13,7 @@
 //     small layers split K over the 8 warps of a CTA and reduce through shared memory in a fixed order (deterministic);
 //   * attention items are split over CTAs along the keys (cross: 1500 frames / split) so that a single utterance still uses
 //     every SM; partials (max, sum, acc[64]) are merged in a fixed order by the last CTA to arrive at the item's counter.
-// Semantics and rounding points are those of the multi-kernel paths (runtime.cu decode_step_small / decode_step_large):
+// Semantics and rounding points are those of the multi-kernel step (runtime.cu decode_step_large):
 // LayerNorm eps 1e-5 in fp32 (layers/normalization.py:6-30), bf16 activations into every Linear (layers/linear.py:38-139),
 // fp32 residual stream, erf GELU, q pre-scaled in the packed weights, fp32 softmax, no mask (model.py:240-304),
 // position = cur_len - 1 (model.py:423-425), tied LM head without bias (modeling_whisper.py:1335,1433).

@@ -47,13 +47,6 @@ bool gemm_tc_supported(const GemmArgs& a);
 void set_gemm_backend(int backend);  // 0 = auto (tcgen05 for bf16), 1 = force SIMT
 int get_gemm_backend();
 
-// Small-batch (M <= 16) weight-streaming kernels with the LayerNorm fused in front (gemv.cu): bf16 weights / activations.
-bool skinny_gemv_supported(int M, int K, int dtype);
-void ln_gemv(const float* x, const float* gamma, const float* beta, float eps, const void* W, long long ldw, const float* bias, void* out,
-             long long ldo, int out_dtype, int M, int N, int d, int act, const int* active, cudaStream_t st);
-void gemv_residual(const void* a, long long lda, const void* W, long long ldw, const float* bias, float* x, long long ldx, int M, int N,
-                   int K, const int* active, cudaStream_t st);
-
 // LayerNorm over the last dim: x fp32 [rows, d] -> out (out_dtype) [rows, d], optional fp32 copy out2
 void layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_dtype, float* out2,
                int rows, int d, float eps, const int* active, cudaStream_t stream);

@@ -132,8 +132,7 @@ struct Session : Buffers {
     void set_encoder_output(const void* enc_states, int dtype, int B, cudaStream_t s);  // external encoder states
     void decode_begin(int B, cudaStream_t s);
     void decode_step(cudaStream_t s);
-    void decode_step_large(cudaStream_t s);   // tcgen05 / CUDA-core GEMMs, split-K with deferred reduction (any batch)
-    void decode_step_small(cudaStream_t s);   // B <= 16, bf16: weight-streaming GEMV kernels with fused LayerNorm
+    void decode_step_large(cudaStream_t s);   // tcgen05 / CUDA-core GEMMs, split-K with deferred reduction (any batch), 268 launches
     void decode_step_mega(cudaStream_t s);    // B <= 16, bf16: ONE persistent cooperative kernel per token (step_mega.cu)
     bool mega_supported() const;
     bool use_mega() const;                    // this batch goes through the whole-step kernel
