@@ -68,7 +68,7 @@ WB_API int wb_set_decode_attention_backend(int backend);
 WB_API int wb_set_self_attention_warp_kernel(int variant);
 /* decode steps of <= 16 utterances (bf16) run as ONE persistent cooperative kernel per token, phases separated by grid barriers
  * (csrc/step_mega.cu); default 1 = on, 0 = the multi-kernel step for every batch size (A/B measurements, parity tests).
- * Captured CUDA graphs keep the path they were captured with. */
+ * Sessions decoded concurrently by wb_decode_run_multi never use it (a cooperative grid needs every SM to itself). */
 WB_API int wb_set_small_batch_path(int enabled);
 /* measurement hook of the whole-step kernel: device buffer of 8 * (8 * decoder_layers + 2) int64; CTA 0 stores its SM clock
  * at 8 points of every phase: [0] start, [1] activations staged, [2] block barrier passed, [3] first weight tile requested,

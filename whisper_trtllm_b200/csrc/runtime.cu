@@ -493,7 +493,8 @@ static bool& whole_step_kernel_enabled() {
 }
 void set_small_batch_path(bool on) { whole_step_kernel_enabled() = on; }
 
-bool Session::use_mega() const { return whole_step_kernel_enabled() && get_gemm_backend() == 0 && mega_supported(); }
+// (not when several sessions decode concurrently on their own streams: a cooperative grid needs every SM to itself)
+bool Session::use_mega() const { return whole_step_kernel_enabled() && exclusive && get_gemm_backend() == 0 && mega_supported(); }
 
 void Session::decode_step(cudaStream_t st) {
     WB_REQUIRE(batch > 0, "decode_begin was not called");
@@ -637,13 +638,15 @@ void Session::build_step_graph(cudaStream_t st) {
     WB_CHECK_CUDA(e);
     step_graph_batch = batch;
     step_graph_generation = m->generation_version;
+    step_graph_mega = use_mega();
 }
 
 // one decode step on the session's loop stream: CUDA-graph replay when possible, eager launches otherwise
 void Session::enqueue_step() {
     cudaStream_t st = loop_stream;
     if (graph_ok()) {
-        if (step_graph == nullptr || step_graph_batch != batch || step_graph_generation != m->generation_version) {
+        if (step_graph == nullptr || step_graph_batch != batch || step_graph_generation != m->generation_version ||
+            step_graph_mega != use_mega()) {
             try {
                 build_step_graph(st);
             } catch (const Error&) {
@@ -652,7 +655,8 @@ void Session::enqueue_step() {
             }
         }
     }
-    if (graph_ok() && step_graph != nullptr && step_graph_batch == batch && step_graph_generation == m->generation_version) {
+    if (graph_ok() && step_graph != nullptr && step_graph_batch == batch && step_graph_generation == m->generation_version &&
+        step_graph_mega == use_mega()) {
         WB_CHECK_CUDA(cudaGraphLaunch(step_graph, st));
         launch_counter().fetch_add(step_graph_launches, std::memory_order_relaxed);
         ++steps_enqueued;
@@ -674,6 +678,7 @@ void decode_run_multi(Session** ss, int n, int max_steps, int check_every, int* 
     if (check_every <= 0) check_every = 32;
     bool pending[8] = {}, stopped[8] = {};
     for (int k = 0; k < n; ++k) {
+        ss[k]->exclusive = n == 1;
         WB_CHECK_CUDA(cudaEventRecord(ss[k]->fence_event, caller));
         WB_CHECK_CUDA(cudaStreamWaitEvent(ss[k]->loop_stream, ss[k]->fence_event, 0));
     }

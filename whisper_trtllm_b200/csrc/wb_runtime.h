@@ -106,6 +106,8 @@ struct Session : Buffers {
     cudaGraphExec_t step_graph = nullptr;
     int step_graph_batch = 0;
     int step_graph_generation = -1;
+    bool step_graph_mega = false;     // the captured step is the whole-step kernel (small batches) / the multi-kernel step
+    bool exclusive = true;            // this session's loop is the only one running on the device (decode_run_multi, n == 1)
     long long step_graph_launches = 0;
     bool step_warm = false;           // one eager step has run (one-time kernel attribute setup done)
     bool graph_ok() const;
