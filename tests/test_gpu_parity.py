@@ -382,17 +382,19 @@ def test_small_and_large_batch_decode_paths_agree():
         _, lg20 = eng.generate(mel.to(DEV), forced_tokens=ref_ids, dump_logits_steps=steps)
         for s in (0, 1, 5, steps - 1):
             assert _rel(lg20[s], ref_logits[s]) < BF16_LOGIT_TOL, s
-        # the same 6 rows through the whole-step kernel and, with the switch off, through the multi-kernel path
+        # the same 6 rows through the whole-step kernel (1: mma.sync attention, 2: CUDA-core attention) and, with the switch
+        # off, through the multi-kernel path
         outs = {}
-        for flag in (1, 0):
+        for flag in (1, 2, 0):
             _abi.call("wb_set_small_batch_path", flag)
             e = WhisperEngine(cfg, sd, dtype="bfloat16", max_batch=6, device=DEV)
             _, lg = e.generate(mel[:6].to(DEV), forced_tokens=ref_ids[:6], dump_logits_steps=steps)
             outs[flag] = lg.clone()
             e.close()
         for s in (0, 1, 5, steps - 1):
-            assert _rel(outs[1][s], ref_logits[s][:6]) < BF16_LOGIT_TOL, s
-            assert _rel(outs[1][s], outs[0][s]) < 1e-2, s
+            for flag in (1, 2):
+                assert _rel(outs[flag][s], ref_logits[s][:6]) < BF16_LOGIT_TOL, (flag, s)
+                assert _rel(outs[flag][s], outs[0][s]) < 1e-2, (flag, s)
             assert _rel(outs[0][s], lg20[s][:6]) < 1e-2, s
         eng.close()
     finally:

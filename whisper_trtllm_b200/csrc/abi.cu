@@ -37,6 +37,7 @@ void set_cuda_graphs(bool on);
 void set_decode_attention_backend(int b);
 void set_lean_decode_gemm(bool on);
 void set_small_batch_path(bool on);
+void set_mega_attention_tc(bool on);
 void set_step_trace(long long* dev_ptr);
 void set_self_attention_variant(int v);
 size_t log_mel_workspace_bytes(int chunk);
@@ -98,9 +99,12 @@ int wb_set_self_attention_warp_kernel(int variant) {
     });
 }
 
-int wb_set_small_batch_path(int enabled) {
-    wb::set_small_batch_path(enabled != 0);
-    return WB_OK;
+int wb_set_small_batch_path(int mode) {
+    return guarded([&] {
+        WB_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (off), 1 (on) or 2 (on, CUDA-core attention)");
+        wb::set_small_batch_path(mode != 0);
+        wb::set_mega_attention_tc(mode != 2);
+    });
 }
 
 int wb_set_step_trace(void* device_buffer) {

@@ -105,6 +105,11 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
 __device__ __forceinline__ void unpack8(const uint4& r, float* f) {
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -470,6 +475,7 @@ __device__ __forceinline__ void linear_phase(const MegaParams& p, const PhaseDes
 }
 
 // ---- one-query attention, one CTA per (item, key split) unit; 8 lanes per key row, 4 rows per warp instruction
+template <bool kTC>
 __device__ __forceinline__ void attention_phase(const MegaParams& p, const bool kPaged, const bf16* __restrict__ kbase, const bf16* __restrict__ vbase,
                                                 int n_keys, int splits, uint8_t* smem, unsigned* item_cnt) {
     float* pm = reinterpret_cast<float*>(smem);
@@ -483,79 +489,183 @@ __device__ __forceinline__ void attention_phase(const MegaParams& p, const bool 
         const int b = item / H, h = item - b * H;
         if (p.unfinished[b] == 0) continue;    // CTA-uniform; every split of the item skips, the counter stays 0
         const int s_beg = (int)((long long)sp * n_keys / splits), s_end = (int)((long long)(sp + 1) * n_keys / splits);
-        float qf[8];
-        unpack8(ldg_cg16(p.q + (size_t)b * d + h * 64 + sub * 8), qf);
-        int my_page = 0;
-        if (kPaged) my_page = lane < p.pages_per_seq ? p.page_table[(size_t)b * p.pages_per_seq + lane] : 0;
-        auto row_off = [&](int s) -> size_t {
-            if (kPaged) {   // CTA-uniform
-                const int page = __shfl_sync(0xffffffffu, my_page, s >> 6);
-                return (((size_t)page * H + h) * 64 + (s & 63)) * 64 + sub * 8;
-            } else {
-                return (size_t)b * p.cross_bstride + ((size_t)h * n_keys + s) * 64 + sub * 8;
+        if constexpr (kTC) {
+            // ---- tensor-core variant: 16 keys per mma.sync block, 2 blocks (32 keys) per warp iteration.
+            //  scores = K q:  A = K block (rows = keys; lane (g, tq) loads dims [8 tq, 8 tq + 8) and [32 + 8 tq, ..) of rows g and g + 8
+            //                 with two 16-byte requests each, K permuted identically in q), B = q in column 0 (lanes g == 0);
+            //  out += p V:    A = p in row 0 (lanes g == 0; keys 4 tq .. 4 tq + 3, bf16), B = V block: lane (g, tq) loads dims
+            //                 [8 g, 8 g + 8) of keys 4 tq .. 4 tq + 3 (16 bytes each) and interleaves key pairs with PRMT; MMA i covers
+            //                 dims 8 n + i of column n, so lane (0, tq) ends with out[16 tq + i] and out[16 tq + 8 + i].
+            // ~7 warp instructions per key instead of ~19 for the 8-lanes-per-key dot products below.
+            const int g = lane >> 2, tq = lane & 3;
+            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+            if (g == 0) {
+                const bf16* qp = p.q + (size_t)b * d + h * 64;
+                q0 = ldg_cg16(qp + 8 * tq);
+                q1 = ldg_cg16(qp + 32 + 8 * tq);
             }
-        };
-        float m_run = -INFINITY, l_run = 0.f, acc[8];
+            int my_page = 0;
+            if (kPaged) my_page = lane < p.pages_per_seq ? p.page_table[(size_t)b * p.pages_per_seq + lane] : 0;
+            auto row_base = [&](int s) -> size_t {
+                if (kPaged) {   // CTA-uniform
+                    const int page = __shfl_sync(0xffffffffu, my_page, s >> 6);
+                    return (((size_t)page * H + h) * 64 + (s & 63)) * 64;
+                } else {
+                    return (size_t)b * p.cross_bstride + ((size_t)h * n_keys + s) * 64;
+                }
+            };
+            float m_run = -INFINITY, l_part = 0.f, acc[8][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        for (int sb = s_beg + warp * 4; sb < s_end; sb += 32 * MG_ATT_UNROLL) {   // warp-uniform trip count
-            uint4 kr[MG_ATT_UNROLL], vr[MG_ATT_UNROLL];
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int u = 0; u < MG_ATT_UNROLL; ++u) {
-                const size_t off = row_off(min(sb + grp + u * 32, s_end - 1));
-                kr[u] = ldg_cg16(kbase + off);          // L2-coherent: the newest self-attention row was written by another CTA
-                vr[u] = ldg_cg16(vbase + off);          // in the previous phase (cross K/V are read-only; same L1 bypass)
+                for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+            for (int blk = s_beg + warp * 32; blk < s_end; blk += MG_WARPS * 32) {   // warp-uniform trip count
+                uint4 ka[2][2], kb[2][2], vv[2][4];
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int base = blk + h2 * 16;
+                    const size_t oa = row_base(min(base + g, s_end - 1)) + 8 * tq;
+                    const size_t ob = row_base(min(base + g + 8, s_end - 1)) + 8 * tq;
+                    ka[h2][0] = ldg_cg16(kbase + oa);
+                    ka[h2][1] = ldg_cg16(kbase + oa + 32);
+                    kb[h2][0] = ldg_cg16(kbase + ob);
+                    kb[h2][1] = ldg_cg16(kbase + ob + 32);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) vv[h2][j] = ldg_cg16(vbase + row_base(min(base + 4 * tq + j, s_end - 1)) + 8 * g);
+                }
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int base = blk + h2 * 16;
+                    if (base < s_end) {   // warp-uniform
+                        float c[4] = {0.f, 0.f, 0.f, 0.f};
+                        mma_16816(c, ka[h2][0].x, kb[h2][0].x, ka[h2][0].y, kb[h2][0].y, q0.x, q0.y);
+                        mma_16816(c, ka[h2][0].z, kb[h2][0].z, ka[h2][0].w, kb[h2][0].w, q0.z, q0.w);
+                        mma_16816(c, ka[h2][1].x, kb[h2][1].x, ka[h2][1].y, kb[h2][1].y, q1.x, q1.y);
+                        mma_16816(c, ka[h2][1].z, kb[h2][1].z, ka[h2][1].w, kb[h2][1].w, q1.z, q1.w);
+                        // column 0 lives in the lanes tq == 0: scores of keys g (c[0]) and g + 8 (c[2])
+                        float s0 = __shfl_sync(0xffffffffu, c[0], lane & ~3), s1 = __shfl_sync(0xffffffffu, c[2], lane & ~3);
+                        if (base + g >= s_end) s0 = -INFINITY;
+                        if (base + g + 8 >= s_end) s1 = -INFINITY;
+                        float mb = fmaxf(s0, s1);
+                        mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 4));
+                        mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 8));
+                        mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 16));
+                        const float m_new = fmaxf(m_run, mb);          // finite: key `base` is valid
+                        const float scale = __expf(m_run - m_new);     // exp(-inf) = 0 while l / acc are still 0
+                        l_part *= scale;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { acc[i][0] *= scale; acc[i][1] *= scale; }
+                        m_run = m_new;
+                        // lane (0, tq) needs p of keys 4 tq .. 4 tq + 3: key k sits in s0 (k < 8) / s1 of the lanes with g = k & 7
+                        const float mine = tq >= 2 ? s1 : s0;
+                        float pj[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float v = __shfl_sync(0xffffffffu, mine, ((((tq & 1) << 2) + j) << 2) + tq);
+                            pj[j] = (g == 0 && v != -INFINITY) ? __expf(v - m_new) : 0.f;
+                        }
+                        const __nv_bfloat162 p01 = __floats2bfloat162_rn(pj[0], pj[1]), p23 = __floats2bfloat162_rn(pj[2], pj[3]);
+                        // the sum uses the rounded probabilities, like the products below
+                        l_part += (__low2float(p01) + __high2float(p01)) + (__low2float(p23) + __high2float(p23));
+                        const uint32_t pa = *reinterpret_cast<const uint32_t*>(&p01), pb = *reinterpret_cast<const uint32_t*>(&p23);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t sel = (i & 1) ? 0x7632u : 0x5410u;
+                            const uint32_t r0 = (i >> 1) == 0 ? vv[h2][0].x : (i >> 1) == 1 ? vv[h2][0].y : (i >> 1) == 2 ? vv[h2][0].z : vv[h2][0].w;
+                            const uint32_t r1 = (i >> 1) == 0 ? vv[h2][1].x : (i >> 1) == 1 ? vv[h2][1].y : (i >> 1) == 2 ? vv[h2][1].z : vv[h2][1].w;
+                            const uint32_t r2 = (i >> 1) == 0 ? vv[h2][2].x : (i >> 1) == 1 ? vv[h2][2].y : (i >> 1) == 2 ? vv[h2][2].z : vv[h2][2].w;
+                            const uint32_t r3 = (i >> 1) == 0 ? vv[h2][3].x : (i >> 1) == 1 ? vv[h2][3].y : (i >> 1) == 2 ? vv[h2][3].z : vv[h2][3].w;
+                            mma_16816(acc[i], pa, 0u, pb, 0u, prmt(r0, r1, sel), prmt(r2, r3, sel));
+                        }
+                    }
+                }
             }
-            float sc[MG_ATT_UNROLL], mb = -INFINITY;
+            float l_run = l_part;
+            l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+            l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+            if (g == 0) {
+                if (tq == 0) { pm[warp] = m_run; pl[warp] = l_run; }
 #pragma unroll
-            for (int u = 0; u < MG_ATT_UNROLL; ++u) {
-                float kf[8];
-                unpack8(kr[u], kf);
-                float dot = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) dot = fmaf(qf[i], kf[i], dot);
-                dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-                dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-                dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-                sc[u] = (sb + grp + u * 32 < s_end) ? dot : -INFINITY;
-                mb = fmaxf(mb, sc[u]);
+                for (int i = 0; i < 8; ++i) {
+                    po[warp * 64 + 16 * tq + i] = acc[i][0];
+                    po[warp * 64 + 16 * tq + 8 + i] = acc[i][1];
+                }
             }
-            const float m_new = fmaxf(m_run, mb);
-            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-            const float scale = __expf(m_run - m_use);
-            l_run *= scale;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] *= scale;
-#pragma unroll
-            for (int u = 0; u < MG_ATT_UNROLL; ++u) {
-                const float pr = __expf(sc[u] - m_use);
-                l_run += pr;
-                float vf[8];
-                unpack8(vr[u], vf);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = fmaf(pr, vf[i], acc[i]);
+        } else {
+            float qf[8];
+            unpack8(ldg_cg16(p.q + (size_t)b * d + h * 64 + sub * 8), qf);
+            int my_page = 0;
+            if (kPaged) my_page = lane < p.pages_per_seq ? p.page_table[(size_t)b * p.pages_per_seq + lane] : 0;
+            auto row_off = [&](int s) -> size_t {
+                if (kPaged) {   // CTA-uniform
+                    const int page = __shfl_sync(0xffffffffu, my_page, s >> 6);
+                    return (((size_t)page * H + h) * 64 + (s & 63)) * 64 + sub * 8;
+                } else {
+                    return (size_t)b * p.cross_bstride + ((size_t)h * n_keys + s) * 64 + sub * 8;
+                }
+            };
+            float m_run = -INFINITY, l_run = 0.f, acc[8];
+    #pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+            for (int sb = s_beg + warp * 4; sb < s_end; sb += 32 * MG_ATT_UNROLL) {   // warp-uniform trip count
+                uint4 kr[MG_ATT_UNROLL], vr[MG_ATT_UNROLL];
+    #pragma unroll
+                for (int u = 0; u < MG_ATT_UNROLL; ++u) {
+                    const size_t off = row_off(min(sb + grp + u * 32, s_end - 1));
+                    kr[u] = ldg_cg16(kbase + off);          // L2-coherent: the newest self-attention row was written by another CTA
+                    vr[u] = ldg_cg16(vbase + off);          // in the previous phase (cross K/V are read-only; same L1 bypass)
+                }
+                float sc[MG_ATT_UNROLL], mb = -INFINITY;
+    #pragma unroll
+                for (int u = 0; u < MG_ATT_UNROLL; ++u) {
+                    float kf[8];
+                    unpack8(kr[u], kf);
+                    float dot = 0.f;
+    #pragma unroll
+                    for (int i = 0; i < 8; ++i) dot = fmaf(qf[i], kf[i], dot);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+                    sc[u] = (sb + grp + u * 32 < s_end) ? dot : -INFINITY;
+                    mb = fmaxf(mb, sc[u]);
+                }
+                const float m_new = fmaxf(m_run, mb);
+                const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+                const float scale = __expf(m_run - m_use);
+                l_run *= scale;
+    #pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] *= scale;
+    #pragma unroll
+                for (int u = 0; u < MG_ATT_UNROLL; ++u) {
+                    const float pr = __expf(sc[u] - m_use);
+                    l_run += pr;
+                    float vf[8];
+                    unpack8(vr[u], vf);
+    #pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] = fmaf(pr, vf[i], acc[i]);
+                }
+                m_run = m_new;
             }
-            m_run = m_new;
-        }
-#pragma unroll
-        for (int o = 8; o < 32; o <<= 1) {      // merge the four key groups of the warp
-            const float om = __shfl_xor_sync(0xffffffffu, m_run, o);
-            const float ol = __shfl_xor_sync(0xffffffffu, l_run, o);
-            const float mm = fmaxf(m_run, om);
-            const float s1 = (m_run == -INFINITY) ? 0.f : __expf(m_run - mm);
-            const float s2 = (om == -INFINITY) ? 0.f : __expf(om - mm);
-            l_run = l_run * s1 + ol * s2;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float oa = __shfl_xor_sync(0xffffffffu, acc[i], o);
-                acc[i] = acc[i] * s1 + oa * s2;
+    #pragma unroll
+            for (int o = 8; o < 32; o <<= 1) {      // merge the four key groups of the warp
+                const float om = __shfl_xor_sync(0xffffffffu, m_run, o);
+                const float ol = __shfl_xor_sync(0xffffffffu, l_run, o);
+                const float mm = fmaxf(m_run, om);
+                const float s1 = (m_run == -INFINITY) ? 0.f : __expf(m_run - mm);
+                const float s2 = (om == -INFINITY) ? 0.f : __expf(om - mm);
+                l_run = l_run * s1 + ol * s2;
+    #pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float oa = __shfl_xor_sync(0xffffffffu, acc[i], o);
+                    acc[i] = acc[i] * s1 + oa * s2;
+                }
+                m_run = mm;
             }
-            m_run = mm;
-        }
-        if (grp == 0) {
-            if (sub == 0) { pm[warp] = m_run; pl[warp] = l_run; }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) po[warp * 64 + sub * 8 + i] = acc[i];
+            if (grp == 0) {
+                if (sub == 0) { pm[warp] = m_run; pl[warp] = l_run; }
+    #pragma unroll
+                for (int i = 0; i < 8; ++i) po[warp * 64 + sub * 8 + i] = acc[i];
+            }
         }
         __syncthreads();
         if (tid < 64) {                         // merge the warps (fixed order)
@@ -694,7 +804,7 @@ __device__ __forceinline__ void prefetch_self(const MegaParams& p, const bf16* k
     }
 }
 
-template <int NM>
+template <int NM, bool kTC>
 __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_mega_kernel(const __grid_constant__ MegaParams p) {
     extern __shared__ __align__(128) uint8_t mg_smem[];
     __shared__ __align__(16) PhaseDesc sdesc[2];
@@ -736,9 +846,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_step_mega_kernel(const _
         } else if (kind == PH_HEAD) {
             linear_phase<NM, MG_HEAD_KS, true>(p, D, pos, mg_smem, trace != nullptr ? trace + 8 * ph : nullptr, first);
         } else if (kind == PH_SELF_ATTN) {   // cached self-attention over cur_len keys (newest row appended by the qkv epilogue)
-            attention_phase(p, true, D.k_pages, D.v_pages, cur_len, 1, mg_smem, item_cnt);
+            attention_phase<kTC>(p, true, D.k_pages, D.v_pages, cur_len, 1, mg_smem, item_cnt);
         } else {                             // cross-attention over the encoder K/V projected once per utterance
-            attention_phase(p, false, D.k_pages, D.v_pages, p.n_ctx, p.cross_splits, mg_smem, item_cnt);
+            attention_phase<kTC>(p, false, D.k_pages, D.v_pages, p.n_ctx, p.cross_splits, mg_smem, item_cnt);
         }
         if (trace != nullptr) trace[8 * ph + 4] = clock64();
         if (ph + 1 == n_phases) break;
@@ -791,6 +901,13 @@ void fill_geometry(PhaseDesc& o, int ks, bool rows16, int grid) {
     o.vpr_rcp = (unsigned)((0x100000000ull + (unsigned)(o.K / 8) - 1) / (unsigned)(o.K / 8));
 }
 }  // namespace
+
+// attention flavour of the whole-step kernel: tensor-core blocks (default) / 8 lanes per key with CUDA-core dot products
+bool& mega_attention_tc() {
+    static bool on = true;
+    return on;
+}
+void set_mega_attention_tc(bool on) { mega_attention_tc() = on; }
 
 long long*& step_trace_ptr() {
     static long long* ptr = nullptr;
@@ -867,11 +984,13 @@ void Session::decode_step_mega(cudaStream_t st) {
     WB_REQUIRE(mega_grid > 0, "whole-step kernel: no phase table");
     const int nm = B <= 8 ? 1 : 2;
     const size_t smem = mega_smem_bytes(nm, g.ffn);
-    auto kernel = nm == 1 ? decode_step_mega_kernel<1> : decode_step_mega_kernel<2>;
-    static size_t configured[3] = {0, 0, 0};
-    if (configured[nm] < smem) {
+    const bool tc = mega_attention_tc();
+    auto kernel = nm == 1 ? (tc ? decode_step_mega_kernel<1, true> : decode_step_mega_kernel<1, false>)
+                          : (tc ? decode_step_mega_kernel<2, true> : decode_step_mega_kernel<2, false>);
+    static size_t configured[3][2] = {};
+    if (configured[nm][tc] < smem) {
         WB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[nm] = smem;
+        configured[nm][tc] = smem;
     }
     int per_sm = 0;
     WB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, MG_THREADS, smem));
