@@ -67,8 +67,8 @@ WB_API int wb_set_decode_attention_backend(int backend);
  * (threads, batch depth) = (128, 4) (128, 8) (64, 8) (256, 4), 5..6 = warp-kernel tuning variants */
 WB_API int wb_set_self_attention_warp_kernel(int variant);
 /* decode steps of <= 16 utterances (bf16) run as ONE persistent cooperative kernel per token, phases separated by grid barriers
- * (csrc/step_mega.cu).  mode 1 (default) = on, attention on mma.sync blocks; 2 = on, attention with CUDA-core dot products
- * (8 lanes per key; A/B measurements); 0 = the multi-kernel step for every batch size (A/B measurements, parity tests).
+ * (csrc/step_mega.cu).  mode 1 (default) = on; 2 = on, with the attention phases on mma.sync blocks of 16 keys instead of
+ * CUDA-core dot products (measured 4-13 % slower, kept for A/B); 0 = the multi-kernel step for every batch size (A/B, parity tests).
  * Sessions decoded concurrently by wb_decode_run_multi never use it (a cooperative grid needs every SM to itself). */
 WB_API int wb_set_small_batch_path(int mode);
 /* measurement hook of the whole-step kernel: device buffer of 8 * (8 * decoder_layers + 2) int64; CTA 0 stores its SM clock

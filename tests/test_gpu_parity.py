@@ -382,7 +382,7 @@ def test_small_and_large_batch_decode_paths_agree():
         _, lg20 = eng.generate(mel.to(DEV), forced_tokens=ref_ids, dump_logits_steps=steps)
         for s in (0, 1, 5, steps - 1):
             assert _rel(lg20[s], ref_logits[s]) < BF16_LOGIT_TOL, s
-        # the same 6 rows through the whole-step kernel (1: mma.sync attention, 2: CUDA-core attention) and, with the switch
+        # the same 6 rows through the whole-step kernel (1: CUDA-core attention, 2: mma.sync attention blocks) and, with the switch
         # off, through the multi-kernel path
         outs = {}
         for flag in (1, 2, 0):

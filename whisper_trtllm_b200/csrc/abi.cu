@@ -101,9 +101,9 @@ int wb_set_self_attention_warp_kernel(int variant) {
 
 int wb_set_small_batch_path(int mode) {
     return guarded([&] {
-        WB_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (off), 1 (on) or 2 (on, CUDA-core attention)");
+        WB_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (off), 1 (on) or 2 (on, mma.sync attention)");
         wb::set_small_batch_path(mode != 0);
-        wb::set_mega_attention_tc(mode != 2);
+        wb::set_mega_attention_tc(mode == 2);
     });
 }
 

@@ -496,7 +496,8 @@ __device__ __forceinline__ void attention_phase(const MegaParams& p, const bool 
             //  out += p V:    A = p in row 0 (lanes g == 0; keys 4 tq .. 4 tq + 3, bf16), B = V block: lane (g, tq) loads dims
             //                 [8 g, 8 g + 8) of keys 4 tq .. 4 tq + 3 (16 bytes each) and interleaves key pairs with PRMT; MMA i covers
             //                 dims 8 n + i of column n, so lane (0, tq) ends with out[16 tq + i] and out[16 tq + 8 + i].
-            // ~7 warp instructions per key instead of ~19 for the 8-lanes-per-key dot products below.
+            // ~7 warp instructions per key instead of ~19 for the 8-lanes-per-key dot products below - and measured slower (see
+            // mega_attention_tc): the default is the CUDA-core flavour.
             const int g = lane >> 2, tq = lane & 3;
             uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
             if (g == 0) {
@@ -902,9 +903,11 @@ void fill_geometry(PhaseDesc& o, int ks, bool rows16, int grid) {
 }
 }  // namespace
 
-// attention flavour of the whole-step kernel: tensor-core blocks (default) / 8 lanes per key with CUDA-core dot products
+// attention flavour of the whole-step kernel: 8 lanes per key with CUDA-core dot products (default) / mma.sync blocks of 16 keys.
+// Measured (profiles/r01_kernel_variants.md): the mma.sync flavour needs 2.7x fewer instructions per key and is still 4-13 %
+// SLOWER per step (B = 1 / 8 / 16: 1013 / 1386 / 2047 us vs 979 / 1277 / 1801) - it stays as a tested, switchable variant.
 bool& mega_attention_tc() {
-    static bool on = true;
+    static bool on = false;
     return on;
 }
 void set_mega_attention_tc(bool on) { mega_attention_tc() = on; }
