@@ -1,16 +1,21 @@
 // Persistent whole-step decoder kernel for small batches (B <= 16 utterances per GPU, bf16).
 //
-// At small batch the decode step is bound by kernel boundaries, not by bytes: 24 layers x 8..11 launches at ~7 us each is
-// 10x above the weight-streaming floor (profiles/r01_decode_step_us.md).  Here ONE cooperative kernel (one 256-thread CTA per
-// SM) runs the whole decoder for one token: embedding, 24 x {LN1+qkv -> paged self-attention -> out-proj(+res) -> LN2+cross-q
-// -> cross-attention -> cross-out(+res) -> LN3+fc1(GELU) -> fc2(+res)}, final LN + LM head.  The phases are separated by a
-// grid barrier (one release-add + acquire-poll in L2) instead of a kernel boundary, and
-//   * the weights of the NEXT phase are requested before the barrier (L2 prefetch) and its first tile is loaded into
-//     registers while the activations are being staged (LayerNorm) - weight latency never sits on the critical path;
+// At small batch the decode step is bound by kernel boundaries, not by bytes: 24 layers x 11 launches at ~8 us each is 14x above
+// the weight-streaming floor (profiles/r01_decode_step_us.md).  Here ONE cooperative kernel (one 256-thread CTA per SM) runs the
+// whole decoder for one token: 24 x {LN1+qkv -> paged self-attention -> out-proj(+res) -> LN2+cross-q -> cross-attention ->
+// cross-out(+res) -> LN3+fc1(GELU) -> fc2(+res)}, final LN + LM head = 193 phases.  The embedding of the token that is fed is
+// written into the residual stream by the greedy kernel of the step that chose it (greedy.cu), so a step is two launches.
+// The phases are separated by a grid barrier (one release-add + acquire-poll in L2) instead of a kernel boundary, and
+//   * the kernel is an interpreter over a table of phase descriptors resolved once per session on the host (PhaseDesc): one
+//     copy of the staging code, of each tile geometry and of each attention flavour - the step has to stay small for the
+//     instruction cache, and every instruction per warp on the critical path counts (8 warps per SM, latency bound);
+//   * between arriving at the barrier and waiting on it, every warp loads the first weight tile of the NEXT linear phase into
+//     registers and requests its LayerNorm parameters / bias / first attention unit into L2: weight latency is hidden behind
+//     the barrier and the staging of the activations;
 //   * linear layers run "swap-AB" on mma.sync m16n8k16: the 16-row MMA dimension walks the WEIGHT rows (streamed straight from
 //     global memory into the A fragment with 16-byte loads, K permuted consistently in both operands), the 8-column dimension
 //     holds the (<= 8 / <= 16) utterances staged once per CTA as bf16 in shared memory; fp32 accumulation;
-//     small layers split K over the 8 warps of a CTA and reduce through shared memory in a fixed order (deterministic);
+//     K is split over the warps of a CTA and reduced through shared memory in a fixed order (deterministic);
 //   * attention items are split over CTAs along the keys (cross: 1500 frames / split) so that a single utterance still uses
 //     every SM; partials (max, sum, acc[64]) are merged in a fixed order by the last CTA to arrive at the item's counter.
 // Semantics and rounding points are those of the multi-kernel step (runtime.cu decode_step_large):
@@ -18,6 +23,7 @@
 // fp32 residual stream, erf GELU, q pre-scaled in the packed weights, fp32 softmax, no mask (model.py:240-304),
 // position = cur_len - 1 (model.py:423-425), tied LM head without bias (modeling_whisper.py:1335,1433).
 // (tcgen05 needs M = 128 row tiles and a TMEM round trip per phase: at <= 16 rows mma.sync from registers is the right tool.)
+// Measurements of every build of this file: profiles/r01_kernel_variants.md; per-phase clock stamps: tools/step_trace.py.
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -28,7 +34,8 @@ namespace wb {
 
 namespace {
 constexpr int MG_THREADS = 256, MG_WARPS = 8;
-constexpr int MG_MAX_LAYERS = 64, MG_MAX_SPLITS = 16;
+constexpr int MG_MAX_LAYERS = 64;     // (any depth works: the phase table lives in global memory; this only bounds the trace buffer)
+constexpr int MG_MAX_SPLITS = 16;
 constexpr int MG_PART = 72;          // floats per attention partial: [0] max, [1] sum, [8..72) acc
 constexpr int MG_RS = 20;            // reduction buffer: floats between consecutive utterance rows (bank-conflict free)
 constexpr int MG_RED_BYTES = 2 * MG_WARPS * 16 * MG_RS * 4;   // two parities x 8 warps x 16 rows
