@@ -122,7 +122,14 @@ WB_API int wb_decode_run(wb_session* s, int max_steps, int check_every, int* fin
  * own stream, so that the HBM-bound cross-attention of one sub-batch overlaps the latency-bound GEMM / LayerNorm kernels of
  * the others.  wb_decode_begin must have been called on every session.  final_lens: one int per session. */
 WB_API int wb_decode_run_multi(wb_session** sessions, int n_sessions, int max_steps, int check_every, int* final_lens, wb_stream stream);
-/* ids int32 [B, max_target_positions] (row stride max_target_positions); device pointer owned by the session */
+/* Finished-row compaction (not in the reference, which decodes one utterance at a time): call between two
+ * wb_decode_run(max_steps = n) windows.  Synchronises `stream`, reads the per-row unfinished flags
+ * (generation/utils.py:1506-1520) and, if rows have emitted EOS, moves the rows still running to the front of the batch (ids,
+ * page-table rows, cross K/V rows) so that the following steps run on fewer rows; the ids of the rows that left are kept in a
+ * result buffer in ORIGINAL row order, which wb_decode_tokens returns from then on.  *rows_running = rows still decoding,
+ * 0 when the loop has stopped.  Not available with teacher forcing / logits dumps. */
+WB_API int wb_decode_compact(wb_session* s, int* rows_running, wb_stream stream);
+/* ids int32 [B, max_target_positions] (row stride max_target_positions), original row order; device pointer owned by the session */
 WB_API int wb_decode_tokens(wb_session* s, const int32_t** tokens_dev, int* row_stride);
 /* raw next-token logits of the last step, fp32 [B, vocab] (the decoder engine's output tensor, model.py:464) */
 WB_API int wb_decode_logits(wb_session* s, const float** logits_dev);

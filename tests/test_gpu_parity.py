@@ -251,6 +251,54 @@ def test_whole_step_kernel_edge_cases():
         _abi.call("wb_set_small_batch_path", 1)
 
 
+def test_finished_rows_leave_the_batch():
+    """Finished-row compaction (wb_decode_compact): utterances that emitted EOS are removed from the decode
+    batch between two windows of steps; ids, page-table rows and cross K/V rows of the others move to the front.  The ids
+    (original row order, pad after EOS) are those of the reference's loop, which keeps every row to the end
+    (generation/utils.py:1506-1520); the session is reusable afterwards (page-table rows are swapped, never lost)."""
+    from whisper_trtllm_b200 import _abi
+    cfg = synth.make_config("micro", max_length=40)
+    sd = synth.make_weights(cfg, seed=0)
+    mel = synth.make_mel(5, seed=1234)
+    free = R.greedy(mel, sd, cfg)
+    # EOS := a token that the rows emit for the first time at different positions (one row never does)
+    eos_tok = None
+    for t in sorted(set(free[:, 2:].flatten().tolist())):
+        first = [((free[r, 2:] == t).nonzero().flatten().tolist() + [None])[0] for r in range(5)]
+        hit = [f for f in first if f is not None]
+        if len(set(first)) >= 3 and len(hit) >= 2 and None in first and min(hit) >= 3:
+            eos_tok = int(t)
+            break
+    assert eos_tok is not None, "the test case needs rows that finish at different times"
+    cfg3 = dict(cfg, eos_token_id=eos_tok, pad_token_id=eos_tok)
+    ref3 = R.greedy(mel, sd, cfg3)
+    assert ref3.shape[1] == 40
+    eng = WhisperEngine(cfg3, sd, dtype="float32", max_batch=6, enc_chunk=3, device=DEV)
+    assert torch.equal(eng.generate(mel.to(DEV)).cpu().long(), ref3)
+    for every in (5, 7, 16):
+        ids = eng.generate(mel.to(DEV), compact_every=every).cpu().long()
+        assert torch.equal(ids, ref3), (every, ids[:, :12], ref3[:, :12])
+    assert torch.equal(eng.generate(mel.to(DEV)).cpu().long(), ref3)      # full batch again on the same session
+    # the batch really shrinks: rows without EOS among their first 6 generated ids are the ones still running
+    eng.encode(mel.to(DEV), return_hidden=False)
+    eng.decode_begin(5)
+    eng.decode_run(max_steps=22)
+    running = int(sum(1 for r in range(5) if eos_tok not in ref3[r, 1:23].tolist()))
+    assert 0 < running < 5, "the test case needs rows that finish at different times"
+    assert eng.decode_compact() == running
+    assert eng.decode_compact() == running                                  # nothing new finished: no-op
+    eng.close()
+    # bf16, whole-step kernel (5 rows <= 16): same loop with rows leaving; the finished row and the first ids agree with the
+    # uncompacted run (the key-split count changes with the batch, so later near-ties may resolve differently)
+    eng = WhisperEngine(cfg3, sd, dtype="bfloat16", max_batch=5, device=DEV)
+    plain = eng.generate(mel.to(DEV)).cpu().long()
+    comp = eng.generate(mel.to(DEV), compact_every=6).cpu().long()
+    assert comp.shape == plain.shape
+    assert torch.equal(comp[:, :6], plain[:, :6])
+    assert float((comp == plain).float().mean()) >= 0.5
+    eng.close()
+
+
 def test_multi_stream_sub_batches_give_the_same_tokens():
     """n_streams > 1: the batch is split into sub-sessions whose greedy loops are interleaved on separate streams
     (wb_decode_run_multi; bulk-ring cross-attention + lean decode GEMM so that their kernels can share an SM).  Rows are

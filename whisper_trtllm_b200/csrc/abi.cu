@@ -228,11 +228,18 @@ int wb_decode_run_multi(wb_session** sessions, int n_sessions, int max_steps, in
         wb::decode_run_multi(reinterpret_cast<wb::Session**>(sessions), n_sessions, max_steps, check_every, final_lens, S(stream));
     });
 }
+int wb_decode_compact(wb_session* s, int* rows_running, wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(s);
+        const int n = SS(s)->decode_compact(S(stream));
+        if (rows_running) *rows_running = n;
+    });
+}
 int wb_decode_tokens(wb_session* s, const int32_t** tokens_dev, int* row_stride) {
     return guarded([&] {
         WB_NOT_NULL(s);
         WB_NOT_NULL(tokens_dev);
-        *tokens_dev = SS(s)->tokens;
+        *tokens_dev = SS(s)->compacted ? SS(s)->result_tokens : SS(s)->tokens;
         if (row_stride) *row_stride = SS(s)->m->cfg.max_tgt;
     });
 }

@@ -268,6 +268,7 @@ size_t layout(Buffers& b, const Model* m, int max_batch, int enc_chunk, void* ba
     c.take(b.mega_part, mega_part_bytes(max_batch, g.n_heads));
     c.take(b.mega_sync, mega_sync_bytes(max_batch, g.n_heads));
     c.take(b.mega_table, mega_table_bytes(g.dec_layers));
+    c.take(b.result_tokens, B * g.max_tgt * 4);
     return c.off + 1024;
 }
 }  // namespace
@@ -290,9 +291,9 @@ Session::Session(Model* model, int mb, int ec, void* workspace, size_t workspace
     pages_per_seq = model->cfg.max_tgt / PAGE_TOKENS;
     num_pages = mb * pages_per_seq;
     // page allocator: every row owns its pages up front (identity map); the kernels only see the table
-    std::vector<int> pt((size_t)num_pages);
-    for (int i = 0; i < num_pages; ++i) pt[i] = i;
-    WB_CHECK_CUDA(cudaMemcpy(page_table, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice));
+    page_table_host.resize((size_t)num_pages);
+    for (int i = 0; i < num_pages; ++i) page_table_host[i] = i;
+    WB_CHECK_CUDA(cudaMemcpy(page_table, page_table_host.data(), page_table_host.size() * 4, cudaMemcpyHostToDevice));
     WB_CHECK_CUDA(cudaMemset(h1p, 0, ((size_t)ec * H1_ROWS + 8) * model->cfg.d_model * dtype_size(model->dtype)));
     WB_CHECK_CUDA(cudaMemset(state, 0, sizeof(StepState)));
     WB_CHECK_CUDA(cudaMemset(mega_sync, 0, mega_sync_bytes(mb, model->cfg.n_heads)));
@@ -478,6 +479,10 @@ void Session::decode_begin(int B, cudaStream_t st) {
     WB_REQUIRE(B > 0 && B <= max_batch, "bad decode batch");
     const ModelConfig& g = m->cfg;
     batch = B;
+    begin_batch = B;
+    compacted = false;
+    row_origin.resize(B);
+    for (int i = 0; i < B; ++i) row_origin[i] = i;
     steps_enqueued = 0;
     greedy_init(tokens, g.max_tgt, unfinished, state, B, g.sot, g.pad, g.max_tgt, st);
     // the whole-step kernel starts from the residual stream: embedding of the start token here, of every later token by the
@@ -495,6 +500,69 @@ void set_small_batch_path(bool on) { whole_step_kernel_enabled() = on; }
 
 // (not when several sessions decode concurrently on their own streams: a cooperative grid needs every SM to itself)
 bool Session::use_mega() const { return whole_step_kernel_enabled() && exclusive && get_gemm_backend() == 0 && mega_supported(); }
+
+// ids of the current decode rows -> result buffer, original row order
+void Session::publish_results(cudaStream_t st) {
+    const size_t row_bytes = (size_t)m->cfg.max_tgt * 4;
+    bool identity = true;
+    for (int i = 0; i < batch; ++i) identity = identity && row_origin[i] == i;
+    if (identity) {
+        WB_CHECK_CUDA(cudaMemcpyAsync(result_tokens, tokens, row_bytes * batch, cudaMemcpyDeviceToDevice, st));
+    } else {
+        for (int i = 0; i < batch; ++i)
+            WB_CHECK_CUDA(cudaMemcpyAsync(result_tokens + (size_t)row_origin[i] * m->cfg.max_tgt, tokens + (size_t)i * m->cfg.max_tgt,
+                                          row_bytes, cudaMemcpyDeviceToDevice, st));
+    }
+}
+
+int Session::decode_compact(cudaStream_t st) {
+    WB_REQUIRE(batch > 0, "decode_begin was not called");
+    WB_REQUIRE(forced_tokens == nullptr && logits_dump == nullptr, "compaction is not available with teacher forcing / logits dumps");
+    const ModelConfig& g = m->cfg;
+    std::vector<int> unf((size_t)batch);
+    StepState hs;
+    WB_CHECK_CUDA(cudaMemcpyAsync(unf.data(), unfinished, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+    WB_CHECK_CUDA(cudaMemcpyAsync(&hs, state, sizeof(StepState), cudaMemcpyDeviceToHost, st));
+    WB_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (hs.active == 0) return 0;
+    std::vector<int> keep;
+    for (int i = 0; i < batch; ++i)
+        if (unf[i] != 0) keep.push_back(i);
+    if ((int)keep.size() == batch) return batch;
+    // the ids of every current row go to the result buffer first (finished rows are final; running rows are refreshed at the end)
+    publish_results(st);
+    compacted = true;
+    // stable compaction: running row i moves to slot j <= i; slot j held a finished row or a row that has already moved
+    const size_t es = dtype_size(m->dtype);
+    const size_t row_bytes = (size_t)g.max_tgt * 4;
+    const size_t kv_row = (size_t)g.n_heads * g.n_ctx * 64;                   // cross K (or V) elements of one utterance and layer
+    const size_t per_kv = (size_t)max_batch * kv_row;
+    for (int j = 0; j < (int)keep.size(); ++j) {
+        const int i = keep[j];
+        if (i == j) continue;
+        WB_CHECK_CUDA(cudaMemcpyAsync(tokens + (size_t)j * g.max_tgt, tokens + (size_t)i * g.max_tgt, row_bytes, cudaMemcpyDeviceToDevice, st));
+        for (int l = 0; l < g.dec_layers; ++l) {
+            for (int kv = 0; kv < 2; ++kv) {
+                uint8_t* base_l = (uint8_t*)cross + ((size_t)l * cross_layer_elems() + (size_t)kv * per_kv) * es;
+                WB_CHECK_CUDA(cudaMemcpyAsync(base_l + (size_t)j * kv_row * es, base_l + (size_t)i * kv_row * es, kv_row * es,
+                                              cudaMemcpyDeviceToDevice, st));
+            }
+        }
+        for (int q = 0; q < pages_per_seq; ++q)                               // the self K/V pages stay where they are
+            std::swap(page_table_host[(size_t)j * pages_per_seq + q], page_table_host[(size_t)i * pages_per_seq + q]);
+        row_origin[j] = row_origin[i];
+    }
+    const int old_batch = batch;
+    batch = (int)keep.size();
+    row_origin.resize(batch);
+    WB_CHECK_CUDA(cudaMemcpyAsync(page_table, page_table_host.data(), (size_t)old_batch * pages_per_seq * 4, cudaMemcpyHostToDevice, st));
+    std::vector<int> ones((size_t)batch, 1);
+    WB_CHECK_CUDA(cudaMemcpyAsync(unfinished, ones.data(), (size_t)batch * 4, cudaMemcpyHostToDevice, st));
+    WB_CHECK_CUDA(cudaStreamSynchronize(st));                                 // the host vectors above go out of scope
+    // the whole-step kernel starts from the residual stream: re-embed the last token of the rows that moved
+    if (use_mega()) decoder_embed(tokens, g.max_tgt, state, m->emb, m->dec_pos, m->dtype, dx, batch, g.d_model, st);
+    return batch;
+}
 
 void Session::decode_step(cudaStream_t st) {
     WB_REQUIRE(batch > 0, "decode_begin was not called");
@@ -715,6 +783,10 @@ void decode_run_multi(Session** ss, int n, int max_steps, int check_every, int* 
         Session* s = ss[k];
         WB_CHECK_CUDA(cudaStreamSynchronize(s->loop_stream));
         if (final_lens) final_lens[k] = s->host_state->active ? s->host_state->cur_len : s->host_state->final_len;
+        if (s->compacted) {       // ids of the rows still in the batch -> result buffer (original row order)
+            s->publish_results(s->loop_stream);
+            WB_CHECK_CUDA(cudaStreamSynchronize(s->loop_stream));
+        }
     }
 }
 

@@ -85,6 +85,7 @@ struct Buffers {
     int* tokens = nullptr; int* unfinished = nullptr; StepState* state = nullptr;
     // whole-step kernel (step_mega.cu): attention partials of split items, grid-barrier / per-item arrival counters
     float* mega_part = nullptr; unsigned* mega_sync = nullptr; void* mega_table = nullptr;
+    int* result_tokens = nullptr;   // [max_batch, max_tgt] ids in ORIGINAL row order once rows have been compacted away
 };
 size_t mega_part_bytes(int max_batch, int heads);
 size_t mega_sync_bytes(int max_batch, int heads);
@@ -141,6 +142,14 @@ struct Session : Buffers {
     void build_mega_table();                  // phase descriptors of the whole-step kernel (constructor)
     int mega_grid = 0;                        // CTAs of the whole-step kernel = SMs of the device the table was built for
     int decode_run(int max_steps, int check_every, cudaStream_t s);  // returns final length (syncs)
+    // Finished-row compaction: utterances that emitted EOS leave the decode batch; the rows still running
+    // move to the front (ids, page-table rows, cross K/V rows) and the following steps run on `batch` = their number.
+    int decode_compact(cudaStream_t s);       // syncs; returns the rows still running (0: the loop has stopped)
+    void publish_results(cudaStream_t s);     // current ids -> result_tokens[row_origin]
+    std::vector<int> row_origin;              // original row of decode row i
+    std::vector<int> page_table_host;         // host mirror of the page table (rows are swapped, never duplicated)
+    bool compacted = false;
+    int begin_batch = 0;
     void enqueue_step();                                             // one step on loop_stream (graph replay or eager)
     size_t cross_layer_elems() const;
     size_t self_layer_elems() const;

@@ -161,6 +161,14 @@ class WhisperEngine:
         self._final_lens = list(lens)
         return max(self._final_lens)
 
+    def decode_compact(self, stream=None) -> int:
+        """Finished-row compaction (wb_decode_compact): utterances that have emitted EOS leave the decode batch,
+        the following steps run on the rows still decoding.  Returns their number (0: the loop has stopped)."""
+        self._single("decode_compact()")
+        n = c_int()
+        _abi.call("wb_decode_compact", self._session, byref(n), stream_handle(stream))
+        return n.value
+
     def _view(self, address: int, shape, dtype) -> torch.Tensor:
         """Zero-copy torch view of session-owned device memory (lives inside sub-session 0's workspace)."""
         return self._view_of(self.workspace, address, shape, dtype)
@@ -219,16 +227,17 @@ class WhisperEngine:
 
     @torch.no_grad()
     def generate(self, mel: torch.Tensor, max_new_tokens: Optional[int] = None, forced_tokens: Optional[torch.Tensor] = None,
-                 dump_logits_steps: int = 0, check_every: int = 32, stream=None):
+                 dump_logits_steps: int = 0, check_every: int = 32, stream=None, compact_every: int = 0):
         """Encoder + on-device greedy loop.  Returns ids int32 [B, L] (L as the oracle's loop would stop),
-        plus per-step raw logits [steps, B, V] when ``dump_logits_steps`` > 0."""
+        plus per-step raw logits [steps, B, V] when ``dump_logits_steps`` > 0.  ``compact_every`` = n > 0: every n steps the
+        utterances that have emitted EOS are removed from the decode batch (same ids, fewer rows per step)."""
         B = mel.shape[0]
         self.encode(mel, return_hidden=False, stream=stream)
-        return self.greedy(B, max_new_tokens, forced_tokens, dump_logits_steps, check_every, stream)
+        return self.greedy(B, max_new_tokens, forced_tokens, dump_logits_steps, check_every, stream, compact_every)
 
     @torch.no_grad()
     def greedy(self, B: int, max_new_tokens=None, forced_tokens=None, dump_logits_steps: int = 0, check_every: int = 32,
-               stream=None):
+               stream=None, compact_every: int = 0):
         dump = None
         if forced_tokens is not None or dump_logits_steps > 0:
             self._single("teacher forcing / logits dump")
@@ -244,7 +253,17 @@ class WhisperEngine:
         _abi.call("wb_decode_set_logits_dump", self._session, ptr(dump), dump_logits_steps)
         self.decode_begin(B, stream)
         steps = 0 if max_new_tokens is None else int(max_new_tokens)
-        final_len = self.decode_run(steps, check_every, stream)
+        if compact_every > 0 and forced_tokens is None and dump_logits_steps == 0 and self.n_streams == 1:
+            total = steps if steps > 0 else self.config["max_length"] - 1
+            done, final_len = 0, 1
+            while done < total:
+                n = min(int(compact_every), total - done)
+                final_len = self.decode_run(n, check_every, stream)
+                done += n
+                if done >= total or self.decode_compact(stream) == 0:
+                    break
+        else:
+            final_len = self.decode_run(steps, check_every, stream)
         ids = self.tokens()[:B, :final_len].clone()
         if self.n_streams > 1:   # a sub-batch whose rows all hit EOS stopped earlier: its tail is pad (GU:1506-1510)
             for (b0, b1), n in zip(self._active, self._final_lens):
