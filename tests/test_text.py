@@ -1,8 +1,15 @@
-"""Token->text and WER: known-answer tests of the byte-level BPE decode, the basic normaliser and
-the corpus WER (jiwer's documented examples)."""
+"""Token->text and WER: known-answer tests of the byte-level BPE decode, the text normalisers
+(against outputs of the reference's own english_normalizer.py, recorded by oracle/make_golden_text.py) and the corpus WER
+(jiwer's documented examples)."""
+import json
+import os
+
 import pytest
 
-from whisper_trtllm_b200.text import BasicTextNormalizer, WhisperDetokenizer, bytes_to_unicode, wer
+from whisper_trtllm_b200.text import (BasicTextNormalizer, EnglishNumberNormalizer, EnglishSpellingNormalizer,
+                                      EnglishTextNormalizer, WhisperDetokenizer, bytes_to_unicode, wer)
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "english_normalizer.json")
 
 
 def _toy_vocab():
@@ -35,10 +42,43 @@ def test_decode_skips_specials_and_joins_split_bytes():
         tok.decode([999])
 
 
-def test_normalizer():
+def test_basic_normalizer_known_answers():
     n = BasicTextNormalizer()
-    assert n("  Hello, World!  (applause) [MUSIC] It's 5 o'clock… ") == "hello world it s 5 o clock"
-    assert BasicTextNormalizer({"colour": "color"})("The Colour") == "the color"
+    # ends are not stripped: one space survives on either side (english_normalizer.py:91)
+    assert n("  Hello, World!  (applause) [MUSIC] It's 5 o'clock… ") == " hello world it s 5 o clock "
+    assert BasicTextNormalizer(remove_diacritics=True)("Café Ærø") == "cafe aero"
+    assert BasicTextNormalizer(split_letters=True)("ab c") == "a b c"
+
+
+def test_english_normalizer_known_answers():
+    n = EnglishTextNormalizer({"colour": "color"})
+    assert n("Mr. Smith won't pay twenty dollars and seven cents!") == "mister smith will not pay $20.07"
+    assert n("one oh one, the nineteen sixties, two and a half percent") == "101 the 1960s 2.5%"
+    assert n("The colour (sic) um is three point one four") == "the color is 3.14"
+    assert EnglishTextNormalizer()("no table given: colour") == "no table given colour"     # cal_wer.py:279 passes none
+    assert EnglishNumberNormalizer()("two hundred and first of one") == "201st of one"
+    assert EnglishSpellingNormalizer({"grey": "gray"})("grey  skies") == "gray skies"
+
+
+def test_normalizers_match_the_reference_goldens():
+    with open(GOLDEN, encoding="utf-8") as f:
+        g = json.load(f)
+    n = EnglishTextNormalizer(g["spelling"])
+    assert len(g["cases"]) > 1000 and len(g["basic"]) > 1000
+    for text, want in g["cases"]:
+        assert n(text) == want, text
+    basic = {}
+    for text, rd, sl, want in g["basic"]:
+        b = basic.setdefault((rd, sl), BasicTextNormalizer(remove_diacritics=rd, split_letters=sl))
+        assert b(text) == want, (text, rd, sl)
+
+
+def test_wer_of_normalised_text():
+    # cal_wer.py:279-286: both sides normalised, then corpus WER
+    n = EnglishTextNormalizer()
+    refs = [n("Twenty one people can't come."), n("Dr. Who's gone")]
+    hyps = [n("21 people can not come"), n("doctor who has left")]
+    assert wer(refs, hyps) == pytest.approx(1 / 9)
 
 
 def test_wer_known_answers():
