@@ -1,0 +1,151 @@
+"""Host side of the scripts around the path (run.py:229-331, cal_wer.py:227-287 equivalents): audio files, manifests, tokenizer
+files of a checkpoint directory, the --compare report.  No GPU: the engine itself is covered by the -m gpu tests."""
+import json
+import os
+import wave
+
+import numpy as np
+import pytest
+
+from whisper_trtllm_b200 import audio, pipeline
+from whisper_trtllm_b200.text import bytes_to_unicode
+
+
+def _tone(n=1600, f=440.0):
+    return (0.5 * np.sin(2 * np.pi * f * np.arange(n) / audio.SAMPLING_RATE)).astype(np.float32)
+
+
+def test_wav_roundtrip_is_within_half_an_lsb(tmp_path):
+    x = _tone()
+    p = str(tmp_path / "a.wav")
+    audio.write_wav(p, x)
+    y, rate = audio.read_wav(p)
+    assert rate == 16000 and y.dtype == np.float32 and y.shape == x.shape
+    assert np.abs(y - x).max() <= 0.5 / 32768 + 1e-7
+    assert np.array_equal(audio.load_audio(p), y)
+    # full-scale values are clipped, not wrapped
+    audio.write_wav(p, np.array([1.0, -1.0, 2.0, -2.0], dtype=np.float32))
+    assert audio.read_wav(p)[0].tolist() == [32767 / 32768, -1.0, 32767 / 32768, -1.0]
+
+
+@pytest.mark.parametrize("width,dtype,scale", [(1, np.uint8, 128.0), (3, None, 8388608.0), (4, "<i4", 2147483648.0)])
+def test_other_pcm_widths_and_stereo(tmp_path, width, dtype, scale):
+    vals = np.array([0, 1, -1, 100, -100, int(scale) - 1, -int(scale)], dtype=np.int64)
+    stereo = np.stack([vals, vals[::-1]], axis=1)                      # two channels, averaged on read
+    if width == 1:
+        raw = (stereo + 128).astype(np.uint8).tobytes()
+    elif width == 3:
+        raw = b"".join(int(v).to_bytes(3, "little", signed=True) for v in stereo.reshape(-1))
+    else:
+        raw = stereo.astype(dtype).tobytes()
+    p = str(tmp_path / "w.wav")
+    with wave.open(p, "wb") as w:
+        w.setnchannels(2)
+        w.setsampwidth(width)
+        w.setframerate(16000)
+        w.writeframes(raw)
+    y, _ = audio.read_wav(p)
+    want = ((vals + vals[::-1]) / 2.0 / scale).astype(np.float32)
+    assert np.allclose(y, want, rtol=0, atol=1e-7)
+
+
+def test_wrong_rate_shape_and_format_are_errors(tmp_path):
+    p = str(tmp_path / "r.wav")
+    audio.write_wav(p, _tone(), rate=8000)
+    with pytest.raises(ValueError, match="8000"):
+        audio.load_audio(p)                                              # as the feature extractor: no silent resampling
+    np.save(str(tmp_path / "m.npy"), np.zeros((2, 10), dtype=np.float32))
+    with pytest.raises(ValueError, match="1-D"):
+        audio.load_audio(str(tmp_path / "m.npy"))
+    with pytest.raises(ValueError, match="unsupported"):
+        audio.load_audio(str(tmp_path / "x.flac"))
+    np.save(str(tmp_path / "ok.npy"), _tone().astype(np.float64))
+    assert audio.load_audio(str(tmp_path / "ok.npy")).dtype == np.float32
+
+
+def test_manifests(tmp_path):
+    d = tmp_path / "spk"
+    d.mkdir()
+    for uid in ("1-2-0001", "1-2-0000"):
+        audio.write_wav(str(d / f"{uid}.wav"), _tone())
+    np.save(str(d / "1-2-0002.npy"), _tone())
+    # a bare directory: sorted audio files, no references
+    paths, refs = audio.read_manifest(str(d))
+    assert [os.path.basename(p) for p in paths] == ["1-2-0000.wav", "1-2-0001.wav", "1-2-0002.npy"] and refs is None
+    # LibriSpeech transcript file (also found through its directory)
+    (d / "1-2.trans.txt").write_text("1-2-0000 HELLO WORLD\n1-2-0002 TWENTY ONE\n")
+    for target in (str(d / "1-2.trans.txt"), str(d)):
+        paths, refs = audio.read_manifest(target)
+        assert [os.path.basename(p) for p in paths] == ["1-2-0000.wav", "1-2-0002.npy"] and refs == ["HELLO WORLD", "TWENTY ONE"]
+    (d / "bad.trans.txt").write_text("9-9-9999 NO AUDIO\n")
+    with pytest.raises(FileNotFoundError):
+        audio.read_manifest(str(d / "bad.trans.txt"))
+    # TSV relative to the manifest, and jsonl
+    (tmp_path / "m.tsv").write_text("spk/1-2-0000.wav\thello\nspk/1-2-0001.wav\tworld\n")
+    paths, refs = audio.read_manifest(str(tmp_path / "m.tsv"))
+    assert paths == [str(d / "1-2-0000.wav"), str(d / "1-2-0001.wav")] and refs == ["hello", "world"]
+    (tmp_path / "m.jsonl").write_text(json.dumps({"audio": str(d / "1-2-0000.wav")}) + "\n")
+    assert audio.read_manifest(str(tmp_path / "m.jsonl")) == ([str(d / "1-2-0000.wav")], None)
+    (tmp_path / "mixed.tsv").write_text("a.wav\thello\nb.wav\n")
+    with pytest.raises(ValueError, match="some"):
+        audio.read_manifest(str(tmp_path / "mixed.tsv"))
+    (tmp_path / "empty.tsv").write_text("\n")
+    with pytest.raises(ValueError, match="empty"):
+        audio.read_manifest(str(tmp_path / "empty.tsv"))
+    e = tmp_path / "none"
+    e.mkdir()
+    with pytest.raises(FileNotFoundError):
+        audio.read_manifest(str(e))
+
+
+def test_batches():
+    assert [list(b) for b in audio.batches(list(range(5)), 2)] == [[0, 1], [2, 3], [4]]
+    assert list(audio.batches([], 4)) == []
+    with pytest.raises(ValueError):
+        list(audio.batches([1], 0))
+
+
+def test_text_tools_from_a_checkpoint_directory(tmp_path):
+    cfg = {"eos_token_id": 50256}
+    # nothing there: ids only, normaliser with an empty spelling table
+    detok, norm = pipeline.load_text_tools(str(tmp_path), cfg)
+    assert detok is None and norm("The colour is twenty one") == "the colour is 21"
+    b2u = bytes_to_unicode()
+    vocab = {"".join(b2u[b] for b in " colour".encode()): 0, "".join(b2u[b] for b in " hi".encode()): 1,
+             "<|endoftext|>": 50256, "<|startoftranscript|>": 50257}
+    (tmp_path / "vocab.json").write_text(json.dumps(vocab))
+    (tmp_path / "normalizer.json").write_text(json.dumps({"colour": "color"}))
+    detok, norm = pipeline.load_text_tools(str(tmp_path), cfg)
+    assert detok.batch_decode([[50257, 1, 0, 50256, 50256]]) == [" hi colour"] and norm(" hi colour") == "hi color"
+    assert pipeline.first_special_token_id(str(tmp_path), cfg) == 50256
+    # a multilingual checkpoint lists its special tokens in added_tokens.json, the first one is 50257 there
+    (tmp_path / "added_tokens.json").write_text(json.dumps({"<|endoftext|>": 50257, "<|startoftranscript|>": 50258}))
+    assert pipeline.first_special_token_id(str(tmp_path), cfg) == 50257
+
+
+def test_compare_report():
+    assert pipeline.compare_transcriptions(["a", "b", "c"], ["a", "x", "c"]) == [("b", "x")]
+    with pytest.raises(ValueError):
+        pipeline.compare_transcriptions(["a"], [])
+
+
+def test_the_pipeline_has_no_cpu_path(tmp_path):
+    import torch
+    from oracle import synth
+    from whisper_trtllm_b200 import WhisperB200Error, checkpoint
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    cfg = synth.make_config("micro")
+    checkpoint.save_hf_checkpoint(str(tmp_path), cfg, synth.make_weights(cfg, seed=2))
+    with pytest.raises(WhisperB200Error):
+        pipeline.WhisperPipeline(str(tmp_path))
+
+
+def test_cli_arguments():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "transcribe_cli", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "transcribe.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    a = cli.parse_arguments(["--whisper", "ckpt", "--audio", "dir", "--wer", "--batch", "8"])
+    assert (a.whisper, a.audio, a.wer, a.compare, a.batch, a.dtype, a.compact_every) == ("ckpt", "dir", True, False, 8, "bfloat16", 32)

@@ -1,0 +1,121 @@
+"""Waveforms in, text (and WER) out: the main loops of the reference's two scripts, batched.
+
+``run.py:259-290`` walks a dataset one utterance at a time — feature extractor on the CPU, encoder engine, greedy loop with a
+host round trip per token, ``batch_decode`` — and ``cal_wer.py:251-287`` does the same over (mel, text) pairs and then
+normalises both sides and calls ``jiwer.wer``.  ``WhisperPipeline`` is that loop over batches of utterances with every stage
+on the device: ``LogMelFrontend`` -> ``WhisperEngine.generate`` (the hot path, §8a) -> ``WhisperDetokenizer``
+-> ``EnglishTextNormalizer`` / ``wer`` (row 3), from a checkpoint directory read by ``checkpoint.load_hf_checkpoint`` (row 1).
+Under ``torchrun`` the utterances are sharded over the ranks and the ids gathered at the end (``dp``).
+
+Host plumbing only: no arithmetic happens here, and there is no CPU fallback (the engine and the front-end raise without a GPU).
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import dp
+from .audio import batches, load_audio
+from .checkpoint import load_hf_checkpoint
+from .text import EnglishTextNormalizer, WhisperDetokenizer, wer
+
+
+def first_special_token_id(checkpoint_dir: str, config: Dict) -> int:
+    """Smallest id of the tokenizer's added (special) tokens: ``added_tokens.json`` when the checkpoint has one, else
+    ``<|endoftext|>`` = eos_token_id (50256 for the `.en` vocabularies, 50257 for the multilingual ones)."""
+    p = os.path.join(checkpoint_dir, "added_tokens.json")
+    if os.path.exists(p):
+        with open(p, encoding="utf-8") as f:
+            added = json.load(f)
+        if added:
+            return min(int(v) for v in added.values())
+    return int(config["eos_token_id"])
+
+
+def load_text_tools(checkpoint_dir: str, config: Dict):
+    """-> (detokenizer or None, normaliser).  ``vocab.json`` and ``normalizer.json`` are the tokenizer files that ship with
+    every Whisper checkpoint; without ``vocab.json`` only token ids can be returned, without ``normalizer.json`` the
+    normaliser runs with an empty spelling table."""
+    vocab = os.path.join(checkpoint_dir, "vocab.json")
+    detok = WhisperDetokenizer(vocab, first_special_token_id(checkpoint_dir, config)) if os.path.exists(vocab) else None
+    spelling = {}
+    p = os.path.join(checkpoint_dir, "normalizer.json")
+    if os.path.exists(p):
+        with open(p, encoding="utf-8") as f:
+            spelling = json.load(f)
+    return detok, EnglishTextNormalizer(spelling)
+
+
+class WhisperPipeline:
+    def __init__(self, checkpoint_dir: str, dtype: str = "bfloat16", max_batch: int = 64, device=None, compact_every: int = 32):
+        """``dtype``: "bfloat16" (tcgen05 speed path) or "float32" (token ids identical to the reference's fp32 run).
+        ``compact_every``: every that many tokens the utterances that have emitted EOS leave the decode batch (0 = never)."""
+        from .engine import WhisperEngine
+        from .frontend import LogMelFrontend
+        self.checkpoint_dir = checkpoint_dir
+        self.config, state_dict = load_hf_checkpoint(checkpoint_dir)
+        self.detokenizer, self.normalizer = load_text_tools(checkpoint_dir, self.config)
+        self.max_batch = int(max_batch)
+        self.compact_every = int(compact_every)
+        self.engine = WhisperEngine(self.config, state_dict, dtype=dtype, max_batch=self.max_batch, device=device)
+        self.frontend = LogMelFrontend(self.engine.device)
+
+    # ------------------------------------------------------------------ ids
+    @torch.no_grad()
+    def transcribe_features(self, input_features: torch.Tensor) -> torch.Tensor:
+        """log-mel fp32 [n, 80, 3000] (host or device) -> ids int32 [n, max_length] on the host, padded with pad_token_id."""
+        L, pad = self.config["max_length"], self.config["pad_token_id"]
+        rows = []
+        for b0 in range(0, input_features.shape[0], self.max_batch):
+            mel = input_features[b0:b0 + self.max_batch].to(self.engine.device, torch.float32).contiguous()
+            ids = self.engine.generate(mel, compact_every=self.compact_every)
+            rows.append(dp.pad_tokens(ids, ids.shape[0], L, pad).cpu())
+        return torch.cat(rows, dim=0) if rows else torch.empty(0, L, dtype=torch.int32)
+
+    @torch.no_grad()
+    def transcribe_waveforms(self, waves: Sequence) -> torch.Tensor:
+        """16 kHz waveforms (any lengths; padded / cut to 30 s) -> ids int32 [n, max_length] on the host."""
+        L, pad = self.config["max_length"], self.config["pad_token_id"]
+        rows = []
+        for chunk in batches(list(waves), self.max_batch):
+            ids = self.engine.generate(self.frontend(chunk), compact_every=self.compact_every)
+            rows.append(dp.pad_tokens(ids, ids.shape[0], L, pad).cpu())
+        return torch.cat(rows, dim=0) if rows else torch.empty(0, L, dtype=torch.int32)
+
+    def transcribe_files(self, paths: Sequence[str]) -> torch.Tensor:
+        """Audio files -> ids of ALL files on every rank; each rank transcribes its contiguous shard (dp.shard_range)."""
+        import torch.distributed as dist
+        L, pad = self.config["max_length"], self.config["pad_token_id"]
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+        b, e = dp.shard_range(len(paths), world, rank)
+        ids = self.transcribe_waveforms([load_audio(p) for p in paths[b:e]])
+        if world == 1:
+            return ids
+        return dp.gather_tokens(ids.to(self.engine.device), len(paths), L, pad).cpu()
+
+    # ------------------------------------------------------------------ text
+    def decode(self, ids) -> List[str]:
+        """``hf_processor.batch_decode(predicted_ids, skip_special_tokens=True)`` (run.py:287)."""
+        if self.detokenizer is None:
+            raise FileNotFoundError(f"{self.checkpoint_dir} has no vocab.json: token ids cannot be turned into text")
+        return self.detokenizer.batch_decode(ids, skip_special_tokens=True)
+
+    def __call__(self, waves: Sequence) -> List[str]:
+        return self.decode(self.transcribe_waveforms(waves))
+
+    def wer(self, hypotheses: Sequence[str], references: Sequence[str]) -> float:
+        """Both sides through the English normaliser, then the corpus word error rate (cal_wer.py:279-286)."""
+        return wer([self.normalizer(t) for t in references], [self.normalizer(t) for t in hypotheses])
+
+    def close(self):
+        self.engine.close()
+
+
+def compare_transcriptions(ours: Sequence[str], theirs: Sequence[str]) -> List[tuple]:
+    """The `--compare` report of run.py:321-331: the (ours, theirs) pairs that differ."""
+    if len(ours) != len(theirs):
+        raise ValueError("the two runs transcribed a different number of utterances")
+    return [(a, b) for a, b in zip(ours, theirs) if a != b]
