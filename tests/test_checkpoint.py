@@ -72,3 +72,28 @@ def test_errors_are_loud(micro, tmp_path):
     checkpoint.save_hf_checkpoint(str(tmp_path / "bad"), cfg, {"foo": torch.zeros(2)})
     with pytest.raises(KeyError):
         checkpoint.load_state_dict(str(tmp_path / "bad"))
+
+
+def test_directory_written_by_installed_transformers(tmp_path):
+    """The on-disk format as today's `transformers` writes it (`save_pretrained`: tied head stored once, generation fields in
+    generation_config.json): every tensor of the model's state_dict comes back under the same key, bit for bit."""
+    transformers = pytest.importorskip("transformers")
+    cfg = transformers.WhisperConfig(
+        vocab_size=51864, num_mel_bins=80, d_model=64, encoder_layers=2, decoder_layers=2, encoder_attention_heads=1,
+        decoder_attention_heads=1, encoder_ffn_dim=256, decoder_ffn_dim=256, max_source_positions=1500, max_target_positions=448,
+        pad_token_id=50256, bos_token_id=50256, eos_token_id=50256, decoder_start_token_id=50257)
+    torch.manual_seed(0)
+    model = transformers.WhisperForConditionalGeneration(cfg)
+    model.generation_config.forced_decoder_ids = [[1, 50362]]
+    model.generation_config.suppress_tokens = [1, 2, 7]
+    model.generation_config.max_length = 448
+    model.save_pretrained(str(tmp_path))
+    cfg2, sd2 = checkpoint.load_hf_checkpoint(str(tmp_path))
+    assert (cfg2["d_model"], cfg2["encoder_layers"], cfg2["decoder_attention_heads"], cfg2["vocab_size"]) == (64, 2, 1, 51864)
+    assert cfg2["forced_decoder_ids"] == [[1, 50362]] and cfg2["suppress_tokens"] == [1, 2, 7] and cfg2["max_length"] == 448
+    assert cfg2["begin_suppress_tokens"] == [220, 50256] and cfg2["decoder_start_token_id"] == 50257
+    sd = model.state_dict()
+    assert set(sd2) == set(sd)
+    for k, v in sd.items():
+        assert torch.equal(sd2[k], v.float()), k
+    assert torch.equal(sd2["proj_out.weight"], sd2["model.decoder.embed_tokens.weight"])
