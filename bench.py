@@ -148,6 +148,28 @@ def cpu_reference_rtfx(size, max_length, sample_batch=4, sample_steps=64):
     return value, cores, sample, total
 
 
+def job_ceiling(cfg, batch, elem_bytes, peaks):
+    """Whole-job roofline of one step: encoder + cross-K/V projection at the measured sustained tensor
+    throughput, then max_length-1 decode steps at the measured HBM bandwidth, each streaming the decoder weights once for the
+    batch and, per utterance, the cross K/V of every layer plus the self K/V written so far.  -> dict with the ceiling RTFx."""
+    d, S, V = cfg["d_model"], cfg["max_source_positions"], cfg["vocab_size"]
+    Le, Ld, steps = cfg["encoder_layers"], cfg["decoder_layers"], cfg["max_length"] - 1
+    mel, frames = cfg["num_mel_bins"], 2 * S
+    enc_flops = 2 * frames * 3 * mel * d + 2 * S * 3 * d * d + Le * (24 * S * d * d + 4 * S * S * d)
+    xkv_flops = Ld * 4 * S * d * d
+    w_step = Ld * 14 * d * d + V * d                      # decoder weights read per step (cross k/v projections excluded)
+    cross = 2 * Ld * S * d                                # cross K/V elements per utterance, read every step
+    self_kv = Ld * d * steps * (steps + 1)                # sum over t = 1..steps of 2 * Ld * t * d
+    dec_bytes = elem_bytes * (steps * w_step + batch * (steps * cross + self_kv))
+    tensor_tflops = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1400.0   # inside a long step: sustained
+    t_enc = batch * (enc_flops + xkv_flops) / (tensor_tflops * 1e12)
+    t_dec = dec_bytes / (peaks["hbm_gbs"] * 1e9)
+    return {"ceiling": round(AUDIO_SECONDS * batch / (t_enc + t_dec), 1), "unit": UNIT, "encoder_floor_ms": round(t_enc * 1e3, 1),
+            "decode_floor_ms": round(t_dec * 1e3, 1), "flops_per_utterance": enc_flops + xkv_flops,
+            "decode_bytes_per_step_mean": int(dec_bytes / steps),
+            "peaks": {"tensor_tflops": tensor_tflops, "hbm_gbs": peaks["hbm_gbs"]}}
+
+
 def workload_config(args, world):
     """The `config` object of the JSON line (same for our arm and the reference arm)."""
     B = args.batch
@@ -352,6 +374,10 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
         }
+        # the whole job against its own roofline (per GPU; ranks are independent): north_star's "fraction of roofline"
+        job = job_ceiling(cfg, B, es, peaks)
+        job["frac"] = round(value / world / job["ceiling"], 4)
+        line["job_roofline"] = job
         if not args.no_cpu_baseline and world == 1:
             v, cores, sample, _ = cpu_reference_rtfx(args.size, args.max_length)
             line["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
