@@ -7,8 +7,9 @@ cal_wer.py:227-287 on top of whisper_trtllm_b200 — batched, log-mel on the GPU
     python examples/transcribe.py --whisper ... --audio wav_dir --compare                 # vs HuggingFace on the CPU (run.py --compare)
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 examples/transcribe.py ...   # sharded by utterance
 
-`--audio` is a directory of 16 kHz .wav / .npy files, a LibriSpeech `*.trans.txt`, a TSV `<path>\\t<text>` or a .jsonl
-(`whisper_trtllm_b200.audio.read_manifest`).  Needs a B200 (there is no CPU path) and a checkpoint directory in the HF layout
+`--audio` is a directory of 16 kHz .wav / .flac / .npy files, a LibriSpeech `*.trans.txt`, a TSV `<path>\\t<text>`, a .jsonl
+(`whisper_trtllm_b200.audio.read_manifest`) or an HF `datasets` directory such as the reference's ./librispeech_asr_dummy
+(run.py:241-247; FLAC bytes are decoded by the repo's own decoder, libwb_audio.so).  Needs a B200 (there is no CPU path) and a checkpoint directory in the HF layout
 (config.json, model.safetensors, vocab.json, optionally normalizer.json).
 """
 import argparse
@@ -50,7 +51,7 @@ def main(argv=None):
     args = parse_arguments(argv)
     import torch
     import torch.distributed as dist
-    from whisper_trtllm_b200.audio import read_manifest
+    from whisper_trtllm_b200.audio import is_hf_dataset, read_hf_dataset, read_manifest
     from whisper_trtllm_b200.pipeline import WhisperPipeline, compare_transcriptions
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -59,14 +60,19 @@ def main(argv=None):
     if world > 1:
         dist.init_process_group("nccl")
 
-    paths, references = read_manifest(args.audio)
+    waves = None
+    if is_hf_dataset(args.audio):
+        waves, references = read_hf_dataset(args.audio)
+        paths = [f"{os.path.basename(os.path.normpath(args.audio))}[{i}]" for i in range(len(waves))]
+    else:
+        paths, references = read_manifest(args.audio)
     if args.wer and references is None:
         raise SystemExit(f"--wer needs reference texts, {args.audio} has none")
     pipe = WhisperPipeline(args.whisper, dtype=args.dtype, max_batch=args.batch, compact_every=args.compact_every)
 
     torch.cuda.synchronize()
     t0 = time.time()
-    ids = pipe.transcribe_files(paths)
+    ids = pipe.transcribe_files(paths) if waves is None else pipe.transcribe_sharded(waves)
     torch.cuda.synchronize()
     elapsed = time.time() - t0
     if rank == 0:
@@ -85,6 +91,8 @@ def main(argv=None):
         if args.wer:
             print(f"WER: {pipe.wer(texts, references) * 100:.2f} %")                      # cal_wer.py:287
         if args.compare:
+            if waves is not None:
+                raise SystemExit("--compare reads audio files; export the dataset's audio to a directory first")
             t0 = time.time()
             hf = huggingface_transcriptions(args.whisper, paths)
             hf_time = time.time() - t0

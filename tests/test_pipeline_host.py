@@ -58,7 +58,7 @@ def test_wrong_rate_shape_and_format_are_errors(tmp_path):
     with pytest.raises(ValueError, match="1-D"):
         audio.load_audio(str(tmp_path / "m.npy"))
     with pytest.raises(ValueError, match="unsupported"):
-        audio.load_audio(str(tmp_path / "x.flac"))
+        audio.load_audio(str(tmp_path / "x.mp3"))
     np.save(str(tmp_path / "ok.npy"), _tone().astype(np.float64))
     assert audio.load_audio(str(tmp_path / "ok.npy")).dtype == np.float32
 

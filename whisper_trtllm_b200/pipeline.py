@@ -85,16 +85,26 @@ class WhisperPipeline:
             rows.append(dp.pad_tokens(ids, ids.shape[0], L, pad).cpu())
         return torch.cat(rows, dim=0) if rows else torch.empty(0, L, dtype=torch.int32)
 
-    def transcribe_files(self, paths: Sequence[str]) -> torch.Tensor:
-        """Audio files -> ids of ALL files on every rank; each rank transcribes its contiguous shard (dp.shard_range)."""
+    def transcribe_sharded(self, items: Sequence, load=None) -> torch.Tensor:
+        """ids of ALL items on every rank: each rank transcribes its contiguous shard (dp.shard_range), one final gather.
+        ``load(item) -> waveform`` is applied on a thread pool (file reading and FLAC decoding release the GIL)."""
         import torch.distributed as dist
         L, pad = self.config["max_length"], self.config["pad_token_id"]
         rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
-        b, e = dp.shard_range(len(paths), world, rank)
-        ids = self.transcribe_waveforms([load_audio(p) for p in paths[b:e]])
+        b, e = dp.shard_range(len(items), world, rank)
+        mine = list(items[b:e])
+        if load is not None and mine:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as pool:
+                mine = list(pool.map(load, mine))
+        ids = self.transcribe_waveforms(mine)
         if world == 1:
             return ids
-        return dp.gather_tokens(ids.to(self.engine.device), len(paths), L, pad).cpu()
+        return dp.gather_tokens(ids.to(self.engine.device), len(items), L, pad).cpu()
+
+    def transcribe_files(self, paths: Sequence[str]) -> torch.Tensor:
+        """Audio files (.wav / .flac / .npy, 16 kHz) -> ids int32 [n, max_length] of all files, on every rank."""
+        return self.transcribe_sharded(paths, load=load_audio)
 
     # ------------------------------------------------------------------ text
     def decode(self, ids) -> List[str]:
