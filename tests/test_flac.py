@@ -259,3 +259,38 @@ def test_hf_dataset_directory_with_flac_bytes(tmp_path):
         assert g.dtype == np.float32 and np.array_equal(g, (w[:, 0] / 32768.0).astype(np.float32))
     with pytest.raises(KeyError):
         audio.read_hf_dataset(str(tmp_path / "librispeech_asr_dummy"), audio_column="speech")
+
+
+# ---------------------------------------------------------------------------------------------------- memory safety
+def test_mutation_fuzz_under_address_and_ub_sanitizers(tmp_path):
+    """tests/fuzz_flac.c + the decoder compiled with -fsanitize=address,undefined: 15 000 mutated streams (bit flips, random
+    bytes, truncations, 0x00 / 0xff runs); any out-of-bounds access or undefined behaviour aborts the run."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "fuzz_flac")
+    build = subprocess.run([gcc, "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-DWB_AUDIO_BUILD", "-o", exe,
+                            os.path.join(ROOT, "tests", "fuzz_flac.c"),
+                            os.path.join(ROOT, "whisper_trtllm_b200", "csrc", "audio", "flac_decode.c")], capture_output=True, text=True)
+    if build.returncode != 0 and "sanitize" in build.stderr.lower() + build.stdout.lower():
+        pytest.skip("sanitizer runtime not available")
+    assert build.returncode == 0, build.stderr[-2000:]
+    cases = [
+        (_signal(3000, 2, 16, 1), dict(stereo="mid_side", kind=("lpc", [1800, -900], 12, 10), blocksize=1024, partition_order=3)),
+        (_signal(2000, 1, 24, 2), dict(bps=24, kind=("fixed", 4), blocksize=576, five_bit=True, partition_order=2)),
+        (_signal(1500, 3, 8, 3), dict(bps=8, kind="verbatim", blocksize=255)),
+        (np.clip(_signal(2500, 2, 16, 4) * 4, -32768, 32764), dict(stereo="left_side", kind=("fixed", 2), blocksize=500, escape=True,
+                                                                     partition_order=2, variable=True)),
+        (np.zeros((5000, 1), dtype=np.int64), dict(kind="constant", blocksize=4096, total_samples_known=False, md5=False)),
+    ]
+    files = []
+    for i, (pcm, kw) in enumerate(cases):
+        files.append(str(tmp_path / f"case{i}.flac"))
+        with open(files[-1], "wb") as f:
+            f.write(FW.encode(pcm, **kw))
+    run = subprocess.run([exe, "3000"] + files, capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, (run.stdout + run.stderr)[-3000:]
+    counts = dict(zip(run.stdout.split()[0::2], map(int, run.stdout.split()[1::2])))
+    assert sum(counts.values()) == 15000 and counts["format"] + counts["checksum"] > 10000

@@ -396,11 +396,13 @@ static int read_subframe(BitReader* b, int64_t* s, uint32_t n, int bits) {
         for (int i = 0; i < order; ++i) s[i] = br_read_signed(b, bits);
         int rc = read_residual(b, s, n, order);
         if (rc) return rc;
+        /* wrapping (unsigned) arithmetic: corrupt residuals must not trigger signed overflow before the CRC rejects the frame */
+        uint64_t* u = (uint64_t*)s;
         switch (order) {
-            case 1: for (uint32_t i = 1; i < n; ++i) s[i] += s[i - 1]; break;
-            case 2: for (uint32_t i = 2; i < n; ++i) s[i] += 2 * s[i - 1] - s[i - 2]; break;
-            case 3: for (uint32_t i = 3; i < n; ++i) s[i] += 3 * s[i - 1] - 3 * s[i - 2] + s[i - 3]; break;
-            case 4: for (uint32_t i = 4; i < n; ++i) s[i] += 4 * s[i - 1] - 6 * s[i - 2] + 4 * s[i - 3] - s[i - 4]; break;
+            case 1: for (uint32_t i = 1; i < n; ++i) u[i] += u[i - 1]; break;
+            case 2: for (uint32_t i = 2; i < n; ++i) u[i] += 2 * u[i - 1] - u[i - 2]; break;
+            case 3: for (uint32_t i = 3; i < n; ++i) u[i] += 3 * u[i - 1] - 3 * u[i - 2] + u[i - 3]; break;
+            case 4: for (uint32_t i = 4; i < n; ++i) u[i] += 4 * u[i - 1] - 6 * u[i - 2] + 4 * u[i - 3] - u[i - 4]; break;
             default: break;
         }
     } else if (type >= 32) { /* LPC, order 1..32 */
@@ -416,9 +418,10 @@ static int read_subframe(BitReader* b, int64_t* s, uint32_t n, int bits) {
         int rc = read_residual(b, s, n, order);
         if (rc) return rc;
         for (uint32_t i = (uint32_t)order; i < n; ++i) {
-            int64_t acc = 0;
-            for (int j = 0; j < order; ++j) acc += coef[j] * s[i - 1 - j];
-            s[i] += acc >> shift; /* arithmetic shift: rounds towards minus infinity, as the format requires */
+            uint64_t acc = 0; /* wrapping arithmetic, see above; exact for every valid stream (|sum| < 2^63) */
+            for (int j = 0; j < order; ++j) acc += (uint64_t)coef[j] * (uint64_t)s[i - 1 - j];
+            /* arithmetic shift: rounds towards minus infinity, as the format requires */
+            s[i] = (int64_t)((uint64_t)s[i] + (uint64_t)((int64_t)acc >> shift));
         }
     } else {
         FAIL(WB_AUDIO_ERR_FORMAT, "reserved subframe type %d", type);
@@ -493,14 +496,14 @@ WB_AUDIO_API int wb_flac_decode_i32(const uint8_t* data, size_t size, int32_t* o
         int64_t* c0 = chan;
         int64_t* c1 = chan + 65536;
         if (h.assignment == 8) { /* left, side = left - right */
-            for (uint32_t i = 0; i < n; ++i) c1[i] = c0[i] - c1[i];
+            for (uint32_t i = 0; i < n; ++i) c1[i] = (int64_t)((uint64_t)c0[i] - (uint64_t)c1[i]);
         } else if (h.assignment == 9) { /* side, right */
-            for (uint32_t i = 0; i < n; ++i) c0[i] += c1[i];
+            for (uint32_t i = 0; i < n; ++i) c0[i] = (int64_t)((uint64_t)c0[i] + (uint64_t)c1[i]);
         } else if (h.assignment == 10) { /* mid = (left + right) >> 1, side = left - right: the dropped bit is side's parity */
             for (uint32_t i = 0; i < n; ++i) {
-                int64_t side = c1[i], mid = (int64_t)((uint64_t)c0[i] << 1) | (side & 1);
-                c0[i] = (mid + side) >> 1;
-                c1[i] = (mid - side) >> 1;
+                uint64_t side = (uint64_t)c1[i], mid = ((uint64_t)c0[i] << 1) | (side & 1);
+                c0[i] = (int64_t)(mid + side) >> 1;
+                c1[i] = (int64_t)(mid - side) >> 1;
             }
         }
         if (info.total_samples && done + n > info.total_samples) BAIL(WB_AUDIO_ERR_FORMAT, "more samples than STREAMINFO announces");
