@@ -9,7 +9,7 @@ cal_wer.py:227-287 on top of whisper_trtllm_b200 — batched, log-mel on the GPU
 
 `--audio` is a directory of 16 kHz .wav / .flac / .npy files, a LibriSpeech `*.trans.txt`, a TSV `<path>\\t<text>`, a .jsonl
 (`whisper_trtllm_b200.audio.read_manifest`) or an HF `datasets` directory such as the reference's ./librispeech_asr_dummy
-(run.py:241-247; FLAC bytes are decoded by the repo's own decoder, libwb_audio.so).  Needs a B200 (there is no CPU path) and a checkpoint directory in the HF layout
+(run.py:241-247; FLAC bytes are decoded by the repo's own decoder, libwb_audio.so), or cal_wer.py's `librispeech.cache`.  Needs a B200 (there is no CPU path) and a checkpoint directory in the HF layout
 (config.json, model.safetensors, vocab.json, optionally normalizer.json).
 """
 import argparse
@@ -51,7 +51,7 @@ def main(argv=None):
     args = parse_arguments(argv)
     import torch
     import torch.distributed as dist
-    from whisper_trtllm_b200.audio import is_hf_dataset, read_hf_dataset, read_manifest
+    from whisper_trtllm_b200.audio import is_hf_dataset, read_hf_dataset, read_manifest, read_mel_cache
     from whisper_trtllm_b200.pipeline import WhisperPipeline, compare_transcriptions
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -60,8 +60,11 @@ def main(argv=None):
     if world > 1:
         dist.init_process_group("nccl")
 
-    waves = None
-    if is_hf_dataset(args.audio):
+    waves, mels = None, None
+    if args.audio.endswith(".cache"):            # cal_wer.py's pickled (log-mel, text) pairs (get_LibriSpeech.py)
+        mels, references = read_mel_cache(args.audio)
+        paths = [f"{os.path.basename(args.audio)}[{i}]" for i in range(mels.shape[0])]
+    elif is_hf_dataset(args.audio):
         waves, references = read_hf_dataset(args.audio)
         paths = [f"{os.path.basename(os.path.normpath(args.audio))}[{i}]" for i in range(len(waves))]
     else:
@@ -72,7 +75,10 @@ def main(argv=None):
 
     torch.cuda.synchronize()
     t0 = time.time()
-    ids = pipe.transcribe_files(paths) if waves is None else pipe.transcribe_sharded(waves)
+    if mels is not None:
+        ids = pipe.transcribe_sharded(mels, features=True)
+    else:
+        ids = pipe.transcribe_files(paths) if waves is None else pipe.transcribe_sharded(waves)
     torch.cuda.synchronize()
     elapsed = time.time() - t0
     if rank == 0:
@@ -91,7 +97,7 @@ def main(argv=None):
         if args.wer:
             print(f"WER: {pipe.wer(texts, references) * 100:.2f} %")                      # cal_wer.py:287
         if args.compare:
-            if waves is not None:
+            if waves is not None or mels is not None:
                 raise SystemExit("--compare reads audio files; export the dataset's audio to a directory first")
             t0 = time.time()
             hf = huggingface_transcriptions(args.whisper, paths)

@@ -98,6 +98,41 @@ def test_manifests(tmp_path):
         audio.read_manifest(str(e))
 
 
+def test_librispeech_tree_and_mel_cache(tmp_path):
+    import pickle
+
+    import torch
+    # LibriSpeech layout: <split>/<speaker>/<chapter>/<speaker>-<chapter>-<utt>.flac + <speaker>-<chapter>.trans.txt
+    import flac_writer as FW
+    want_paths, want_refs = [], []
+    for spk, chap in (("1089", "134686"), ("1089", "134691"), ("121", "127105")):
+        d = tmp_path / "test-clean" / spk / chap
+        d.mkdir(parents=True)
+        lines = []
+        for u in range(2):
+            uid = f"{spk}-{chap}-{u:04d}"
+            pcm = np.rint(_tone(800 + 100 * u) * 32767).astype(np.int64)
+            (d / f"{uid}.flac").write_bytes(FW.encode(pcm, blocksize=256))
+            lines.append(f"{uid} TEXT OF {uid.replace('-', ' ')}")
+        (d / f"{spk}-{chap}.trans.txt").write_text("\n".join(lines) + "\n")
+    paths, refs = audio.read_manifest(str(tmp_path / "test-clean"))
+    assert [os.path.basename(p) for p in paths] == ["1089-134686-0000.flac", "1089-134686-0001.flac", "1089-134691-0000.flac",
+                                                    "1089-134691-0001.flac", "121-127105-0000.flac", "121-127105-0001.flac"]
+    assert refs[0] == "TEXT OF 1089 134686 0000" and len(refs) == 6
+    x = audio.load_audio(paths[1])
+    assert x.shape == (900,) and np.abs(x - _tone(900)).max() < 1e-4
+    # cal_wer.py's librispeech.cache: pickled (mel, text) pairs
+    pairs = [(torch.full((80, 3000), float(i)), f"text {i}") for i in range(3)]
+    with open(tmp_path / "librispeech.cache", "wb") as f:
+        pickle.dump(pairs, f)
+    mels, texts = audio.read_mel_cache(str(tmp_path / "librispeech.cache"))
+    assert mels.shape == (3, 80, 3000) and mels.dtype == torch.float32 and float(mels[2, 5, 7]) == 2.0 and texts == ["text 0", "text 1", "text 2"]
+    with open(tmp_path / "short.cache", "wb") as f:
+        pickle.dump([(torch.zeros(80, 100), "x")], f)
+    with pytest.raises(ValueError, match="3000"):
+        audio.read_mel_cache(str(tmp_path / "short.cache"))
+
+
 def test_batches():
     assert [list(b) for b in audio.batches(list(range(5)), 2)] == [[0, 1], [2, 3], [4]]
     assert list(audio.batches([], 4)) == []

@@ -163,25 +163,29 @@ def _find_audio(stem: str) -> Optional[str]:
 def read_manifest(path: str) -> Tuple[List[str], Optional[List[str]]]:
     """-> (audio paths, reference texts or None).
 
-    * a directory: every .wav / .npy in it (sorted); references from the ``*.trans.txt`` files in it when there are any;
+    * a directory: every .wav / .flac / .npy in it and below it (sorted by path); when there are ``*.trans.txt`` files anywhere
+      below it (a LibriSpeech split: ``test-clean/<speaker>/<chapter>/``), the utterances and references they list;
     * ``*.trans.txt``: LibriSpeech transcript file, ``<id> <TEXT>``, audio = ``<dir>/<id>.wav|.npy``;
     * ``*.jsonl``: one object per line with ``audio`` (path, relative to the file) and optionally ``text``;
     * anything else: TSV ``<path>[\\t<text>]``; a line without a tab is an audio path without a reference.
     """
-    if os.path.isdir(path):
-        trans = sorted(f for f in os.listdir(path) if f.endswith(".trans.txt"))
+    if os.path.isdir(path):            # the directory and everything below it (LibriSpeech: <split>/<speaker>/<chapter>/...)
+        trans, files = [], []
+        for root, dirs, names in os.walk(path):
+            dirs.sort()
+            trans += [os.path.join(root, f) for f in sorted(names) if f.endswith(".trans.txt")]
+            files += [os.path.join(root, f) for f in sorted(names) if f.lower().endswith(AUDIO_EXTENSIONS)]
         if trans:
             audio: List[str] = []
             texts: List[str] = []
             for t in trans:
-                a, r = read_manifest(os.path.join(path, t))
+                a, r = read_manifest(t)
                 audio += a
                 texts += r or []
             return audio, texts
-        files = sorted(f for f in os.listdir(path) if f.lower().endswith(AUDIO_EXTENSIONS))
         if not files:
             raise FileNotFoundError(f"no {' / '.join(AUDIO_EXTENSIONS)} files under {path}")
-        return [os.path.join(path, f) for f in files], None
+        return files, None
     base = os.path.dirname(os.path.abspath(path))
     audio, texts, have_text = [], [], []
     with open(path, encoding="utf-8") as f:
@@ -244,6 +248,23 @@ def read_hf_dataset(path: str, audio_column: str = "audio", text_column: str = "
         waves.append(x)
     texts = list(ds[text_column]) if text_column in ds.column_names else None
     return waves, texts
+
+
+def read_mel_cache(path: str):
+    """The reference's ``librispeech.cache`` (get_LibriSpeech.py:32-41, read by cal_wer.py:248-249): a pickled list of
+    (log-mel [80, 3000], text) pairs -> (fp32 tensor [n, 80, 3000], texts).  A pickle runs code when loaded: only open files you
+    made yourself, exactly as with the reference's script."""
+    import pickle
+
+    import torch
+    with open(path, "rb") as f:
+        pairs = pickle.load(f)
+    if not pairs:
+        raise ValueError(f"{path}: empty cache")
+    mels = torch.stack([torch.as_tensor(m, dtype=torch.float32).reshape(80, -1) for m, _ in pairs])
+    if mels.shape[-1] != 3000:
+        raise ValueError(f"{path}: log-mel windows of {mels.shape[-1]} frames, expected 3000 (30 s)")
+    return mels.contiguous(), [t for _, t in pairs]
 
 
 def batches(items: Sequence, size: int):

@@ -85,13 +85,17 @@ class WhisperPipeline:
             rows.append(dp.pad_tokens(ids, ids.shape[0], L, pad).cpu())
         return torch.cat(rows, dim=0) if rows else torch.empty(0, L, dtype=torch.int32)
 
-    def transcribe_sharded(self, items: Sequence, load=None) -> torch.Tensor:
+    def transcribe_sharded(self, items, load=None, features: bool = False) -> torch.Tensor:
         """ids of ALL items on every rank: each rank transcribes its contiguous shard (dp.shard_range), one final gather.
-        ``load(item) -> waveform`` is applied on a thread pool (file reading and FLAC decoding release the GIL)."""
+        ``load(item) -> waveform`` is applied on a thread pool (file reading and FLAC decoding release the GIL).
+        ``features``: the items are log-mel windows [n, 80, 3000] (cal_wer.py's librispeech.cache), not waveforms."""
         import torch.distributed as dist
         L, pad = self.config["max_length"], self.config["pad_token_id"]
         rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
         b, e = dp.shard_range(len(items), world, rank)
+        if features:
+            ids = self.transcribe_features(items[b:e])
+            return ids if world == 1 else dp.gather_tokens(ids.to(self.engine.device), len(items), L, pad).cpu()
         mine = list(items[b:e])
         if load is not None and mine:
             from concurrent.futures import ThreadPoolExecutor
