@@ -90,3 +90,23 @@ def test_wer_known_answers():
     assert wer(["a b c d", "e f"], ["a x c d", "e f g"]) == pytest.approx(2 / 6)
     with pytest.raises(ValueError):
         wer(["a"], ["a", "b"])
+
+
+def test_detokenizer_matches_both_reference_tokenizers():
+    """oracle/make_golden_detok.py: `decode` of the reference's WhisperTokenizer (slow: no clean-up) and WhisperTokenizerFast
+    (clean_up_tokenization_spaces, the class run.py:239 gets) over a synthetic byte-level vocabulary with the full set of special
+    tokens; with and without skip_special_tokens; prompts (<|startofprev|> ...) stripped as the reference does."""
+    with open(os.path.join(os.path.dirname(GOLDEN), "detokenizer.json"), encoding="utf-8") as f:
+        g = json.load(f)
+    assert len(g["cases"]) > 400 and g["fast_clean_up"] is True and g["slow_clean_up"] is False
+    differ = 0
+    for clean, cols in ((False, (1, 2)), (True, (3, 4))):
+        d = WhisperDetokenizer(g["vocab"], g["first_special_id"], clean_up_tokenization_spaces=clean, added_tokens=g["added_tokens"])
+        for case in g["cases"]:
+            assert d.decode(case[0], skip_special_tokens=True) == case[cols[0]], (clean, case[0])
+            assert d.decode(case[0], skip_special_tokens=False) == case[cols[1]], (clean, case[0])
+            differ += case[1] != case[3]
+        # the per-call argument overrides the tokenizer's setting
+        assert d.decode(g["cases"][1][0], clean_up_tokenization_spaces=True) == g["cases"][1][3]
+        assert d.batch_decode([g["cases"][1][0]], clean_up_tokenization_spaces=False) == [g["cases"][1][1]]
+    assert differ > 100          # the clean-up matters: the two classes disagree on a third of the cases

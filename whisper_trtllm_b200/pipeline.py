@@ -39,8 +39,18 @@ def load_text_tools(checkpoint_dir: str, config: Dict):
     """-> (detokenizer or None, normaliser).  ``vocab.json`` and ``normalizer.json`` are the tokenizer files that ship with
     every Whisper checkpoint; without ``vocab.json`` only token ids can be returned, without ``normalizer.json`` the
     normaliser runs with an empty spelling table."""
+    def read_json(name):
+        p = os.path.join(checkpoint_dir, name)
+        if not os.path.exists(p):
+            return {}
+        with open(p, encoding="utf-8") as f:
+            return json.load(f)
     vocab = os.path.join(checkpoint_dir, "vocab.json")
-    detok = WhisperDetokenizer(vocab, first_special_token_id(checkpoint_dir, config)) if os.path.exists(vocab) else None
+    detok = None
+    if os.path.exists(vocab):
+        clean_up = read_json("tokenizer_config.json").get("clean_up_tokenization_spaces", True)   # tokenization_utils_base.py:1552
+        detok = WhisperDetokenizer(vocab, first_special_token_id(checkpoint_dir, config), clean_up_tokenization_spaces=clean_up,
+                                   added_tokens=read_json("added_tokens.json"))
     spelling = {}
     p = os.path.join(checkpoint_dir, "normalizer.json")
     if os.path.exists(p):

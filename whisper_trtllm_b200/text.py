@@ -3,8 +3,10 @@
 normaliser and ``jiwer.wer`` (cal_wer.py:279-287).  Pure host-side string work, no arithmetic on the path.
 
 * ``WhisperDetokenizer``: Whisper's tokenizer is GPT-2 byte-level BPE; decoding needs only ``vocab.json``
-  (token string -> id) and the byte<->unicode table (tokenization_whisper.py ``bytes_to_unicode`` / ``decode``).
-  Special tokens are every id >= the first added token (``<|endoftext|>`` = 50256 for the ``.en`` vocabularies).
+  (token string -> id) and the byte<->unicode table (tokenization_whisper.py ``bytes_to_unicode`` / ``_decode``).
+  Special tokens are every id >= the first added token (``<|endoftext|>`` = 50256 for the ``.en`` vocabularies).  Output equals
+  the reference's ``WhisperTokenizer.decode`` (clean-up off) and ``WhisperTokenizerFast.decode`` (clean-up on, the default of
+  ``WhisperProcessor``) — tests/golden/detokenizer.json.
 * ``BasicTextNormalizer`` / ``EnglishTextNormalizer`` (+ ``EnglishNumberNormalizer``, ``EnglishSpellingNormalizer``): the
   normalisers of english_normalizer.py:75-595 — same class names, constructor arguments and outputs (pinned against the
   reference's own outputs on 2500 inputs, tests/golden/english_normalizer.json).  The British->American table is the
@@ -33,39 +35,70 @@ def bytes_to_unicode() -> Dict[int, str]:
     return dict(zip(bs, [chr(c) for c in cs]))
 
 
+# `PreTrainedTokenizerBase.clean_up_tokenization` (tokenization_utils_base.py:3598-3620): English detokenisation artefacts,
+# applied in this order by the FAST tokenizer's decode (tokenization_utils_fast.py:566-575) — the class
+# `WhisperProcessor.from_pretrained` (run.py:239) loads when `tokenizers` is installed.  The slow WhisperTokenizer._decode
+# (tokenization_whisper.py:613-645) never applies it.
+_CLEAN_UP = ((" .", "."), (" ?", "?"), (" !", "!"), (" ,", ","), (" ' ", "'"), (" n't", "n't"), (" 'm", "'m"), (" 's", "'s"),
+             (" 've", "'ve"), (" 're", "'re"))
+
+
+def clean_up_tokenization(text: str) -> str:
+    for a, b in _CLEAN_UP:
+        text = text.replace(a, b)
+    return text
+
+
 class WhisperDetokenizer:
-    def __init__(self, vocab: Union[str, Dict[str, int]], first_special_id: int = 50256):
+    def __init__(self, vocab: Union[str, Dict[str, int]], first_special_id: int = 50256, clean_up_tokenization_spaces: bool = True,
+                 added_tokens: Optional[Dict[str, int]] = None):
+        """``clean_up_tokenization_spaces``: the tokenizer's setting of that name (``tokenizer_config.json``; the base-class default
+        is True, tokenization_utils_base.py:1552).  ``added_tokens``: the checkpoint's ``added_tokens.json`` (special-token
+        strings for ``skip_special_tokens=False`` and the prompt markers)."""
         if isinstance(vocab, str):
             with open(vocab, encoding="utf-8") as f:
                 vocab = json.load(f)
         self.id_to_token = {int(i): t for t, i in vocab.items()}
+        for t, i in (added_tokens or {}).items():
+            self.id_to_token.setdefault(int(i), t)
         self.first_special_id = first_special_id
+        self.clean_up_tokenization_spaces = bool(clean_up_tokenization_spaces)
         self.byte_decoder = {c: b for b, c in bytes_to_unicode().items()}
+        token_to_id = {t: i for i, t in self.id_to_token.items()}
+        self.prompt_token_id = token_to_id.get("<|startofprev|>")
+        self.decoder_start_token_id = token_to_id.get("<|startoftranscript|>")
 
-    def decode(self, ids: Iterable[int], skip_special_tokens: bool = True) -> str:
-        pieces: List[str] = []
+    def _strip_prompt(self, ids: List[int]) -> List[int]:
+        """A sequence that starts with <|startofprev|> carries a text prompt: drop it up to <|startoftranscript|>
+        (tokenization_whisper.py `_strip_prompt`, applied when special tokens are skipped)."""
+        if ids and self.prompt_token_id is not None and ids[0] == self.prompt_token_id:
+            if self.decoder_start_token_id in ids:
+                return ids[ids.index(self.decoder_start_token_id):]
+            return []
+        return ids
+
+    def decode(self, ids: Iterable[int], skip_special_tokens: bool = True, clean_up_tokenization_spaces: Optional[bool] = None) -> str:
+        ids = [int(i) for i in ids]
+        if skip_special_tokens:
+            ids = self._strip_prompt(ids)
+        out = bytearray()
         for i in ids:
-            i = int(i)
             if i >= self.first_special_id:
-                if not skip_special_tokens:
-                    pieces.append(self.id_to_token.get(i, f"<|{i}|>"))
+                if not skip_special_tokens:           # special tokens are kept verbatim, not byte-decoded
+                    out.extend(self.id_to_token.get(i, f"<|{i}|>").encode("utf-8"))
                 continue
             tok = self.id_to_token.get(i)
             if tok is None:
                 raise KeyError(f"token id {i} is not in the vocabulary")
-            pieces.append(tok)
-        text = "".join(pieces)
-        out = bytearray()
-        for ch in text:
-            if ch in self.byte_decoder:
-                out.append(self.byte_decoder[ch])
-            else:                       # a special token kept verbatim
-                out.extend(ch.encode("utf-8"))
-        return out.decode("utf-8", errors="replace")
+            out.extend(self.byte_decoder[ch] for ch in tok)
+        text = out.decode("utf-8", errors="replace")
+        if self.clean_up_tokenization_spaces if clean_up_tokenization_spaces is None else clean_up_tokenization_spaces:
+            text = clean_up_tokenization(text)
+        return text
 
-    def batch_decode(self, batch_ids, skip_special_tokens: bool = True) -> List[str]:
+    def batch_decode(self, batch_ids, skip_special_tokens: bool = True, clean_up_tokenization_spaces: Optional[bool] = None) -> List[str]:
         rows = batch_ids.tolist() if hasattr(batch_ids, "tolist") else batch_ids
-        return [self.decode(r, skip_special_tokens) for r in rows]
+        return [self.decode(r, skip_special_tokens, clean_up_tokenization_spaces) for r in rows]
 
 
 # ---------------------------------------------------------------------------------------------------------------------
