@@ -184,3 +184,39 @@ def test_cli_arguments():
     spec.loader.exec_module(cli)
     a = cli.parse_arguments(["--whisper", "ckpt", "--audio", "dir", "--wer", "--batch", "8"])
     assert (a.whisper, a.audio, a.wer, a.compare, a.batch, a.dtype, a.compact_every) == ("ckpt", "dir", True, False, 8, "bfloat16", 32)
+
+
+def test_sharded_transcription_prefetches_the_next_batch_and_keeps_order():
+    """The scheduling around the engine, with the engine replaced by a stub: files of batch k + 1 are loaded while batch k is
+    'on the GPU', results come back in input order, a short last batch is fine."""
+    import threading
+
+    import torch
+    pipe = object.__new__(pipeline.WhisperPipeline)
+    pipe.config = {"max_length": 6, "pad_token_id": 0}
+    pipe.max_batch = 3
+    events, lock = [], threading.Lock()
+
+    def load(item):
+        with lock:
+            events.append(("load", item))
+        return np.full(4, item, dtype=np.float32)
+
+    def fake_transcribe(waves):
+        with lock:
+            events.append(("gpu", [int(w[0]) for w in waves]))
+        return torch.tensor([[int(w[0])] * 6 for w in waves], dtype=torch.int32).reshape(len(waves), 6)
+
+    pipe.transcribe_waveforms = fake_transcribe
+    ids = pipe.transcribe_sharded(list(range(8)), load=load)
+    assert ids[:, 0].tolist() == list(range(8)) and ids.shape == (8, 6)
+    gpu = [e[1] for e in events if e[0] == "gpu"]
+    assert gpu == [[0, 1, 2], [3, 4, 5], [6, 7]]
+    # every file of batch 1 was handed to the pool before batch 0 went to the engine ... and nothing was loaded twice
+    first_gpu = events.index(("gpu", [0, 1, 2]))
+    assert sorted(e[1] for e in events if e[0] == "load") == list(range(8))
+    assert {e[1] for e in events[:first_gpu] if e[0] == "load"} >= {0, 1, 2}
+    # no loader: the items are waveforms already
+    ids = pipe.transcribe_sharded([np.full(4, 9, dtype=np.float32)])
+    assert ids.tolist() == [[9] * 6]
+    assert pipe.transcribe_sharded([], load=load).shape[0] == 0

@@ -107,11 +107,20 @@ class WhisperPipeline:
             ids = self.transcribe_features(items[b:e])
             return ids if world == 1 else dp.gather_tokens(ids.to(self.engine.device), len(items), L, pad).cpu()
         mine = list(items[b:e])
-        if load is not None and mine:
+        if load is None or not mine:
+            ids = self.transcribe_waveforms(mine)
+        else:
+            # software pipeline: while the GPU works on batch k, the pool reads and decodes the files of batch k + 1
             from concurrent.futures import ThreadPoolExecutor
+            chunks = list(batches(mine, self.max_batch))
+            rows = []
             with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as pool:
-                mine = list(pool.map(load, mine))
-        ids = self.transcribe_waveforms(mine)
+                pending = [pool.submit(load, it) for it in chunks[0]]
+                for k in range(len(chunks)):
+                    waves = [f.result() for f in pending]
+                    pending = [pool.submit(load, it) for it in chunks[k + 1]] if k + 1 < len(chunks) else []
+                    rows.append(self.transcribe_waveforms(waves))
+            ids = torch.cat(rows, dim=0)
         if world == 1:
             return ids
         return dp.gather_tokens(ids.to(self.engine.device), len(items), L, pad).cpu()
