@@ -2,7 +2,6 @@
 absent, i.e. on the GPU box; there the committed goldens stand in).  Each check runs in a fresh interpreter: the vendored
 `transformers` must not meet the installed one that other tests import."""
 import json
-import os
 import subprocess
 import sys
 
