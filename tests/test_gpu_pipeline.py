@@ -73,3 +73,42 @@ def test_wav_files_to_text_and_wer(tmp_path):
     n_words = sum(len(pipe.normalizer(t).split()) for t in texts)
     assert pipe.wer(one_wrong, texts) == pytest.approx(1.0 / n_words)
     pipe.close()
+
+
+def _script(name):
+    import importlib.util
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("examples_whisper_" + name, os.path.join(ROOT, "examples", "whisper", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_reference_style_scripts_end_to_end(tmp_path, capsys):
+    """build_encoder.py + build_decoder.py + run.py with the reference's flags (examples/whisper/): engine files and config.pkl in
+    --engine_dir, runner classes + greedy_search over a directory of FLAC files; the printed transcriptions are those of the
+    pipeline on the same files."""
+    import flac_writer as FW
+    from whisper_trtllm_b200.pipeline import WhisperPipeline
+    cfg = synth.make_config("micro", max_length=16)
+    sd = synth.make_weights(cfg, seed=4)
+    ckpt = _checkpoint_dir(tmp_path, cfg, sd)
+    engine_dir = str(tmp_path / "whisper_outputs")
+    for name in ("build_encoder", "build_decoder"):
+        _script(name).main(["--whisper", ckpt, "--engine_dir", engine_dir])
+    data = tmp_path / "flac"
+    data.mkdir()
+    for i, kind in enumerate(("chirp_short", "silence", "chirp_short")):
+        w = LM.synth_wave(kind, seed=10 + i)[:24000 + 8000 * i]
+        pcm = np.clip(np.rint(w.astype(np.float64) * 32768.0), -32768, 32767).astype(np.int64)
+        (data / f"utt-{i}.flac").write_bytes(FW.encode(pcm, blocksize=4096, kind=("fixed", 2), partition_order=2))
+    capsys.readouterr()
+    _script("run").main(["--whisper", ckpt, "--engine_dir", engine_dir, "--dataset", str(data), "--batch", "2"])
+    lines = capsys.readouterr().out.splitlines()
+    assert lines[-1].startswith("B200 time:")
+    printed = lines[-4:-1]
+    pipe = WhisperPipeline(ckpt, dtype="float32", max_batch=2, device="cuda:0", compact_every=0)
+    paths, _ = audio.read_manifest(str(data))
+    want = pipe.decode(pipe.transcribe_files(paths))
+    pipe.close()
+    assert printed == want and all(printed)

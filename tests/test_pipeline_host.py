@@ -220,3 +220,47 @@ def test_sharded_transcription_prefetches_the_next_batch_and_keeps_order():
     ids = pipe.transcribe_sharded([np.full(4, 9, dtype=np.float32)])
     assert ids.tolist() == [[9] * 6]
     assert pipe.transcribe_sharded([], load=load).shape[0] == 0
+
+
+def _load_script(name):
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "whisper", name + ".py")
+    spec = importlib.util.spec_from_file_location("examples_whisper_" + name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_reference_style_build_scripts(tmp_path, capsys):
+    """examples/whisper/build_encoder.py / build_decoder.py: the reference's flags, engine files + config.pkl in --engine_dir
+    (build_encoder.py:22-28, :42-45, :109; build_decoder.py:119), loadable by Session.from_serialized_engine."""
+    import pickle
+
+    import torch
+    from oracle import synth
+    from whisper_trtllm_b200 import checkpoint, run, runtime
+    cfg = synth.make_config("micro")
+    sd = synth.make_weights(cfg, seed=2)
+    ckpt, out = str(tmp_path / "whisper-micro.en"), str(tmp_path / "whisper_outputs")
+    checkpoint.save_hf_checkpoint(ckpt, cfg, sd)
+    for name in ("build_encoder", "build_decoder"):
+        script = _load_script(name)
+        a = script.parse_arguments([])
+        assert (a.whisper, a.engine_precision, a.log_level, a.engine_dir) == ("whisper-tiny.en", "float32", "error", "whisper_outputs")
+        script.main(["--whisper", ckpt, "--engine_dir", out])
+    assert sorted(os.listdir(out)) == ["WhisperDecoder.engine", "WhisperEncoder.engine", "config.pkl"]
+    with open(os.path.join(out, "config.pkl"), "rb") as f:
+        config = pickle.load(f)
+    assert config["d_model"] == cfg["d_model"] and config["forced_decoder_ids"] == cfg["forced_decoder_ids"]
+    with open(os.path.join(out, "WhisperEncoder.engine"), "rb") as f:
+        kind, enc = runtime.deserialize_engine(f.read())
+    assert kind == "WhisperEncoder" and torch.equal(enc.conv1.weight.data.cpu().reshape(-1), sd["model.encoder.conv1.weight"].reshape(-1))
+    with open(os.path.join(out, "WhisperDecoder.engine"), "rb") as f:
+        kind, dec = runtime.deserialize_engine(f.read())
+    assert kind == "WhisperDecoder" and dec.dtype == torch.float32
+    # bfloat16 engines
+    _load_script("build_decoder").main(["--whisper", ckpt, "--engine_dir", out, "--engine_precision", "bfloat16"])
+    with open(os.path.join(out, "WhisperDecoder.engine"), "rb") as f:
+        assert runtime.deserialize_engine(f.read())[1].dtype == torch.bfloat16
+    a = _load_script("run").parse_arguments(["--whisper", ckpt, "--compare"])
+    assert (a.engine_dir, a.compare, a.dataset, a.batch) == ("whisper_outputs", True, "./librispeech_asr_dummy", 1)
