@@ -82,7 +82,7 @@ class WhisperEncoder(Module):
         src = self.embed_positions_weight
         key = (id(src), str(device))
         if self._pos_cache is None or self._pos_cache[0] != key:
-            t = torch.from_numpy(np.ascontiguousarray(src)) if isinstance(src, np.ndarray) else torch.as_tensor(src)
+            t = torch.from_numpy(np.array(src, copy=True)) if isinstance(src, np.ndarray) else torch.as_tensor(src)   # own, writable copy
             self._pos_cache = (key, t.detach().to(device=device, dtype=torch.float32).contiguous(), src)
         return self._pos_cache[1]
 
