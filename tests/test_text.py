@@ -90,6 +90,9 @@ def test_wer_known_answers():
     assert wer(["a b c d", "e f"], ["a x c d", "e f g"]) == pytest.approx(2 / 6)
     with pytest.raises(ValueError):
         wer(["a"], ["a", "b"])
+    with pytest.raises(ValueError, match="empty"):
+        wer(["a b", "  "], ["a b", "c"])                              # jiwer: "one or more references are empty strings"
+    assert wer("a b", "") == 1.0                                      # an empty hypothesis is fine: every word deleted
 
 
 def test_detokenizer_matches_both_reference_tokenizers():

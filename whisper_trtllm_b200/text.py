@@ -464,14 +464,20 @@ def _edit_distance(ref: Sequence[str], hyp: Sequence[str]) -> int:
 
 
 def wer(references: Union[str, Sequence[str]], hypotheses: Union[str, Sequence[str]]) -> float:
-    """Corpus word error rate: total word-level edit distance / total reference words."""
+    """Corpus word error rate as ``jiwer.wer(reference, hypothesis)`` (cal_wer.py:286): total word-level edit distance
+    (substitutions + deletions + insertions) over all sentence pairs / total reference words; words are whitespace-separated.
+    Like jiwer, a reference without any word is an error (the rate of that pair would be undefined)."""
     if isinstance(references, str):
-        references, hypotheses = [references], [hypotheses]
+        references = [references]
+    if isinstance(hypotheses, str):
+        hypotheses = [hypotheses]
     if len(references) != len(hypotheses):
         raise ValueError("references and hypotheses differ in length")
     edits = words = 0
     for r, h in zip(references, hypotheses):
         rw, hw = r.split(), h.split()
+        if not rw:
+            raise ValueError("one or more references are empty strings")
         edits += _edit_distance(rw, hw)
         words += len(rw)
     if words == 0:
