@@ -294,3 +294,23 @@ def test_mutation_fuzz_under_address_and_ub_sanitizers(tmp_path):
     assert run.returncode == 0, (run.stdout + run.stderr)[-3000:]
     counts = dict(zip(run.stdout.split()[0::2], map(int, run.stdout.split()[1::2])))
     assert sum(counts.values()) == 15000 and counts["format"] + counts["checksum"] > 10000
+
+
+# ---------------------------------------------------------------------------------------------------- known-answer files
+def test_rfc9639_example_files():
+    """The three example files of RFC 9639 Appendix D (made by reference libFLAC 1.3.3): the decoder reproduces their PCM, and the
+    files certify themselves — hashlib's MD5 of the decoded samples equals the signature stored inside each file."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "flac_rfc9639.json")) as f:
+        g = json.load(f)
+    assert len(g["files"]) == 3
+    for case in g["files"]:
+        data = bytes.fromhex(case["hex"])
+        pcm, info = audio.decode_flac_pcm(data, verify_md5=True)
+        assert (info["sample_rate"], info["channels"], info["bits_per_sample"]) == (case["sample_rate"], case["channels"], case["bits_per_sample"])
+        assert pcm.tolist() == case["pcm"], case["name"]
+        nbytes = (info["bits_per_sample"] + 7) // 8
+        raw = b"".join(int(v).to_bytes(nbytes, "little", signed=True) for v in pcm.reshape(-1))
+        assert hashlib.md5(raw).hexdigest() == info["md5"] == case["md5"]
+    first = g["files"][0]
+    assert first["pcm"] == [[25588, 10416]] and first["sample_rate"] == 44100
