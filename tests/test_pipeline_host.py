@@ -153,9 +153,12 @@ def test_text_tools_from_a_checkpoint_directory(tmp_path):
     detok, norm = pipeline.load_text_tools(str(tmp_path), cfg)
     assert detok.batch_decode([[50257, 1, 0, 50256, 50256]]) == [" hi colour"] and norm(" hi colour") == "hi color"
     assert pipeline.first_special_token_id(str(tmp_path), cfg) == 50256
-    # a multilingual checkpoint lists its special tokens in added_tokens.json, the first one is 50257 there
+    # `.en`: <|endoftext|> = 50256 sits in vocab.json, added_tokens.json starts at 50257 -> the block of specials starts at 50256
+    (tmp_path / "added_tokens.json").write_text(json.dumps({"<|startoftranscript|>": 50257, "<|notimestamps|>": 50362}))
+    assert pipeline.first_special_token_id(str(tmp_path), cfg) == 50256
+    # multilingual: <|endoftext|> = eos = 50257 is itself the first added token
     (tmp_path / "added_tokens.json").write_text(json.dumps({"<|endoftext|>": 50257, "<|startoftranscript|>": 50258}))
-    assert pipeline.first_special_token_id(str(tmp_path), cfg) == 50257
+    assert pipeline.first_special_token_id(str(tmp_path), {"eos_token_id": 50257}) == 50257
 
 
 def test_compare_report():

@@ -10,7 +10,7 @@ C-ABI of ``libwhisper_b200.so`` (include/whisper_b200.h).  There is no CPU or li
     whisper_trtllm_b200.run      runner classes + greedy_search / get_logits_processor / get_stopping_criteria (run.py)
     whisper_trtllm_b200.WhisperEngine   the native runtime (packed weights, paged KV, on-device greedy loop)
     whisper_trtllm_b200.dp       data-parallel sharding by utterance + the final token gather
-    whisper_trtllm_b200.checkpoint / .frontend / .text / .audio / .pipeline
+    whisper_trtllm_b200.checkpoint / .frontend / .processor / .text / .audio / .pipeline
                                   either side of the path: HF checkpoint directory -> weights, PCM -> log-mel on the GPU,
                                   ids -> text -> WER, and the scripts' main loops (WhisperPipeline)
 """

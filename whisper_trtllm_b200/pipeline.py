@@ -24,15 +24,17 @@ from .text import EnglishTextNormalizer, WhisperDetokenizer, wer
 
 
 def first_special_token_id(checkpoint_dir: str, config: Dict) -> int:
-    """Smallest id of the tokenizer's added (special) tokens: ``added_tokens.json`` when the checkpoint has one, else
-    ``<|endoftext|>`` = eos_token_id (50256 for the `.en` vocabularies, 50257 for the multilingual ones)."""
+    """Smallest special-token id.  Whisper's special tokens are one block at the top of the vocabulary: ``<|endoftext|>``
+    (= eos_token_id: 50256 in the `.en` vocabularies, where it is part of ``vocab.json``; 50257 in the multilingual ones) followed
+    by the tokens of ``added_tokens.json``."""
+    first = int(config["eos_token_id"])
     p = os.path.join(checkpoint_dir, "added_tokens.json")
     if os.path.exists(p):
         with open(p, encoding="utf-8") as f:
             added = json.load(f)
         if added:
-            return min(int(v) for v in added.values())
-    return int(config["eos_token_id"])
+            first = min(first, min(int(v) for v in added.values()))
+    return first
 
 
 def load_text_tools(checkpoint_dir: str, config: Dict):
