@@ -267,3 +267,72 @@ def test_reference_style_build_scripts(tmp_path, capsys):
         assert runtime.deserialize_engine(f.read())[1].dtype == torch.bfloat16
     a = _load_script("run").parse_arguments(["--whisper", ckpt, "--compare"])
     assert (a.engine_dir, a.compare, a.dataset, a.batch) == ("whisper_outputs", True, "./librispeech_asr_dummy", 1)
+
+
+def test_transcribe_cli_flow_with_a_stub_engine(tmp_path, monkeypatch, capsys):
+    """examples/transcribe.py end to end on the host: manifest / HF-style inputs -> (stub) pipeline -> printed transcripts, --out
+    JSON lines, --wer.  The stub stands where the GPU pipeline is; everything around it is the real code."""
+    import importlib.util
+    import pickle
+
+    import torch
+    spec = importlib.util.spec_from_file_location(
+        "transcribe_cli2", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "transcribe.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+
+    class FakePipeline:
+        made = []
+
+        def __init__(self, checkpoint_dir, dtype, max_batch, compact_every):
+            self.args = (checkpoint_dir, dtype, max_batch, compact_every)
+            FakePipeline.made.append(self)
+            from whisper_trtllm_b200.text import EnglishTextNormalizer
+            self.normalizer = EnglishTextNormalizer()
+
+        def transcribe_files(self, paths):
+            return torch.tensor([[len(audio.load_audio(p))] for p in paths], dtype=torch.int32)
+
+        def transcribe_sharded(self, items, load=None, features=False):
+            return torch.tensor([[int(m[0, 0])] for m in items], dtype=torch.int32) if features else \
+                torch.tensor([[len(w)] for w in items], dtype=torch.int32)
+
+        def decode(self, ids):
+            return [f"utterance of {int(r[0])} samples" for r in ids]
+
+        def wer(self, hyp, ref):
+            from whisper_trtllm_b200.text import wer
+            return wer([self.normalizer(t) for t in ref], [self.normalizer(t) for t in hyp])
+
+        def close(self):
+            self.closed = True
+
+    from whisper_trtllm_b200 import pipeline as pl
+    monkeypatch.setattr(pl, "WhisperPipeline", FakePipeline)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *_: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *_: None)
+    for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+
+    d = tmp_path / "wavs"
+    d.mkdir()
+    audio.write_wav(str(d / "a.wav"), _tone(800))
+    audio.write_wav(str(d / "b.wav"), _tone(1200))
+    (tmp_path / "m.tsv").write_text("wavs/a.wav\tutterance of 800 samples\nwavs/b.wav\tutterance of twelve hundred samples\n")
+    out = tmp_path / "out.jsonl"
+    cli.main(["--whisper", "ckpt", "--audio", str(tmp_path / "m.tsv"), "--wer", "--out", str(out), "--batch", "4", "--dtype", "float32"])
+    printed = capsys.readouterr().out.splitlines()
+    assert printed[:2] == ["a.wav\tutterance of 800 samples", "b.wav\tutterance of 1200 samples"]
+    assert printed[2] == "WER: 0.00 %"                       # "twelve hundred" and "1200" normalise to the same words
+    rows = [json.loads(ln) for ln in out.read_text().splitlines()]
+    assert rows[1] == {"audio": str(d / "b.wav"), "text": "utterance of 1200 samples", "reference": "utterance of twelve hundred samples"}
+    assert FakePipeline.made[-1].args == ("ckpt", "float32", 4, 32) and FakePipeline.made[-1].closed
+    # a directory without references: --wer is refused before any work is done
+    with pytest.raises(SystemExit):
+        cli.main(["--whisper", "ckpt", "--audio", str(d), "--wer"])
+    # cal_wer.py's librispeech.cache goes through the feature path
+    with open(tmp_path / "librispeech.cache", "wb") as f:
+        pickle.dump([(torch.full((80, 3000), 5.0), "utterance of five samples"), (torch.full((80, 3000), 7.0), "nothing alike")], f)
+    cli.main(["--whisper", "ckpt", "--audio", str(tmp_path / "librispeech.cache"), "--wer"])
+    printed = capsys.readouterr().out.splitlines()
+    assert printed[0] == "librispeech.cache[0]\tutterance of 5 samples" and printed[-1] == "WER: 66.67 %"
