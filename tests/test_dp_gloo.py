@@ -76,3 +76,48 @@ def test_gather_without_process_group_is_identity_padding():
     ids = torch.arange(6, dtype=torch.int32).reshape(2, 3)
     out = dp.gather_tokens(ids, 2, 5, 9)
     assert out.tolist() == [[0, 1, 2, 9, 9], [3, 4, 5, 9, 9]]
+
+
+# ---------------------------------------------------------------------------------------------------- the pipeline's sharding
+def _pipeline_worker(rank, world, port, n, out_dir):
+    """WhisperPipeline.transcribe_sharded under a process group, the engine replaced by a stub: each rank loads and transcribes
+    only its shard (with the prefetching loader), every rank ends with the ids of ALL utterances in input order."""
+    import types
+
+    import numpy as np
+    from whisper_trtllm_b200 import pipeline
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pipe = object.__new__(pipeline.WhisperPipeline)
+        pipe.config = {"max_length": 7, "pad_token_id": 50256}
+        pipe.max_batch = 2
+        pipe.engine = types.SimpleNamespace(device=torch.device("cpu"))
+        loaded = []
+
+        def load(item):
+            loaded.append(item)
+            return np.full(3, item, dtype=np.float32)
+
+        pipe.transcribe_waveforms = lambda waves: torch.tensor([[int(w[0]), 1, 2, 50256, 50256, 50256, 50256] for w in waves],
+                                                               dtype=torch.int32).reshape(len(waves), 7)
+        got = pipe.transcribe_sharded(list(range(100, 100 + n)), load=load)
+        b, e = dp.shard_range(n, world, rank)
+        assert sorted(loaded) == list(range(100 + b, 100 + e)), (rank, loaded)       # nothing outside the shard was read
+        feats = torch.arange(n, dtype=torch.float32).reshape(n, 1, 1).expand(n, 80, 3000)
+        pipe.transcribe_features = lambda m: torch.stack([torch.full((7,), int(x[0, 0]), dtype=torch.int32) for x in m]) \
+            if len(m) else torch.empty(0, 7, dtype=torch.int32)
+        got_f = pipe.transcribe_sharded(feats, features=True)
+        torch.save((got, got_f), os.path.join(out_dir, f"pipe_rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [5, 1])
+def test_pipeline_sharding_world_2(n, tmp_path):
+    world = 2
+    mp.spawn(_pipeline_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        got, got_f = torch.load(os.path.join(str(tmp_path), f"pipe_rank{r}.pt"))
+        assert got.shape == (n, 7) and got[:, 0].tolist() == list(range(100, 100 + n)) and got[:, 3:].eq(50256).all()
+        assert got_f.shape == (n, 7) and got_f[:, 0].tolist() == list(range(n))
