@@ -71,6 +71,11 @@ WB_API int wb_set_self_attention_warp_kernel(int variant);
  * CUDA-core dot products (measured 4-13 % slower, kept for A/B); 0 = the multi-kernel step for every batch size (A/B, parity tests).
  * Sessions decoded concurrently by wb_decode_run_multi never use it (a cooperative grid needs every SM to itself). */
 WB_API int wb_set_small_batch_path(int mode);
+/* decode steps of > 16 utterances (bf16): the GEMM / LayerNorm chains between the attention kernels run as persistent
+ * cooperative tcgen05 kernels with grid barriers between their phases (csrc/step_chain.cu; 4 launches per decoder layer
+ * instead of 11).  1 (default) = on, 0 = one kernel per GEMM / LayerNorm (A/B, parity tests).  Same rounding points either
+ * way.  Replaces nothing in the reference (its decode step is one TensorRT engine execution, run.py:93-148). */
+WB_API int wb_set_decode_chain_path(int enabled);
 /* measurement hook of the whole-step kernel: device buffer of 8 * (8 * decoder_layers + 2) int64; CTA 0 stores its SM clock
  * at 8 points of every phase: [0] start, [1] activations staged, [2] block barrier passed, [3] first weight tile requested,
  * [4] phase done, [5] arrived at the grid barrier + next phase prefetched, [8] = next [0] grid barrier passed
@@ -180,6 +185,17 @@ WB_API int wb_encoder_attention(const void* qkv, void* out, int dtype, int batch
  * model.py:240-304): q [B, H*64] pre-scaled, n_keys <= T */
 WB_API int wb_decode_attention(const void* q, const void* k, const void* v, void* out, int dtype, int batch, int heads,
                         int n_keys, int64_t kv_batch_stride, int64_t kv_head_stride, wb_stream stream);
+/* Cached decoder SELF-attention of one greedy step on its own (WhisperDecoderAttention, self / with-cache mode:
+ * models/whisper/model.py:273-281 slice + concat, modeling_whisper.py:490-497 torch.cat): the new key / value rows are appended
+ * IN PLACE at slot cur_len - 1 of the paged cache (pages of 64 tokens x all heads, [page][H][64][64]; row b owns
+ * page_table[b * pages_per_seq ..]) and every (utterance, head) attends over its cur_len keys.  qkv: fused rows
+ * [batch, 3 * heads * 64] (q pre-scaled | k | v), row_stride elements apart; out [batch, heads * 64].
+ * state: device pointer to 8 int32 {cur_len, active, ...} (the loop state of the greedy session; active == 0 -> no-op);
+ * row_active: optional [batch] int32, rows with 0 are skipped.  Same dispatch as the session's decode step (one warp per
+ * item when batch * heads exceeds two items per SM, one CTA per item below). */
+WB_API int wb_paged_self_attention(const void* qkv, int64_t row_stride, void* out, void* k_pages, void* v_pages,
+                                   const int32_t* page_table, int pages_per_seq, int dtype, int batch, int heads,
+                                   const int32_t* state, const int32_t* row_active, wb_stream stream);
 /* masked argmax per row: logits fp32 [B, V]; mask (optional) uint8 [V], a token is skipped if mask & bits */
 WB_API int wb_argmax(const float* logits, int64_t ld, int batch, int vocab, const uint8_t* mask, int bits, int32_t* out,
               wb_stream stream);

@@ -33,6 +33,10 @@ CASES = {
     "base_b16": ("base.en", 16, 0, 6, 448, [0, 1, 2, 9, 200, 446]),  # BASELINE.json configs[1]
     "small": ("small.en", 2, 0, 1234, 33, [0, 1, 2, 9, 31]),
     "medium": ("medium.en", 2, 0, 1234, 25, [0, 1, 2, 9, 23]),
+    # the BENCHMARKED large-batch regime: B * H > 2 * SMs (warp-per-item paged self-attention, multi-kernel /
+    # fused-chain decode step at d = 1024) and BASELINE.json configs[2] (small.en, batch 64)
+    "medium_b24": ("medium.en", 24, 0, 4321, 25, [0, 1, 2, 9, 23]),
+    "small_b64": ("small.en", 64, 0, 99, 17, [0, 1, 2, 9, 15]),
 }
 ENC_T_STRIDE, ENC_D_STRIDE, LOGIT_STRIDE = 97, 7, 53
 

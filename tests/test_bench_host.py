@@ -25,10 +25,27 @@ def test_job_ceiling_reproduces_the_survey_figures():
 
 
 def test_workload_config_names_the_workload():
-    class A:
-        size, dtype, batch, max_length = "medium.en", "bf16", 256, 448
+    class A:   # --batch 256: weak scaling, 256 utterances per GPU
+        size, dtype, batch, global_batch, max_length = "medium.en", "bf16", 256, 256, 448
     c = bench.workload_config(A, 8)
     assert c["global_batch"] == 2048 and c["parallelism"] == "dp8" and "medium.en" in c["workload"] and "model" not in c
+    assert bench.batch_plan(A, 8, 3) == (256, 256, 2048, "weak")
+
+    class S:   # default: BASELINE.json configs[3], a global batch of 256 sharded over the ranks
+        size, dtype, batch, global_batch, max_length = "medium.en", "bf16", 0, 256, 448
+    for world, per in ((1, 256), (2, 128), (4, 64), (8, 32)):
+        c = bench.workload_config(S, world)
+        assert c["global_batch"] == 256 and c["batch_per_gpu"] == per and c["parallelism"] == f"dp{world}"
+        assert [bench.batch_plan(S, world, r)[0] for r in range(world)] == [per] * world
+        assert bench.batch_plan(S, world, 0)[3] == "strong"
+    S.global_batch = 10                                  # ragged shards: earlier ranks take the remainder
+    assert [bench.batch_plan(S, 4, r)[0] for r in range(4)] == [3, 3, 2, 2] and bench.batch_plan(S, 4, 0)[1] == 3
+
+
+def test_cpu_sample_shrinks_with_the_number_of_passes():
+    assert bench.pick_cpu_sample(6) == (16, 128)         # default bench run: the largest sample
+    assert bench.pick_cpu_sample(25) in ((8, 64), (4, 128), (8, 128))
+    assert bench.pick_cpu_sample(1000) == (4, 64)
 
 
 def test_reference_arm_prints_one_contract_line():
@@ -41,4 +58,8 @@ def test_reference_arm_prints_one_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT and d["higher_is_better"] is True
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # ms_per_step is what actually RAN (the measured sample), never an extrapolation; the extrapolated job time is beside it
+    cb = d["cpu_baseline"]
+    assert abs(cb["measured_ms_per_sample"] - d["ms_per_step"]) < 1e-6 and cb["extrapolated_ms_per_sample"] >= cb["measured_ms_per_sample"]
+    assert d["scaling"] == "strong" and d["config"]["global_batch"] == 256
     assert d["e2e"] == {"value": d["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -234,3 +234,95 @@ def test_decode_attention_bulk_ring_kernel(B, H, T, n):
         _abi.call("wb_set_decode_attention_backend", 0)
     assert G.rel_err(out, ref) < 6e-3
     assert G.rel_err(out, base) < 6e-3
+
+
+def _paged_self_attention_case(B, H, n, dtype, seed, finished=()):
+    """Random fused qkv rows + a paged cache holding n - 1 tokens per row behind a SHUFFLED page table; the op appends row n - 1
+    in place and attends over n keys.  -> (out, fp32 torch reference, pages after, expected appended rows)."""
+    from whisper_trtllm_b200 import _abi
+    g = _gen(seed)
+    d, pps = H * 64, 7
+    qkv = (torch.randn(B, 3 * d, generator=g) * 0.5).to(DEV).to(dtype)
+    num_pages = B * pps
+    k_pages = torch.randn(num_pages, H, 64, 64, generator=g).to(DEV).to(dtype)
+    v_pages = torch.randn(num_pages, H, 64, 64, generator=g).to(DEV).to(dtype)
+    table = torch.randperm(num_pages, generator=g).to(torch.int32).view(B, pps).to(DEV)
+    state = torch.zeros(8, dtype=torch.int32, device=DEV)
+    state[0], state[1] = n, 1
+    row_active = torch.ones(B, dtype=torch.int32, device=DEV)
+    for r in finished:
+        row_active[r] = 0
+    out = torch.full((B, d), float("nan"), device=DEV).to(dtype)
+    k_before, v_before = k_pages.clone(), v_pages.clone()
+    _abi.call("wb_paged_self_attention", G.ptr(qkv), 3 * d, G.ptr(out), G.ptr(k_pages), G.ptr(v_pages), G.ptr(table), pps,
+              G.DT[dtype], B, H, G.ptr(state), G.ptr(row_active), G.stream_handle())
+    torch.cuda.synchronize()
+    # dense reference: gather the pages, put the new row at slot n - 1
+    def dense(pages):
+        x = pages[table.long()]                                     # [B, pps, H, 64, 64]
+        return x.permute(0, 2, 1, 3, 4).reshape(B, H, pps * 64, 64).float()
+    K, V = dense(k_before), dense(v_before)
+    q = qkv[:, :d].float().view(B, H, 64)
+    K[:, :, n - 1] = qkv[:, d:2 * d].float().view(B, H, 64)
+    V[:, :, n - 1] = qkv[:, 2 * d:].float().view(B, H, 64)
+    w = torch.softmax(torch.einsum("bhd,bhtd->bht", q, K[:, :, :n]), dim=-1)
+    ref = torch.einsum("bht,bhtd->bhd", w, V[:, :, :n]).reshape(B, d)
+    return out, ref, (k_pages, v_pages, k_before, v_before, table, qkv)
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 128, 224, 447])
+@pytest.mark.parametrize("B,H", [(32, 16), (64, 16), (40, 12)])
+def test_paged_self_attention_warp_per_item_bf16(B, H, n):
+    """The kernel the headline configuration launches for the cached self-attention: self_attn_warp_kernel<bf16, 4> (one warp per
+    (utterance, head) item; taken when B * H exceeds two items per SM) against fp32 torch on the same bf16 inputs: lengths at
+    and around the page boundaries, 1 key, the maximum; the appended row lands in its page and nothing else is touched."""
+    import ctypes
+    from whisper_trtllm_b200 import _abi
+    sms = ctypes.c_int()
+    _abi.call("wb_device_info", ctypes.byref(sms), ctypes.byref(ctypes.c_int()), ctypes.byref(ctypes.c_int()))
+    assert B * H > 2 * sms.value, "this case must take the warp-per-item kernel"
+    out, ref, (kp, vp, kb, vb, table, qkv) = _paged_self_attention_case(B, H, n, torch.bfloat16, 1000 + n + B)
+    assert torch.isfinite(out.float()).all()
+    assert G.rel_err(out, ref) < 8e-3, (B, H, n)
+    d = H * 64
+    page = table[:, (n - 1) // 64].long()
+    slot = (n - 1) % 64
+    assert torch.equal(kp[page, :, slot], qkv[:, d:2 * d].view(B, H, 64))
+    assert torch.equal(vp[page, :, slot], qkv[:, 2 * d:].view(B, H, 64))
+    kb[page, :, slot] = kp[page, :, slot]
+    vb[page, :, slot] = vp[page, :, slot]
+    assert torch.equal(kp, kb) and torch.equal(vp, vb)
+
+
+def test_paged_self_attention_skips_finished_rows_and_matches_the_cta_kernel():
+    """Rows whose utterance has emitted EOS are skipped (output untouched, nothing appended); the warp-per-item kernel and the
+    CTA-per-item kernel (small item counts) agree on the rows they both compute; fp32 instance within 1e-5."""
+    out, ref, (kp, vp, kb, vb, table, qkv) = _paged_self_attention_case(48, 16, 130, torch.bfloat16, 5, finished=(0, 17, 47))
+    live = [r for r in range(48) if r not in (0, 17, 47)]
+    assert torch.isnan(out[[0, 17, 47]].float()).all()
+    assert G.rel_err(out[live], ref[live]) < 8e-3
+    for r in (0, 17, 47):
+        pg = table[r].long()
+        assert torch.equal(kp[pg], kb[pg]) and torch.equal(vp[pg], vb[pg])
+    small, ref_s, _ = _paged_self_attention_case(4, 16, 130, torch.bfloat16, 6)        # 64 items: CTA per item
+    assert G.rel_err(small, ref_s) < 8e-3
+    o32, r32, _ = _paged_self_attention_case(32, 16, 200, torch.float32, 7)            # fp32 warp kernel
+    assert G.rel_err(o32, r32) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,n", [(256, 16, 1500), (64, 16, 1500), (24, 16, 1500), (40, 12, 1500), (32, 16, 777)])
+def test_cross_attention_large_batch_kernel_bf16(B, H, n):
+    """decode_attn_kernel<bf16, false, 128, 8>: the cross-attention kernel of the headline configuration (persistent, 4 CTAs per
+    SM, taken when B * H exceeds two items per SM) asserted DIRECTLY against fp32 torch on the same bf16 K/V."""
+    g = _gen(B + H + n)
+    q = (torch.randn(B, H * 64, generator=g) * 0.3).to(DEV).to(torch.bfloat16)
+    k = torch.randn(B, H, 1500, 64, generator=g).to(DEV).to(torch.bfloat16)
+    v = torch.randn(B, H, 1500, 64, generator=g).to(DEV).to(torch.bfloat16)
+    out = G.decode_attention(q, k, v, n)
+    torch.cuda.synchronize()
+    ref = torch.empty(B, H * 64, device=DEV)
+    for b0 in range(0, B, 32):     # chunked: the fp32 copy of K/V of 256 utterances would not be small
+        kk, vv = k[b0:b0 + 32, :, :n].float(), v[b0:b0 + 32, :, :n].float()
+        w = torch.softmax(torch.einsum("bhd,bhtd->bht", q[b0:b0 + 32].float().view(-1, H, 64), kk), dim=-1)
+        ref[b0:b0 + 32] = torch.einsum("bht,bhtd->bhd", w, vv).reshape(-1, H * 64)
+    assert G.rel_err(out, ref) < 6e-3

@@ -23,10 +23,13 @@ def main():
     p.add_argument("--lengths", default="1,64,128,256,436")   # the 10 timed / warm steps must fit below max_length 448
     p.add_argument("--steps", type=int, default=8)
     p.add_argument("--small-path", type=int, default=-1, help="wb_set_small_batch_path: 1 = whole-step kernel for B <= 16 (library default), 2 = same with mma.sync attention, 0 = multi-kernel step")
+    p.add_argument("--chain", type=int, default=-1, help="wb_set_decode_chain_path: 1 = fused GEMM / LayerNorm chains for B > 16 (library default), 0 = one kernel per GEMM / LayerNorm")
     a = p.parse_args()
     from whisper_trtllm_b200 import WhisperEngine, _abi, synthetic as synth
     if a.small_path >= 0:
         _abi.call("wb_set_small_batch_path", a.small_path)
+    if a.chain >= 0:
+        _abi.call("wb_set_decode_chain_path", a.chain)
 
     dev = torch.device("cuda", 0)
     cfg = synth.make_config(a.size)

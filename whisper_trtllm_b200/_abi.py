@@ -40,6 +40,7 @@ SIGNATURES = {
     "wb_set_gemm_block_n": (c_int, [c_int]),
     "wb_set_lean_decode_gemm": (c_int, [c_int]),
     "wb_set_small_batch_path": (c_int, [c_int]),
+    "wb_set_decode_chain_path": (c_int, [c_int]),
     "wb_set_step_trace": (c_int, [c_void_p]),
     "wb_set_self_attention_warp_kernel": (c_int, [c_int]),
     "wb_set_decode_attention_backend": (c_int, [c_int]),
@@ -79,6 +80,8 @@ SIGNATURES = {
     "wb_encoder_stem": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "wb_encoder_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "wb_decode_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int64, c_void_p]),
+    "wb_paged_self_attention": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                        c_void_p, c_void_p]),
     "wb_argmax": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "wb_embed": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "wb_kv_append": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p]),

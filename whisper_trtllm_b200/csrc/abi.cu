@@ -37,6 +37,7 @@ void set_cuda_graphs(bool on);
 void set_decode_attention_backend(int b);
 void set_lean_decode_gemm(bool on);
 void set_small_batch_path(bool on);
+void set_chain_path(bool on);
 void set_mega_attention_tc(bool on);
 void set_step_trace(long long* dev_ptr);
 void set_self_attention_variant(int v);
@@ -105,6 +106,11 @@ int wb_set_small_batch_path(int mode) {
         wb::set_small_batch_path(mode != 0);
         wb::set_mega_attention_tc(mode == 2);
     });
+}
+
+int wb_set_decode_chain_path(int enabled) {
+    wb::set_chain_path(enabled != 0);
+    return WB_OK;
 }
 
 int wb_set_step_trace(void* device_buffer) {
@@ -382,6 +388,23 @@ int wb_decode_attention(const void* q, const void* k, const void* v, void* out, 
         a.dtype = dtype; a.q = q; a.q_stride = (long long)heads * 64; a.out = out; a.out_stride = (long long)heads * 64;
         a.B = batch; a.H = heads; a.k = k; a.v = v; a.kv_bstride = kv_batch_stride; a.kv_hstride = kv_head_stride;
         a.n_keys = n_keys;
+        wb::decode_attention(a, S(stream));
+    });
+}
+
+int wb_paged_self_attention(const void* qkv, int64_t row_stride, void* out, void* k_pages, void* v_pages, const int32_t* page_table,
+                            int pages_per_seq, int dtype, int batch, int heads, const int32_t* state, const int32_t* row_active,
+                            wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(qkv); WB_NOT_NULL(out); WB_NOT_NULL(k_pages); WB_NOT_NULL(v_pages); WB_NOT_NULL(page_table); WB_NOT_NULL(state);
+        WB_REQUIRE(dtype == wb::F32 || dtype == wb::BF16, "dtype must be 0 (fp32) or 1 (bf16)");
+        const size_t es = wb::dtype_size(dtype);
+        const long long d = (long long)heads * 64;
+        wb::DecAttnArgs a;
+        a.dtype = dtype; a.q = qkv; a.q_stride = row_stride; a.out = out; a.out_stride = d; a.B = batch; a.H = heads;
+        a.state = reinterpret_cast<const wb::StepState*>(state); a.row_active = row_active;
+        a.k_new = (const uint8_t*)qkv + d * es; a.v_new = (const uint8_t*)qkv + 2 * d * es; a.new_stride = row_stride;
+        a.k_pages = k_pages; a.v_pages = v_pages; a.page_table = page_table; a.pages_per_seq = pages_per_seq; a.page_tokens = 64;
         wb::decode_attention(a, S(stream));
     });
 }

@@ -269,6 +269,8 @@ size_t layout(Buffers& b, const Model* m, int max_batch, int enc_chunk, void* ba
     c.take(b.mega_sync, mega_sync_bytes(max_batch, g.n_heads));
     c.take(b.mega_table, mega_table_bytes(g.dec_layers));
     c.take(b.result_tokens, B * g.max_tgt * 4);
+    c.take(b.chain_table, chain_table_bytes(g.dec_layers));
+    c.take(b.chain_sync, chain_sync_bytes());
     return c.off + 1024;
 }
 }  // namespace
@@ -298,6 +300,7 @@ Session::Session(Model* model, int mb, int ec, void* workspace, size_t workspace
     WB_CHECK_CUDA(cudaMemset(state, 0, sizeof(StepState)));
     WB_CHECK_CUDA(cudaMemset(mega_sync, 0, mega_sync_bytes(mb, model->cfg.n_heads)));
     build_mega_table();
+    init_chain();
     WB_CHECK_CUDA(cudaMallocHost(&host_state, sizeof(StepState)));
     std::memset(host_state, 0, sizeof(StepState));
     WB_CHECK_CUDA(cudaEventCreateWithFlags(&check_event, cudaEventDisableTiming));
@@ -348,14 +351,6 @@ void Session::prof_read(double* total_ms, long long* launches) {
     if (launches) *launches = (long long)(prof_used / 2);
     prof_used = 0;
 }
-
-namespace {
-struct ProfScope {
-    Session* s; int cls; cudaStream_t st;
-    ProfScope(Session* s_, int c, cudaStream_t t) : s(s_), cls(c), st(t) { s->prof_begin(cls, st); }
-    ~ProfScope() noexcept(false) { s->prof_end(cls, st); }
-};
-}  // namespace
 
 size_t Session::cross_layer_elems() const { return (size_t)2 * max_batch * m->cfg.n_heads * m->cfg.n_ctx * 64; }
 size_t Session::self_layer_elems() const { return (size_t)num_pages * m->cfg.n_heads * PAGE_TOKENS * 64; }
@@ -486,8 +481,10 @@ void Session::decode_begin(int B, cudaStream_t st) {
     steps_enqueued = 0;
     greedy_init(tokens, g.max_tgt, unfinished, state, B, g.sot, g.pad, g.max_tgt, st);
     // the whole-step kernel starts from the residual stream: embedding of the start token here, of every later token by the
-    // greedy kernel of the step that chose it
-    if (use_mega()) decoder_embed(tokens, g.max_tgt, state, m->emb, m->dec_pos, m->dtype, dx, B, g.d_model, st);
+    // greedy kernel of the step that chose it.  ALWAYS written (one tiny kernel): which step path runs is only known when the
+    // loop starts (decode_run_multi sets `exclusive`), so the decision must not depend on the previous run's state
+    decoder_embed(tokens, g.max_tgt, state, m->emb, m->dec_pos, m->dtype, dx, B, g.d_model, st);
+    dx_embedded = true;
 }
 
 // small batches (B <= 16, bf16) run the whole decoder for one token in ONE persistent cooperative kernel (step_mega.cu); the
@@ -500,6 +497,8 @@ void set_small_batch_path(bool on) { whole_step_kernel_enabled() = on; }
 
 // (not when several sessions decode concurrently on their own streams: a cooperative grid needs every SM to itself)
 bool Session::use_mega() const { return whole_step_kernel_enabled() && exclusive && get_gemm_backend() == 0 && mega_supported(); }
+bool chain_path_enabled();   // step_chain.cu
+bool Session::use_chain() const { return chain_path_enabled() && exclusive && get_gemm_backend() == 0 && chain_supported() && !use_mega(); }
 
 // ids of the current decode rows -> result buffer, original row order
 void Session::publish_results(cudaStream_t st) {
@@ -560,7 +559,8 @@ int Session::decode_compact(cudaStream_t st) {
     WB_CHECK_CUDA(cudaMemcpyAsync(unfinished, ones.data(), (size_t)batch * 4, cudaMemcpyHostToDevice, st));
     WB_CHECK_CUDA(cudaStreamSynchronize(st));                                 // the host vectors above go out of scope
     // the whole-step kernel starts from the residual stream: re-embed the last token of the rows that moved
-    if (use_mega()) decoder_embed(tokens, g.max_tgt, state, m->emb, m->dec_pos, m->dtype, dx, batch, g.d_model, st);
+    decoder_embed(tokens, g.max_tgt, state, m->emb, m->dec_pos, m->dtype, dx, batch, g.d_model, st);
+    dx_embedded = true;
     return batch;
 }
 
@@ -568,8 +568,11 @@ void Session::decode_step(cudaStream_t st) {
     WB_REQUIRE(batch > 0, "decode_begin was not called");
     const ModelConfig& g = m->cfg;
     const int d = g.d_model, dt = m->dtype, B = batch;
-    const bool mega = use_mega();
-    if (mega) decode_step_mega(st);
+    const int mode = step_mode();
+    const bool mega = mode != 0;    // the step starts from the residual stream and its greedy kernel embeds the chosen token
+    prepare_step(st);
+    if (mode == 1) decode_step_mega(st);
+    else if (mode == 2) decode_step_chain(st);
     else decode_step_large(st);
     // logits -> processors -> argmax -> EOS / length bookkeeping, common to both paths
     if (logits_dump != nullptr && steps_enqueued < logits_dump_steps)
@@ -587,6 +590,7 @@ void Session::decode_step(cudaStream_t st) {
         ProfScope ps(this, PROF_GREEDY, st);
         greedy_step(a, st);
     }
+    dx_embedded = mega;   // the greedy kernel of a whole-step launch wrote the next token's embedding
     ++steps_enqueued;
 }
 
@@ -706,27 +710,53 @@ void Session::build_step_graph(cudaStream_t st) {
     WB_CHECK_CUDA(e);
     step_graph_batch = batch;
     step_graph_generation = m->generation_version;
-    step_graph_mega = use_mega();
+    step_graph_mode = step_mode();
 }
 
 // one decode step on the session's loop stream: CUDA-graph replay when possible, eager launches otherwise
+// Host-side work of a step that must not end up inside a graph capture: the fused-chain phase table of the current batch,
+// and the fed token's embedding in dx when a multi-kernel step (which embeds for itself and then overwrites dx with its
+// residual stream) has run since it was last written there.
+void Session::prepare_step(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    WB_CHECK_CUDA(cudaStreamIsCapturing(st, &cs));
+    if (cs != cudaStreamCaptureStatusNone) return;    // enqueue_step prepared the step before it began the capture
+    const int mode = step_mode();
+    if (mode == 2 && chain_batch != batch) {
+        WB_CHECK_CUDA(cudaStreamSynchronize(st));     // queued steps may still read the table
+        build_chain_table();
+    }
+    if (mode != 0 && !dx_embedded) {
+        decoder_embed(tokens, m->cfg.max_tgt, state, m->emb, m->dec_pos, m->dtype, dx, batch, m->cfg.d_model, st);
+        dx_embedded = true;
+    }
+}
+
 void Session::enqueue_step() {
     cudaStream_t st = loop_stream;
+    prepare_step(st);
     if (graph_ok()) {
         if (step_graph == nullptr || step_graph_batch != batch || step_graph_generation != m->generation_version ||
-            step_graph_mega != use_mega()) {
+            step_graph_mode != step_mode()) {
             try {
                 build_step_graph(st);
-            } catch (const Error&) {
+            } catch (const Error& e) {
                 graphs_enabled() = false;   // capture not possible here: stay on eager launches
                 cudaGetLastError();         // do not leave the (non-sticky) capture error for the next caller to trip over
+                static bool warned = false;
+                if (!warned) {              // a silent perf fallback is a bug report waiting to happen: say it once
+                    warned = true;
+                    std::fprintf(stderr, "[whisper_b200] CUDA graph capture of the decode step failed (%s): decode steps are "
+                                         "launched kernel by kernel from now on (slower, same results)\n", e.what());
+                }
             }
         }
     }
     if (graph_ok() && step_graph != nullptr && step_graph_batch == batch && step_graph_generation == m->generation_version &&
-        step_graph_mega == use_mega()) {
+        step_graph_mode == step_mode()) {
         WB_CHECK_CUDA(cudaGraphLaunch(step_graph, st));
         launch_counter().fetch_add(step_graph_launches, std::memory_order_relaxed);
+        dx_embedded = step_graph_mode != 0;
         ++steps_enqueued;
     } else {
         decode_step(st);

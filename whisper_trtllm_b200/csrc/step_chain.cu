@@ -1,0 +1,571 @@
+// Fused decode-step chains for large batches (17 <= B <= 512 utterances per GPU, bf16).
+//
+// Between two attention kernels the decode step is a chain of skinny GEMMs (M = B rows) and LayerNorms:
+//     out-proj -> (+res) LN2 -> cross-q            |  cross-out -> (+res) LN3 -> fc1 (GELU) -> fc2 -> (+res) LN1' -> qkv'
+// As separate launches (runtime.cu decode_step_large: 11 kernels per layer) every link costs a kernel boundary plus the
+// prologue of a tcgen05 kernel (barrier init, TMEM allocation, descriptor fetch, pipeline fill): 8-14 us per link for 0.3 us
+// of weight bytes (ncu, profiles/r01_ncu_decode_layer_v15.md) - 1.55 ms of a 7.9 ms step at B = 256 and 1.6 ms of a 2.5 ms
+// step at B = 32 (the per-rank batch of the 8-GPU strong-scaling configuration).
+//
+// Here a whole chain is ONE persistent cooperative kernel (one CTA per SM, warp-specialised like gemm_tc.cu):
+//   warp 0      TMA producer: weight tiles of the NEXT phase are requested BEFORE the grid barrier (they do not depend on it),
+//               activation tiles right after it
+//   warp 1      tcgen05.mma issuer (UMMA 128 x BN x 16, BN chosen per phase on the host, fp32 accumulators in TMEM, two
+//               accumulator buffers so that the epilogue of one tile overlaps the main loop of the next)
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue (tcgen05.ld -> transpose through swizzled smem -> bias / erf-GELU -> 128-byte row stores), and the
+//               workers of the LayerNorm phases: x += bias + split-K slabs (fixed order, deterministic), LayerNorm, bf16 out
+// The phases of a chain are separated by a grid barrier (release-add / acquire-poll on one L2 word) instead of a kernel
+// boundary; the TMEM allocation, the mbarriers and the smem ring live across phases.  The kernel is an interpreter over a
+// table of phase descriptors (tensor maps included) built once per (session, batch) on the host.
+// Semantics and rounding points are exactly those of decode_step_large (fp32 residual stream, LayerNorm eps 1e-5 in fp32,
+// bf16 activations into every Linear, split-K partials summed in slab order): models/whisper/model.py:321-369,
+// layers/normalization.py:6-30, modeling_whisper.py:710-751.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "wb_runtime.h"
+#include "wb_ptx.cuh"
+
+namespace wb {
+
+CUtensorMap make_tmap_bf16_2d(const void* ptr, long long ld_elems, int rows, int cols, int box_rows);   // gemm_tc.cu
+
+namespace {
+constexpr int CH_BM = 128, CH_BK = 64, CH_MAX_BN = 128;
+constexpr int CH_STAGES = 6;
+constexpr uint32_t CH_A_BYTES = CH_BM * CH_BK * 2;                 // 16 KB
+constexpr uint32_t CH_STAGE_BYTES = CH_A_BYTES + CH_MAX_BN * CH_BK * 2;   // 32 KB
+constexpr int CH_EPI_WARPS = 8;
+constexpr int CH_THREADS = (4 + CH_EPI_WARPS) * 32;                // 384
+constexpr uint32_t CH_STAGING_BYTES = CH_EPI_WARPS * 32 * 32 * 4;  // one 32x32 fp32 transpose tile per epilogue warp
+constexpr uint32_t CH_TMEM_COLS = 2 * CH_MAX_BN;                   // two accumulator buffers
+constexpr uint32_t CH_SMEM_BYTES = CH_STAGES * CH_STAGE_BYTES + CH_STAGING_BYTES + 512 /*barriers, LN scratch*/ + 1024 /*alignment*/;
+constexpr int CH_MAX_PARTS = MAX_K_SPLITS;
+
+enum { CH_GEMM = 0, CH_LN = 1 };
+enum { CH_EPI_PARTIAL = 0, CH_EPI_BF16 = 1, CH_EPI_GELU_BF16 = 2 };
+
+// One phase of a chain.  GEMM: out = epi(A[M, K] W[N, K]^T) on 128 x bn tiles, k_splits slabs; LN: the consumer side of a
+// split-K GEMM fused with the LayerNorm in front of the next Linear.
+struct alignas(128) ChainPhase {
+    CUtensorMap tmA;            // activations [M, K] bf16, box {64, 128}
+    CUtensorMap tmW;            // weights [N, K] bf16, box {64, bn}
+    int kind;
+    int bn, K, N, n_tiles_n, k_splits, epi;
+    int n_parts;                // LN: slabs to add to x (0: plain LayerNorm of x)
+    long long split_stride;     // GEMM (partial epilogue) / LN: floats between consecutive slabs
+    long long ldo;              // GEMM: elements between output rows
+    const float* bias;          // GEMM: epilogue bias (bf16 epilogues); LN: bias of the split-K GEMM that produced the slabs
+    void* out;                  // GEMM: fp32 slabs or bf16 rows; LN: bf16 normalised rows [M, d]
+    const float* parts;         // LN: slabs
+    const float* gamma; const float* beta;
+    float* x;                   // LN: fp32 residual stream [M, d], updated in place
+    int pad[8];
+};
+static_assert(sizeof(ChainPhase) == 384, "ChainPhase layout");
+
+struct ChainParams {
+    const ChainPhase* table;
+    int ph_begin, ph_end;
+    int M, d;
+    float eps;
+    const StepState* state;
+    unsigned* sync;             // [0] grid-barrier counter: zero between launches
+};
+
+__device__ __forceinline__ unsigned ch_ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ch_red_release(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// generic-proxy writes (st.global by other CTAs) -> async-proxy reads (TMA) of the same global addresses
+__device__ __forceinline__ void ch_fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ float4 ch_ld_cg_f4(const float* p) {   // written by other CTAs of this kernel: read at L2
+    float4 r;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void ch_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void ch_named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// every CTA has arrived `target` times: all writes of the phases before are visible.  A lost CTA traps instead of hanging.
+__device__ __forceinline__ void ch_grid_poll(const unsigned* counter, unsigned target) {
+    if (ch_ld_acquire(counter) >= target) return;
+    const long long t0 = clock64();
+    while (ch_ld_acquire(counter) < target) {
+        if (clock64() - t0 > 4000000000ll) {
+            printf("wb: chain grid barrier timeout (block %d thread %d target %u)\n", blockIdx.x, threadIdx.x, target);
+            __trap();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const ChainParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    if (p.state->active == 0) return;   // the loop has stopped: grid-uniform, nobody touches the barrier
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1024-byte aligned bases
+    float* staging = reinterpret_cast<float*>(smem + CH_STAGES * CH_STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + CH_STAGES * CH_STAGE_BYTES + CH_STAGING_BYTES);
+    uint64_t* empty_bar = full_bar + CH_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + CH_STAGES;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    float* ln_red = reinterpret_cast<float*>(tmem_ptr_smem + 4);        // [2 groups][2 reductions][4 warps]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_mt = (p.M + CH_BM - 1) / CH_BM;
+    const unsigned grid = gridDim.x;
+    unsigned* const bar = p.sync;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < CH_STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tmem_full_bar[s], 1);
+            ptx::mbar_init(&tmem_empty_bar[s], CH_EPI_WARPS);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<CH_TMEM_COLS>(tmem_ptr_smem);
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    ptx::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int ph = p.ph_begin; ph < p.ph_end; ++ph) {
+            const ChainPhase* D = p.table + ph;
+            if (D->kind != CH_GEMM) continue;
+            const int bn = D->bn, nt = D->n_tiles_n, ksp = D->k_splits;
+            const int num_tiles = n_mt * nt * ksp, nk = D->K / CH_BK / ksp;
+            const uint32_t tx_bytes = CH_A_BYTES + (uint32_t)bn * CH_BK * 2;
+            bool need_wait = ph > p.ph_begin;    // the activations were written by the previous phase of this launch
+            if (lane == 0 && ph + 1 < p.ph_end) {
+                ptx::prefetch_tensormap(&D[1].tmA);
+                ptx::prefetch_tensormap(&D[1].tmW);
+                ch_prefetch_l1(&D[1].kind);
+            }
+            for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
+                const int mn = tile / ksp, ks = tile - mn * ksp;
+                const int m_blk = mn / nt, n_blk = mn - m_blk * nt;
+                int kb0 = 0;
+                if (need_wait) {
+                    // weights do not depend on the previous phase: their first tiles are in flight while we wait at the barrier
+                    const int pre = nk < CH_STAGES ? nk : CH_STAGES;
+                    const int st0 = stage;
+                    for (int i = 0; i < pre; ++i) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (lane == 0) {
+                            ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+                            ptx::tma_load_2d(smem + stage * CH_STAGE_BYTES + CH_A_BYTES, &D->tmW, &full_bar[stage],
+                                             (ks * nk + i) * CH_BK, n_blk * bn);
+                        }
+                        __syncwarp();
+                        if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    if (lane == 0) {
+                        ch_grid_poll(bar, (unsigned)(ph - p.ph_begin) * grid);
+                        ch_fence_proxy_async_all();
+                        int s2 = st0;
+                        for (int i = 0; i < pre; ++i) {
+                            ptx::tma_load_2d(smem + s2 * CH_STAGE_BYTES, &D->tmA, &full_bar[s2], (ks * nk + i) * CH_BK, m_blk * CH_BM);
+                            if (++s2 == CH_STAGES) s2 = 0;
+                        }
+                    }
+                    __syncwarp();
+                    need_wait = false;
+                    kb0 = pre;
+                }
+                for (int kb = kb0; kb < nk; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (lane == 0) {
+                        uint8_t* sa = smem + stage * CH_STAGE_BYTES;
+                        ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+                        ptx::tma_load_2d(sa, &D->tmA, &full_bar[stage], (ks * nk + kb) * CH_BK, m_blk * CH_BM);
+                        ptx::tma_load_2d(sa + CH_A_BYTES, &D->tmW, &full_bar[stage], (ks * nk + kb) * CH_BK, n_blk * bn);
+                    }
+                    __syncwarp();
+                    if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int ph = p.ph_begin; ph < p.ph_end; ++ph) {
+            const ChainPhase* D = p.table + ph;
+            if (D->kind != CH_GEMM) continue;
+            const int bn = D->bn, ksp = D->k_splits;
+            const int num_tiles = n_mt * D->n_tiles_n * ksp, nk = D->K / CH_BK / ksp;
+            const uint32_t idesc = ptx::make_idesc_bf16(CH_BM, (uint32_t)bn, 0, 0);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
+                ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue drained this accumulator
+                ptx::tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * CH_MAX_BN;
+                for (int kb = 0; kb < nk; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tcgen05_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = ptx::smem_u32(smem + stage * CH_STAGE_BYTES);
+                        const uint64_t da = ptx::make_smem_desc_sw128(sa, 1024, 16);
+                        const uint64_t db = ptx::make_smem_desc_sw128(sa + CH_A_BYTES, 1024, 16);
+#pragma unroll
+                        for (int k = 0; k < CH_BK / 16; ++k) ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        ptx::umma_commit(&empty_bar[stage]);
+                        if (kb == nk - 1) ptx::umma_commit(&tmem_full_bar[acc]);
+                    }
+                    __syncwarp();
+                    if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue / LayerNorm workers =====================
+        const int et = threadIdx.x - 128;       // 0..255
+        const int q = warp & 3;                 // TMEM lane quarter of this warp
+        const int half = (warp - 4) >> 2;       // column-slab share (GEMM) / row group (LN)
+        float4* st4 = reinterpret_cast<float4*>(staging + (warp - 4) * 32 * 32);
+        const int rrow = lane >> 3, rchunk = lane & 7;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int ph = p.ph_begin; ph < p.ph_end; ++ph) {
+            const ChainPhase* D = p.table + ph;
+            if (lane == 0 && ph + 1 < p.ph_end) ch_prefetch_l1(&D[1].kind);
+            if (D->kind == CH_GEMM) {
+                const int bn = D->bn, nt = D->n_tiles_n, ksp = D->k_splits, N = D->N, epi = D->epi;
+                const int num_tiles = n_mt * nt * ksp;
+                const int slabs = bn >> 5, spw = (slabs + 1) >> 1;
+                const float* __restrict__ bias = D->bias;
+                const long long ldo = D->ldo, sstride = D->split_stride;
+                void* const outp = D->out;
+                for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
+                    const int mn = tile / ksp, ks = tile - mn * ksp;
+                    const int m_blk = mn / nt, n_blk = mn - m_blk * nt;
+                    ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+                    ptx::tcgen05_fence_after();
+                    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * CH_MAX_BN;
+                    const int row0 = m_blk * CH_BM + q * 32;
+#pragma unroll 1
+                    for (int ci = 0; ci < spw; ++ci) {
+                        const int c = half * spw + ci;
+                        if (c >= slabs) break;
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32(t_row + c * 32, v);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            st4[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        __syncwarp();
+                        const int n0 = n_blk * bn + c * 32 + rchunk * 4;
+                        const bool col_ok = n0 < N;
+                        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (epi != CH_EPI_PARTIAL && bias != nullptr && col_ok) bb = __ldg(reinterpret_cast<const float4*>(bias + n0));
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = i * 4 + rrow;
+                            const int row = row0 + rr;
+                            const float4 f = st4[rr * 8 + (rchunk ^ (rr & 7))];
+                            if (row < p.M && col_ok) {
+                                if (epi == CH_EPI_PARTIAL) {
+                                    float* o = reinterpret_cast<float*>(outp) + (long long)ks * sstride + (long long)row * ldo + n0;
+                                    *reinterpret_cast<float4*>(o) = f;
+                                } else {
+                                    float o0 = f.x + bb.x, o1 = f.y + bb.y, o2 = f.z + bb.z, o3 = f.w + bb.w;
+                                    if (epi == CH_EPI_GELU_BF16) {
+                                        o0 = gelu_erf_fast(o0); o1 = gelu_erf_fast(o1); o2 = gelu_erf_fast(o2); o3 = gelu_erf_fast(o3);
+                                    }
+                                    __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+                                    uint2 u;
+                                    u.x = *reinterpret_cast<uint32_t*>(&p0);
+                                    u.y = *reinterpret_cast<uint32_t*>(&p1);
+                                    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(outp) + (long long)row * ldo + n0) = u;
+                                }
+                            }
+                        }
+                        __syncwarp();   // the staging tile is rewritten by the next slab
+                    }
+                    ptx::tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            } else {
+                // ---- LayerNorm phase: x[r] += bias + sum of slabs (fixed order); out[r] = LN(x[r]) as bf16
+                if (ph > p.ph_begin) {
+                    if (et == 0) ch_grid_poll(bar, (unsigned)(ph - p.ph_begin) * grid);
+                    ch_named_bar(1, CH_EPI_WARPS * 32);
+                }
+                const int d = p.d, nvec = d >> 2;
+                const int gt = et & 127, gw = gt >> 5;              // thread / warp inside the 128-thread row group
+                const int n_parts = D->n_parts;
+                const long long pstride = D->split_stride;
+                float* const xp = D->x;
+                const float* const partp = D->parts;
+                const float4* const biasp = reinterpret_cast<const float4*>(D->bias);
+                const float4* const gammap = reinterpret_cast<const float4*>(D->gamma);
+                const float4* const betap = reinterpret_cast<const float4*>(D->beta);
+                bf16* const lnout = reinterpret_cast<bf16*>(D->out);
+                float* red0 = ln_red + half * 8;
+                float* red1 = red0 + 4;
+                const float inv_d = 1.0f / (float)d;
+                for (int row = (int)blockIdx.x * 2 + half; row < p.M; row += (int)grid * 2) {   // group-uniform trip count
+                    float4 v[2], g[2], be[2];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int t = gt + j * 128;
+                        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        g[j] = v[j]; be[j] = v[j];
+                        if (t < nvec) {
+                            float* xr = xp + (size_t)row * d + t * 4;
+                            v[j] = ch_ld_cg_f4(xr);
+                            if (n_parts > 0) {
+                                float4 b = biasp != nullptr ? __ldg(biasp + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                float4 pq[CH_MAX_PARTS];
+#pragma unroll
+                                for (int s = 0; s < CH_MAX_PARTS; ++s)   // all slabs in flight together
+                                    pq[s] = s < n_parts ? ch_ld_cg_f4(partp + (size_t)s * pstride + (size_t)row * d + t * 4)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                                for (int s = 0; s < CH_MAX_PARTS; ++s) { b.x += pq[s].x; b.y += pq[s].y; b.z += pq[s].z; b.w += pq[s].w; }
+                                v[j].x += b.x; v[j].y += b.y; v[j].z += b.z; v[j].w += b.w;
+                                *reinterpret_cast<float4*>(xr) = v[j];
+                            }
+                            g[j] = __ldg(gammap + t);
+                            be[j] = __ldg(betap + t);
+                        }
+                    }
+                    float s = warp_sum(((v[0].x + v[0].y) + (v[0].z + v[0].w)) + ((v[1].x + v[1].y) + (v[1].z + v[1].w)));
+                    if (lane == 0) red0[gw] = s;
+                    ch_named_bar(2 + half, 128);
+                    const float mean = ((red0[0] + red0[1]) + (red0[2] + red0[3])) * inv_d;
+                    float ss = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        if (gt + j * 128 < nvec) {
+                            v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+                            ss += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+                        }
+                    }
+                    ss = warp_sum(ss);
+                    if (lane == 0) red1[gw] = ss;
+                    ch_named_bar(2 + half, 128);
+                    const float rstd = rsqrtf(((red1[0] + red1[1]) + (red1[2] + red1[3])) * inv_d + p.eps);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int t = gt + j * 128;
+                        if (t < nvec) {
+                            const float y0 = v[j].x * rstd * g[j].x + be[j].x, y1 = v[j].y * rstd * g[j].y + be[j].y;
+                            const float y2 = v[j].z * rstd * g[j].z + be[j].z, y3 = v[j].w * rstd * g[j].w + be[j].w;
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(y0, y1), p1 = __floats2bfloat162_rn(y2, y3);
+                            uint2 u;
+                            u.x = *reinterpret_cast<uint32_t*>(&p0);
+                            u.y = *reinterpret_cast<uint32_t*>(&p1);
+                            *reinterpret_cast<uint2*>(lnout + (size_t)row * d + t * 4) = u;
+                        }
+                    }
+                }
+            }
+            // ---- this CTA's share of the phase is written: arrive at the grid barrier (the last phase needs none)
+            if (ph + 1 < p.ph_end) {
+                ch_named_bar(1, CH_EPI_WARPS * 32);
+                if (et == 0) {
+                    __threadfence();
+                    ch_fence_proxy_async_all();   // the next phase reads these rows through TMA
+                    ch_red_release(bar, 1u);
+                }
+            }
+        }
+    }
+
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc<CH_TMEM_COLS>(tmem_base);
+    // leave the barrier counter at zero for the next launch: the last CTA to get here resets it (nobody polls it any more:
+    // a CTA gets here only after all of its warps have passed every poll of the launch)
+    if (threadIdx.x == 0) {
+        const unsigned total = (unsigned)(p.ph_end - p.ph_begin) * grid;
+        const unsigned old = atomicAdd(bar, 1u);
+        if (old == total - 1) atomicExch(bar, 0u);
+    }
+}
+
+// tile width / split-K of one chain GEMM: same cost model as gemm_tc.cu pick_config (skinny M: bytes a CTA has to pull, one
+// wave, the partial slabs its consumer re-reads), tile width limited to CH_MAX_BN
+void pick_chain_config(int M, int N, int K, int max_splits, int sms, int& bn_out, int& splits_out) {
+    const int mt = ceil_div(M, CH_BM), nkb = K / CH_BK;
+    double best = 1e30;
+    bn_out = 32; splits_out = 1;
+    for (int bn : {32, 64, 128}) {
+        for (int s = 1; s <= max_splits; s *= 2) {
+            if (nkb % s != 0) continue;
+            const long long ctas = (long long)mt * ceil_div(N, bn) * s;
+            const double waves = (double)((ctas + sms - 1) / sms);
+            const double ingest = (double)(CH_BM + bn) * (K / s) * 2.0;
+            const double partial = s > 1 ? (double)M * N * 4.0 * s * 2.0 / 6000.0 : 0.0;
+            const double t = waves * (ingest / 40.0 + 1500.0) + partial;
+            if (t < best) { best = t; bn_out = bn; splits_out = s; }
+        }
+    }
+}
+}  // namespace
+
+size_t chain_table_bytes(int dec_layers) { return (size_t)(2 + 9 * dec_layers) * sizeof(ChainPhase); }
+size_t chain_sync_bytes() { return 256; }
+
+static bool& chain_enabled() {
+    static bool on = true;
+    return on;
+}
+void set_chain_path(bool on) { chain_enabled() = on; }
+bool chain_path_enabled() { return chain_enabled(); }
+
+bool Session::chain_supported() const {
+    const ModelConfig& g = m->cfg;
+    return chain_table != nullptr && m->dtype == BF16 && batch >= 1 && g.d_model % 64 == 0 && g.d_model <= 1024 && g.ffn % 64 == 0 &&
+           chain_grid > 0;
+}
+
+// The phase table of this session for the current batch.  Phase indices:
+//   0 LN1(0), 1 qkv(0); layer l at base = 2 + 9 l: +0 out-proj (slabs), +1 LN2, +2 cross-q (slabs) | +3 cross-out (slabs), +4 LN3,
+//   +5 fc1 (GELU), +6 fc2 (slabs), +7 LN1 of layer l + 1 (final LayerNorm after the last layer), +8 qkv of layer l + 1
+void Session::build_chain_table() {
+    const ModelConfig& g = m->cfg;
+    const int d = g.d_model, B = batch, L = g.dec_layers;
+    WB_REQUIRE(chain_grid > 0 && chain_table != nullptr, "fused chains: no table");
+    std::vector<ChainPhase> t((size_t)2 + 9 * L);
+    std::memset(t.data(), 0, t.size() * sizeof(ChainPhase));
+    const long long part_stride = (long long)B * d;
+    auto gemm_phase = [&](ChainPhase& o, const void* A, int K, const Linear& l, int epi, void* out, long long ldo) -> int {
+        WB_REQUIRE(l.k == K && K % CH_BK == 0 && l.n % 8 == 0, "fused chains: unsupported Linear shape");
+        int bn = 64, splits = 1;
+        pick_chain_config(B, l.n, K, epi == CH_EPI_PARTIAL ? MAX_K_SPLITS : 1, chain_grid, bn, splits);
+        o.kind = CH_GEMM; o.bn = bn; o.K = K; o.N = l.n; o.n_tiles_n = ceil_div(l.n, bn); o.k_splits = splits; o.epi = epi;
+        o.split_stride = part_stride; o.ldo = ldo; o.bias = epi == CH_EPI_PARTIAL ? nullptr : l.b; o.out = out;
+        o.tmA = make_tmap_bf16_2d(A, K, B, K, CH_BM);
+        o.tmW = make_tmap_bf16_2d(l.w, l.k, l.n, l.k, bn);
+        return splits;
+    };
+    auto ln_phase = [&](ChainPhase& o, const LNorm& n, int n_parts, const float* bias) {
+        o.kind = CH_LN; o.n_parts = n_parts; o.split_stride = part_stride; o.bias = bias; o.parts = dpart;
+        o.gamma = n.g; o.beta = n.b; o.x = dx; o.out = dln;
+    };
+    chain_q_parts.assign((size_t)L, 1);
+    ln_phase(t[0], m->dec[0].ln1, 0, nullptr);
+    gemm_phase(t[1], dln, d, m->dec[0].qkv, CH_EPI_BF16, dqkv, 3 * d);
+    for (int l = 0; l < L; ++l) {
+        const DecLayer& Y = m->dec[l];
+        ChainPhase* o = &t[(size_t)2 + 9 * l];
+        int s = gemm_phase(o[0], datt, d, Y.out, CH_EPI_PARTIAL, dpart, d);
+        ln_phase(o[1], Y.ln2, s, Y.out.b);
+        chain_q_parts[l] = gemm_phase(o[2], dln, d, Y.cq, CH_EPI_PARTIAL, dpart, d);
+        s = gemm_phase(o[3], datt, d, Y.cout, CH_EPI_PARTIAL, dpart, d);
+        ln_phase(o[4], Y.ln3, s, Y.cout.b);
+        gemm_phase(o[5], dln, d, Y.fc1, CH_EPI_GELU_BF16, dffn, g.ffn);
+        s = gemm_phase(o[6], dffn, g.ffn, Y.fc2, CH_EPI_PARTIAL, dpart, d);
+        if (l + 1 < L) {
+            ln_phase(o[7], m->dec[l + 1].ln1, s, Y.fc2.b);
+            gemm_phase(o[8], dln, d, m->dec[l + 1].qkv, CH_EPI_BF16, dqkv, 3 * d);
+        } else {
+            ln_phase(o[7], m->dec_ln, s, Y.fc2.b);
+        }
+    }
+    WB_CHECK_CUDA(cudaMemcpy(chain_table, t.data(), t.size() * sizeof(ChainPhase), cudaMemcpyHostToDevice));
+    chain_batch = B;
+}
+
+void Session::init_chain() {
+    chain_grid = 0;
+    chain_batch = -1;
+    if (m->dtype != BF16 || chain_table == nullptr) return;
+    int dev = 0, sms = 0;
+    WB_CHECK_CUDA(cudaGetDevice(&dev));
+    WB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    WB_CHECK_CUDA(cudaFuncSetAttribute(decode_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_BYTES));
+    int per_sm = 0;
+    WB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_chain_kernel, CH_THREADS, CH_SMEM_BYTES));
+    if (per_sm < 1) return;   // does not fit on this device: the multi-kernel step stays
+    chain_grid = sms;
+    WB_CHECK_CUDA(cudaMemset(chain_sync, 0, chain_sync_bytes()));
+}
+
+void Session::launch_chain(int ph_begin, int ph_end, cudaStream_t st) {
+    ChainParams p{};
+    p.table = reinterpret_cast<const ChainPhase*>(chain_table);
+    p.ph_begin = ph_begin; p.ph_end = ph_end; p.M = batch; p.d = m->cfg.d_model; p.eps = 1e-5f;
+    p.state = state; p.sync = chain_sync;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(chain_grid);
+    cfg.blockDim = dim3(CH_THREADS);
+    cfg.dynamicSmemBytes = CH_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident, or the launch fails: the grid barrier cannot deadlock
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    launch_counter().fetch_add(1, std::memory_order_relaxed);
+    WB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_chain_kernel, p));
+}
+
+// one token for the whole batch: 4 launches per layer (self-attention, chain, cross-attention, chain) instead of 11
+void Session::decode_step_chain(cudaStream_t st) {
+    const ModelConfig& g = m->cfg;
+    const int d = g.d_model, dt = m->dtype, B = batch, L = g.dec_layers;
+    WB_REQUIRE(chain_batch == B, "fused chains: the phase table was built for another batch (prepare_step was not called)");
+    const int* active = &state->active;
+    { ProfScope ps(this, PROF_DEC_GEMM, st); launch_chain(0, 2, st); }
+    for (int l = 0; l < L; ++l) {
+        const int base = 2 + 9 * l;
+        {
+            DecAttnArgs a;
+            a.dtype = dt; a.q = dqkv; a.q_stride = 3 * d; a.out = datt; a.out_stride = d; a.B = B; a.H = g.n_heads;
+            a.state = state; a.row_active = unfinished;
+            a.k_new = (uint8_t*)dqkv + (size_t)d * 2; a.v_new = (uint8_t*)dqkv + (size_t)2 * d * 2; a.new_stride = 3 * d;
+            a.k_pages = (uint8_t*)self_k + (size_t)l * self_layer_elems() * 2;
+            a.v_pages = (uint8_t*)self_v + (size_t)l * self_layer_elems() * 2;
+            a.page_table = page_table; a.pages_per_seq = pages_per_seq; a.page_tokens = PAGE_TOKENS;
+            ProfScope ps(this, PROF_SELF_ATTN, st);
+            decode_attention(a, st);
+        }
+        { ProfScope ps(this, PROF_DEC_GEMM, st); launch_chain(base, base + 3, st); }
+        {
+            DecAttnArgs a;
+            a.dtype = dt; a.out = datt; a.out_stride = d; a.B = B; a.H = g.n_heads;
+            a.q_parts = dpart; a.q_n_parts = chain_q_parts[l]; a.q_part_stride = (long long)B * d; a.q_bias = m->dec[l].cq.b;
+            a.state = nullptr; a.n_keys = g.n_ctx; a.active = active; a.row_active = unfinished;
+            const size_t per_kv = (size_t)max_batch * g.n_heads * g.n_ctx * 64;
+            a.k = (uint8_t*)cross + (size_t)l * cross_layer_elems() * 2;
+            a.v = (uint8_t*)cross + ((size_t)l * cross_layer_elems() + per_kv) * 2;
+            a.kv_bstride = (long long)g.n_heads * g.n_ctx * 64; a.kv_hstride = (long long)g.n_ctx * 64;
+            ProfScope ps(this, PROF_CROSS_ATTN, st);
+            decode_attention(a, st);
+        }
+        { ProfScope ps(this, PROF_DEC_GEMM, st); launch_chain(base + 3, l + 1 < L ? base + 9 : base + 8, st); }
+    }
+    {
+        // LM head: proj_out shares storage with embed_tokens (modeling_whisper.py:1335,1433), no bias
+        GemmArgs a;
+        a.A = dln; a.lda = d; a.W = m->emb; a.ldw = d; a.in_dtype = dt;
+        a.out = logits; a.ldo = g.vocab; a.out_dtype = F32; a.M = B; a.N = g.vocab; a.K = d; a.active = active;
+        ProfScope ps(this, PROF_LM_HEAD, st);
+        gemm(a, st);
+    }
+}
+
+}  // namespace wb

@@ -86,10 +86,14 @@ struct Buffers {
     // whole-step kernel (step_mega.cu): attention partials of split items, grid-barrier / per-item arrival counters
     float* mega_part = nullptr; unsigned* mega_sync = nullptr; void* mega_table = nullptr;
     int* result_tokens = nullptr;   // [max_batch, max_tgt] ids in ORIGINAL row order once rows have been compacted away
+    // fused decode chains (step_chain.cu): phase descriptors (tensor maps included) and the grid-barrier word
+    void* chain_table = nullptr; unsigned* chain_sync = nullptr;
 };
 size_t mega_part_bytes(int max_batch, int heads);
 size_t mega_sync_bytes(int max_batch, int heads);
 size_t mega_table_bytes(int dec_layers);
+size_t chain_table_bytes(int dec_layers);
+size_t chain_sync_bytes();
 
 struct Session : Buffers {
     Model* m;
@@ -107,10 +111,12 @@ struct Session : Buffers {
     cudaGraphExec_t step_graph = nullptr;
     int step_graph_batch = 0;
     int step_graph_generation = -1;
-    bool step_graph_mega = false;     // the captured step is the whole-step kernel (small batches) / the multi-kernel step
+    int step_graph_mode = 0;          // path of the captured step: 0 multi-kernel, 1 whole-step kernel (B <= 16), 2 fused chains
+    int step_mode() const { return use_mega() ? 1 : use_chain() ? 2 : 0; }
     bool exclusive = true;            // this session's loop is the only one running on the device (decode_run_multi, n == 1)
     long long step_graph_launches = 0;
     bool step_warm = false;           // one eager step has run (one-time kernel attribute setup done)
+    bool dx_embedded = false;         // dx holds E[last token] + P[position] of every row (what the whole-step kernel starts from)
     bool graph_ok() const;
     void build_step_graph(cudaStream_t s);
     cudaEvent_t check_event = nullptr;
@@ -141,6 +147,17 @@ struct Session : Buffers {
     bool use_mega() const;                    // this batch goes through the whole-step kernel
     void build_mega_table();                  // phase descriptors of the whole-step kernel (constructor)
     int mega_grid = 0;                        // CTAs of the whole-step kernel = SMs of the device the table was built for
+    // B > 16, bf16: the GEMM / LayerNorm chains between the attention kernels as persistent cooperative tcgen05 kernels
+    // (step_chain.cu): 4 launches per layer instead of 11
+    void decode_step_chain(cudaStream_t s);
+    bool chain_supported() const;
+    bool use_chain() const;
+    void init_chain();                        // constructor: kernel attributes, grid size
+    void build_chain_table();                 // phase table for the current batch
+    void launch_chain(int ph_begin, int ph_end, cudaStream_t s);
+    void prepare_step(cudaStream_t s);        // host-side work a step needs OUTSIDE a graph capture (phase table, embedding in dx)
+    int chain_grid = 0, chain_batch = -1;
+    std::vector<int> chain_q_parts;           // split-K slabs of each layer's cross-attention q projection
     int decode_run(int max_steps, int check_every, cudaStream_t s);  // returns final length (syncs)
     // Finished-row compaction: utterances that emitted EOS leave the decode batch; the rows still running
     // move to the front (ids, page-table rows, cross K/V rows) and the following steps run on `batch` = their number.
@@ -153,6 +170,13 @@ struct Session : Buffers {
     void enqueue_step();                                             // one step on loop_stream (graph replay or eager)
     size_t cross_layer_elems() const;
     size_t self_layer_elems() const;
+};
+
+// CUDA events around the launches of one kernel class (Session::prof_*)
+struct ProfScope {
+    Session* s; int cls; cudaStream_t st;
+    ProfScope(Session* s_, int c, cudaStream_t t) : s(s_), cls(c), st(t) { s->prof_begin(cls, st); }
+    ~ProfScope() noexcept(false) { s->prof_end(cls, st); }
 };
 
 void decode_run_multi(Session** sessions, int n, int max_steps, int check_every, int* final_lens, cudaStream_t caller);

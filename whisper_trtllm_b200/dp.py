@@ -32,6 +32,9 @@ def max_shard(n_utterances: int, world_size: int) -> int:
 def pad_tokens(ids: torch.Tensor, rows: int, max_length: int, pad_token_id: int) -> torch.Tensor:
     """ids [b, L<=max_length] -> int32 [rows, max_length], right/bottom padded with pad_token_id (rows finished early are
     already padded with it by the greedy loop, generation/utils.py:1506-1510)."""
+    if ids.shape[1] > max_length or ids.shape[0] > rows:
+        raise ValueError(f"ids {tuple(ids.shape)} do not fit the gather buffer [{rows}, {max_length}]: max_length must be the "
+                         "longest sequence any rank can produce")
     out = torch.full((rows, max_length), pad_token_id, dtype=torch.int32, device=ids.device)
     out[:ids.shape[0], :ids.shape[1]] = ids.to(torch.int32)
     return out
@@ -56,9 +59,12 @@ def gather_tokens(ids: torch.Tensor, n_utterances: int, max_length: int, pad_tok
 
 
 def transcribe_sharded(transcribe_fn: Callable[[torch.Tensor], torch.Tensor], mel_all: torch.Tensor, max_length: int,
-                       pad_token_id: int, group=None, rank: Optional[int] = None, world_size: Optional[int] = None) -> torch.Tensor:
+                       pad_token_id: int, group=None, rank: Optional[int] = None, world_size: Optional[int] = None,
+                       device: Optional[torch.device] = None) -> torch.Tensor:
     """Run ``transcribe_fn`` (mel shard -> ids) on this rank's shard of ``mel_all [N, 80, 3000]`` and gather.
-    ``mel_all`` may live on the host: only the shard is moved by ``transcribe_fn``."""
+    ``mel_all`` may live on the host: only the shard is moved by ``transcribe_fn``.  ``device`` is where the collective runs
+    (the engine's / NCCL device): a rank with an EMPTY shard must enter the all-gather with a tensor on the same kind of
+    device as the others.  Default: the device of the ids ``transcribe_fn`` returns, else of ``mel_all``."""
     import torch.distributed as dist
     if rank is None or world_size is None:
         if dist.is_available() and dist.is_initialized():
@@ -69,6 +75,8 @@ def transcribe_sharded(transcribe_fn: Callable[[torch.Tensor], torch.Tensor], me
     b, e = shard_range(n, world_size, rank)
     if e > b:
         ids = transcribe_fn(mel_all[b:e])
+        if device is not None:
+            ids = ids.to(device)
     else:
-        ids = torch.empty(0, 1, dtype=torch.int32, device=mel_all.device)
+        ids = torch.empty(0, 1, dtype=torch.int32, device=device if device is not None else mel_all.device)
     return gather_tokens(ids, n, max_length, pad_token_id, group)

@@ -236,13 +236,17 @@ class FastPath:
 
     def __init__(self, engine: WhisperEngine):
         self.engine = engine
-        self._enc_key = None
+        self._enc_ref = None      # STRONG reference to the tensor whose cross K/V the engine holds: identity, not address
+        self._enc_version = -1
 
     def note_encoder_output(self, hidden: torch.Tensor):
-        self._enc_key = (hidden.data_ptr(), hidden._version, tuple(hidden.shape))
+        # holding the tensor pins its storage: the caching allocator cannot hand the same address to another tensor, and
+        # `is` + the version counter cannot be fooled by a different tensor of the same shape
+        self._enc_ref = hidden
+        self._enc_version = hidden._version
 
     def has_encoder_output(self, hidden: torch.Tensor) -> bool:
-        return self._enc_key == (hidden.data_ptr(), hidden._version, tuple(hidden.shape))
+        return self._enc_ref is hidden and self._enc_version == hidden._version
 
 
 def link(encoder: WhisperEncoder, decoder: WhisperDecoder, config: Dict, max_batch: int = 1, dtype: Optional[str] = None,
