@@ -15,6 +15,8 @@
 //     instruction covers 4 complete rows = 512 contiguous bytes; K and V rows of UNROLL iterations are all in
 //     flight before the first use (16-byte L1-bypassing loads);
 //   - each 8-lane group keeps its own running (max, sum, acc[8]) and the groups/warps are merged once per item.
+#include <cstdlib>
+
 #include "wb_internal.h"
 
 namespace wb {
@@ -408,6 +410,14 @@ void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
     const bool few_items = a.B * a.H <= 2 * num_sms();
     if (paged && few_items && a.dtype == BF16 && g_self_attn_variant == 0) {
         launch<bf16, true, 256, 4>(a, stream);
+        return;
+    }
+    // medium item counts (two .. ~eight items per SM): one warp per item leaves most of every SM's load slots empty and each
+    // warp walks its whole sequence alone (23 us per launch at B = 32, medium.en, where the bytes need 4 us) -> a 128-thread
+    // CTA per item, the keys split over its 4 warps.  (dev) WB_SELF_CTA_ITEMS overrides the threshold.
+    static const int cta_items_max = std::getenv("WB_SELF_CTA_ITEMS") ? std::atoi(std::getenv("WB_SELF_CTA_ITEMS")) : 1024;
+    if (paged && a.dtype == BF16 && g_self_attn_variant == 0 && a.B * a.H <= cta_items_max) {
+        launch<bf16, true, THREADS_SELF, 4>(a, stream);
         return;
     }
     const bool warp_variant = g_self_attn_variant == 0 || g_self_attn_variant == 5 || g_self_attn_variant == 6;

@@ -60,7 +60,13 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint64_t* o_empty = o_full + 2;          // 2
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_empty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform by construction: uniform role branches
+    const int lane = threadIdx.x & 31;
+    const uint32_t smem_a = raw_addr + ((1024u - (raw_addr & 1023u)) & 1023u);   // shared-memory address of `smem` (warp-uniform)
+    // the barriers by shared-memory address (uniform operands of the converged-warp issue forms below)
+    const uint32_t q_full_a = smem_a + SMEM_BAR, k_full_a = q_full_a + 8, v_full_a = k_full_a + STAGES * 8;
+    const uint32_t kv_empty_a = v_full_a + STAGES * 8, s_full_a = kv_empty_a + STAGES * 8, s_empty_a = s_full_a + 16;
+    const uint32_t p_full_a = s_empty_a + 16, o_full_a = p_full_a + 16, o_empty_a = o_full_a + 16;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int d = H * DH;
     const int q0 = qt * TQ;
@@ -94,67 +100,64 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            ptx::mbar_expect_tx(q_full, Q_BYTES);
-            ptx::tma_load_2d(smem + SMEM_Q, &tmQ, q_full, h * DH, row_base + q0);
-        }
+        // ===================== TMA producer (converged warp, the elected lane issues) =====================
+        ptx::mbar_expect_tx_elect(q_full_a, Q_BYTES);
+        ptx::tma_load_2d_elect(smem_a + SMEM_Q, &tmQ, q_full_a, h * DH, row_base + q0);
         for (int j = 0; j < n_tiles; ++j) {
             const int st = j % STAGES;
-            ptx::mbar_wait(&kv_empty[st], ((j / STAGES) & 1) ^ 1);
-            if (lane == 0) {
-                ptx::mbar_expect_tx(&k_full[st], KV_BYTES);
-                ptx::tma_load_2d(smem + SMEM_K + st * KV_BYTES, &tmKV, &k_full[st], d + h * DH, row_base + j * TKV);
-                ptx::mbar_expect_tx(&v_full[st], KV_BYTES);
-                ptx::tma_load_2d(smem + SMEM_V + st * KV_BYTES, &tmKV, &v_full[st], 2 * d + h * DH, row_base + j * TKV);
-            }
-            __syncwarp();
+            ptx::mbar_wait_addr(kv_empty_a + st * 8, ((j / STAGES) & 1) ^ 1);
+            ptx::mbar_expect_tx_elect(k_full_a + st * 8, KV_BYTES);
+            ptx::tma_load_2d_elect(smem_a + SMEM_K + st * KV_BYTES, &tmKV, k_full_a + st * 8, d + h * DH, row_base + j * TKV);
+            ptx::mbar_expect_tx_elect(v_full_a + st * 8, KV_BYTES);
+            ptx::tma_load_2d_elect(smem_a + SMEM_V + st * KV_BYTES, &tmKV, v_full_a + st * 8, 2 * d + h * DH, row_base + j * TKV);
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer (converged warp, the elected lane issues) =====================
+        // tcgen05.mma / commit operands live in uniform registers; issued from an `if (lane == 0)` region every operand was moved
+        // across with ELECT + R2UR.BROADCAST (~100 cycles per MMA, 8 MMAs per key tile against 256 cycles of tensor pipe).  The
+        // warp stays converged and every operand derives from kernel parameters, block indices and the uniform tile counter.
         constexpr uint32_t idesc_s = ptx::make_idesc_bf16(TQ, TKV, 0, 0);   // S = Q K^T : both operands K-major
         constexpr uint32_t idesc_o = ptx::make_idesc_bf16(TQ, DH, 0, 1);    // O = P V   : V is MN-major (dh contiguous)
-        const uint32_t q_addr = ptx::smem_u32(smem + SMEM_Q);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint64_t dq = ptx::make_smem_desc_sw128(smem_a + SMEM_Q, 1024, 16);
         auto issue_s = [&](int j) {
             const int st = j % STAGES;
-            const uint64_t da = ptx::make_smem_desc_sw128(q_addr, 1024, 16);
-            const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + SMEM_K + st * KV_BYTES), 1024, 16);
-            const uint32_t dst = tmem_base + (j & 1) * 64;
-#pragma unroll
-            for (int k = 0; k < DH / 16; ++k) ptx::umma_f16(dst, da + 2 * k, db + 2 * k, idesc_s, k != 0);
-            ptx::umma_commit(&s_full[j & 1]);
+            const uint64_t db = ptx::make_smem_desc_sw128(smem_a + SMEM_K + st * KV_BYTES, 1024, 16);
+            const uint32_t dst = tmem_u + (j & 1) * 64;
+            ptx::umma_f16_elect(dst, dq, db, idesc_s, 0);
+            ptx::umma_f16_elect(dst, dq + 2, db + 2, idesc_s, 1);
+            ptx::umma_f16_elect(dst, dq + 4, db + 4, idesc_s, 1);
+            ptx::umma_f16_elect(dst, dq + 6, db + 6, idesc_s, 1);
+            ptx::umma_commit_elect(s_full_a + (j & 1) * 8);
         };
-        ptx::mbar_wait(q_full, 0);
-        ptx::mbar_wait(&k_full[0], 0);
+        ptx::mbar_wait_addr(q_full_a, 0);
+        ptx::mbar_wait_addr(k_full_a, 0);
         ptx::tcgen05_fence_after();
-        if (lane == 0) issue_s(0);
-        __syncwarp();
+        issue_s(0);
         for (int j = 0; j < n_tiles; ++j) {
             if (j + 1 < n_tiles) {
                 const int jn = j + 1;
-                ptx::mbar_wait(&k_full[jn % STAGES], (jn / STAGES) & 1);
-                ptx::mbar_wait(&s_empty[jn & 1], ((jn >> 1) & 1) ^ 1);
+                ptx::mbar_wait_addr(k_full_a + (jn % STAGES) * 8, (jn / STAGES) & 1);
+                ptx::mbar_wait_addr(s_empty_a + (jn & 1) * 8, ((jn >> 1) & 1) ^ 1);
                 ptx::tcgen05_fence_after();
-                if (lane == 0) issue_s(jn);
-                __syncwarp();
+                issue_s(jn);
             }
             const int st = j % STAGES;
-            ptx::mbar_wait(&v_full[st], (j / STAGES) & 1);
-            ptx::mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-            ptx::mbar_wait(&o_empty[j & 1], ((j >> 1) & 1) ^ 1);
+            ptx::mbar_wait_addr(v_full_a + st * 8, (j / STAGES) & 1);
+            ptx::mbar_wait_addr(p_full_a + (j & 1) * 8, (j >> 1) & 1);
+            ptx::mbar_wait_addr(o_empty_a + (j & 1) * 8, ((j >> 1) & 1) ^ 1);
             ptx::tcgen05_fence_after();
-            if (lane == 0) {
-                // A = P [128 x 64 keys] K-major; B = V_j [64 keys x 64 dh], MN-major: key rows are 128 B apart,
-                // 8-row swizzle atoms 1024 B apart (SBO); one UMMA_K step = 16 keys = 2048 B
-                const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + SMEM_P + (j & 1) * P_BYTES), 1024, 16);
-                const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + SMEM_V + st * KV_BYTES), 1024, KV_BYTES);
-                const uint32_t dst = tmem_base + 128 + (j & 1) * 64;
-#pragma unroll
-                for (int k = 0; k < TKV / 16; ++k) ptx::umma_f16(dst, da + 2 * k, db + 128 * k, idesc_o, k != 0);
-                ptx::umma_commit(&o_full[j & 1]);
-                ptx::umma_commit(&kv_empty[st]);
-            }
-            __syncwarp();
+            // A = P [128 x 64 keys] K-major; B = V_j [64 keys x 64 dh], MN-major: key rows are 128 B apart,
+            // 8-row swizzle atoms 1024 B apart (SBO); one UMMA_K step = 16 keys = 2048 B
+            const uint64_t da = ptx::make_smem_desc_sw128(smem_a + SMEM_P + (j & 1) * P_BYTES, 1024, 16);
+            const uint64_t db = ptx::make_smem_desc_sw128(smem_a + SMEM_V + st * KV_BYTES, 1024, KV_BYTES);
+            const uint32_t dst = tmem_u + 128 + (j & 1) * 64;
+            ptx::umma_f16_elect(dst, da, db, idesc_o, 0);
+            ptx::umma_f16_elect(dst, da + 2, db + 128, idesc_o, 1);
+            ptx::umma_f16_elect(dst, da + 4, db + 256, idesc_o, 1);
+            ptx::umma_f16_elect(dst, da + 6, db + 384, idesc_o, 1);
+            ptx::umma_commit_elect(o_full_a + (j & 1) * 8);
+            ptx::umma_commit_elect(kv_empty_a + st * 8);
         }
     } else {
         // ===================== softmax + accumulate: thread == query row =====================

@@ -56,9 +56,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp-uniform by construction (the role branches below are then uniform branches: the MMA / TMA issuing code stays on
+    // the uniform datapath, see the note at the MMA issuer)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
     const int num_tiles = num_m_tiles * num_n_tiles * k_splits;   // work item = (m tile, n tile, k split)
     const int nk = K / BK / k_splits;                             // k blocks per work item
+    const uint32_t smem_a = raw_addr + ((1024u - (raw_addr & 1023u)) & 1023u);   // shared-memory address of the ring
+    constexpr uint32_t BAR_OFF = STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES;
+    const uint32_t full_a = smem_a + BAR_OFF, empty_a = full_a + STAGES * 8;
+    const uint32_t tfull_a = empty_a + STAGES * 8, tempty_a = tfull_a + 16;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
@@ -89,49 +96,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool run = (active == nullptr) || (*active != 0);
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (converged warp, the elected lane issues) =====================
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int mn = tile / k_splits, ks = tile - mn * k_splits;
             const int m_blk = mn / num_n_tiles, n_blk = mn - m_blk * num_n_tiles;
             for (int kb = 0; kb < nk; ++kb) {
-                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                if (lane == 0) {
-                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                    ptx::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    ptx::tma_load_2d(sa, &tmA, &full_bar[stage], (ks * nk + kb) * BK, m_blk * BM);
-                    ptx::tma_load_2d(sa + A_BYTES, &tmW, &full_bar[stage], (ks * nk + kb) * BK, n_blk * BN);
-                }
-                __syncwarp();
+                ptx::mbar_wait_addr(empty_a + stage * 8, phase ^ 1);
+                const uint32_t sa = smem_a + stage * Cfg::STAGE_BYTES;
+                ptx::mbar_expect_tx_elect(full_a + stage * 8, Cfg::STAGE_BYTES);
+                ptx::tma_load_2d_elect(sa, &tmA, full_a + stage * 8, (ks * nk + kb) * BK, m_blk * BM);
+                ptx::tma_load_2d_elect(sa + A_BYTES, &tmW, full_a + stage * 8, (ks * nk + kb) * BK, n_blk * BN);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer (converged warp, the elected lane issues) =====================
+        // tcgen05.mma / tcgen05.commit read their operands from UNIFORM registers.  Issued from inside an `if (lane == 0)`
+        // region ptxas moved every operand across with ELECT + R2UR.BROADCAST, ~100 cycles per MMA (measured with clock stamps
+        // in the decode chains, profiles/r02_chain_trace_*.md): 4 MMAs of a 128 x 256 x 64 k-block need 512 cycles of tensor
+        // pipe, their issue took ~650.  With the warp converged and all operands derived from kernel parameters and uniform
+        // loop counters the descriptors are computed on the uniform datapath and the MMAs issue back to back.
         constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, 0, 0);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+            ptx::mbar_wait_addr(tempty_a + acc * 8, acc_phase ^ 1);  // epilogue drained this accumulator
             ptx::tcgen05_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
+            const uint32_t d_tmem = tmem_u + acc * BN;
             for (int kb = 0; kb < nk; ++kb) {
-                ptx::mbar_wait(&full_bar[stage], phase);  // TMA bytes landed
+                ptx::mbar_wait_addr(full_a + stage * 8, phase);  // TMA bytes landed
                 ptx::tcgen05_fence_after();
-                if (lane == 0) {
-                    const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint64_t da = ptx::make_smem_desc_sw128(sa, 1024, 16);
-                    const uint64_t db = ptx::make_smem_desc_sw128(sa + A_BYTES, 1024, 16);
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)  // advance 16 bf16 = 32 B inside the swizzle atom
-                        ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                    ptx::umma_commit(&empty_bar[stage]);                     // smem slot reusable when MMAs finish
-                    if (kb == nk - 1) ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator complete
-                }
-                __syncwarp();
+                const uint32_t sa = smem_a + stage * Cfg::STAGE_BYTES;
+                const uint64_t da = ptx::make_smem_desc_sw128(sa, 1024, 16);
+                const uint64_t db = ptx::make_smem_desc_sw128(sa + A_BYTES, 1024, 16);
+                ptx::umma_f16_elect(d_tmem, da, db, idesc, kb != 0);      // advance 16 bf16 = 32 B inside the swizzle atom
+                ptx::umma_f16_elect(d_tmem, da + 2, db + 2, idesc, 1);
+                ptx::umma_f16_elect(d_tmem, da + 4, db + 4, idesc, 1);
+                ptx::umma_f16_elect(d_tmem, da + 6, db + 6, idesc, 1);
+                ptx::umma_commit_elect(empty_a + stage * 8);                     // smem slot reusable when MMAs finish
+                if (kb == nk - 1) ptx::umma_commit_elect(tfull_a + acc * 8);     // accumulator complete
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }

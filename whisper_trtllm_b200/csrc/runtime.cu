@@ -269,7 +269,6 @@ size_t layout(Buffers& b, const Model* m, int max_batch, int enc_chunk, void* ba
     c.take(b.mega_sync, mega_sync_bytes(max_batch, g.n_heads));
     c.take(b.mega_table, mega_table_bytes(g.dec_layers));
     c.take(b.result_tokens, B * g.max_tgt * 4);
-    c.take(b.chain_table, chain_table_bytes(g.dec_layers));
     c.take(b.chain_sync, chain_sync_bytes());
     return c.off + 1024;
 }

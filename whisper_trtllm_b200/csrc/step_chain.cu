@@ -22,6 +22,7 @@
 // bf16 activations into every Linear, split-K partials summed in slab order): models/whisper/model.py:321-369,
 // layers/normalization.py:6-30, modeling_whisper.py:710-751.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -31,6 +32,7 @@
 namespace wb {
 
 CUtensorMap make_tmap_bf16_2d(const void* ptr, long long ld_elems, int rows, int cols, int box_rows);   // gemm_tc.cu
+long long*& step_trace_ptr();                                                                            // step_mega.cu
 
 namespace {
 constexpr int CH_BM = 128, CH_BK = 64, CH_MAX_BN = 128;
@@ -55,6 +57,7 @@ struct alignas(128) ChainPhase {
     int kind;
     int bn, K, N, n_tiles_n, k_splits, epi;
     int n_parts;                // LN: slabs to add to x (0: plain LayerNorm of x)
+    int a_bytes;                // GEMM: bytes of one activation box ({64, a_rows}: only the rows that exist are loaded)
     long long split_stride;     // GEMM (partial epilogue) / LN: floats between consecutive slabs
     long long ldo;              // GEMM: elements between output rows
     const float* bias;          // GEMM: epilogue bias (bf16 epilogues); LN: bias of the split-K GEMM that produced the slabs
@@ -62,17 +65,26 @@ struct alignas(128) ChainPhase {
     const float* parts;         // LN: slabs
     const float* gamma; const float* beta;
     float* x;                   // LN: fp32 residual stream [M, d], updated in place
-    int pad[8];
+    int pad[6];
 };
 static_assert(sizeof(ChainPhase) == 384, "ChainPhase layout");
 
+constexpr int CH_MAX_PHASES = 6;   // phases of one launch: the descriptors travel as kernel parameters
+
+// The phase descriptors of ONE launch live in the kernel parameters (constant bank): every per-phase scalar is a uniform
+// load, the loops they control are provably warp-uniform, and the tensor maps sit where the TMA unit fetches them fastest.
+// (A table in global memory cost a cold ~1.5 us descriptor + tensor-map fetch per launch and, worse, made ptxas treat the
+// k-loop state as divergent: every tcgen05.mma / TMA operand was moved lane -> uniform register one by one, ~100 cycles per
+// instruction, profiles/r02_chain_trace_*.md.)
 struct ChainParams {
-    const ChainPhase* table;
-    int ph_begin, ph_end;
+    ChainPhase ph[CH_MAX_PHASES];
+    int n_ph;                   // phases of this launch
+    int ph0;                    // index of ph[0] in the step's phase list (trace slots only)
     int M, d;
     float eps;
     const StepState* state;
-    unsigned* sync;             // [0] grid-barrier counter: zero between launches
+    unsigned* sync;             // [0] grid-barrier arrivals, [1] exits: zero between launches
+    long long* trace;           // optional (tools/chain_trace.py): SM clock stamps of CTA 0, 8 slots per phase
 };
 
 __device__ __forceinline__ unsigned ch_ld_acquire(const unsigned* p) {
@@ -90,8 +102,50 @@ __device__ __forceinline__ float4 ch_ld_cg_f4(const float* p) {   // written by 
     asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
     return r;
 }
-__device__ __forceinline__ void ch_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// Converged-warp TMA forms (see ptx::umma_f16_elect): every lane executes the call with warp-uniform operands, the elected
+// lane issues; operands stay in uniform registers.
+__device__ __forceinline__ void ch_tma_load_2d_elect(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void ch_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+        ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA prefetch of one box into L2 (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void ch_tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void ch_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void ch_named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ bool ch_mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait on an mbarrier given by its shared-memory address (a protocol bug traps instead of hanging the GPU)
+__device__ __forceinline__ void ch_mbar_wait(uint32_t bar, uint32_t parity) {
+    if (ch_mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!ch_mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            printf("wb: chain mbarrier timeout (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
 
 // every CTA has arrived `target` times: all writes of the phases before are visible.  A lost CTA traps instead of hanging.
 __device__ __forceinline__ void ch_grid_poll(const unsigned* counter, unsigned target) {
@@ -105,27 +159,39 @@ __device__ __forceinline__ void ch_grid_poll(const unsigned* counter, unsigned t
     }
 }
 
-__global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const ChainParams p) {
+__global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const __grid_constant__ ChainParams p) {
     extern __shared__ uint8_t smem_raw[];
     if (p.state->active == 0) return;   // the loop has stopped: grid-uniform, nobody touches the barrier
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
-    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1024-byte aligned bases
+    const uint32_t skew = (1024u - (raw_addr & 1023u)) & 1023u;          // SWIZZLE_128B tiles need 1024-byte aligned bases
+    uint8_t* smem = smem_raw + skew;
+    const uint32_t smem_a = raw_addr + skew;                             // shared-memory address of the ring (warp-uniform)
+    constexpr uint32_t BAR_OFF = CH_STAGES * CH_STAGE_BYTES + CH_STAGING_BYTES;
     float* staging = reinterpret_cast<float*>(smem + CH_STAGES * CH_STAGE_BYTES);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + CH_STAGES * CH_STAGE_BYTES + CH_STAGING_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
     uint64_t* empty_bar = full_bar + CH_STAGES;
     uint64_t* tmem_full_bar = empty_bar + CH_STAGES;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
     float* ln_red = reinterpret_cast<float*>(tmem_ptr_smem + 4);        // [2 groups][2 reductions][4 warps]
+    // the same barriers by shared-memory address
+    const uint32_t full_a = smem_a + BAR_OFF, empty_a = full_a + CH_STAGES * 8;
+    const uint32_t tfull_a = empty_a + CH_STAGES * 8, tempty_a = tfull_a + 16;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform by construction
+    const int lane = threadIdx.x & 31;
+    // stamps (CTA 0, lane 0 of each role): [0] phase start, [1] epilogue leader past the grid barrier, [2] producer past it,
+    // [3] activation loads issued, [4] first k-block landed, [5] first accumulator complete, [6] this CTA's share written,
+    // [7] arrived at the next grid barrier
+    const bool tracing = p.trace != nullptr && blockIdx.x == 0;         // uniform
     const int n_mt = (p.M + CH_BM - 1) / CH_BM;
+    const int n_ph = p.n_ph;
     const unsigned grid = gridDim.x;
     unsigned* const bar = p.sync;
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < CH_STAGES; ++s) {
-            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&full_bar[s], 2);    // the two producer warps
             ptx::mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -141,94 +207,131 @@ __global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const Chain
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer of the ACTIVATION tiles (converged warp, elected lane issues) =====================
+        // Two producer warps: a TMA instruction costs its issuing warp ~150-300 cycles whatever the box size, and a k-block of
+        // these skinny tiles is worth ~150 cycles of MMA issue: one warp issuing both loads of a stage was the pace-maker of
+        // every k-loop (394 cycles per k-block, profiles/r02_chain_trace_*.md).  Each warp posts its own bytes on the stage's
+        // full barrier (initialised with two arrivals).
         int stage = 0;
         uint32_t phase = 0;
-        for (int ph = p.ph_begin; ph < p.ph_end; ++ph) {
-            const ChainPhase* D = p.table + ph;
-            if (D->kind != CH_GEMM) continue;
-            const int bn = D->bn, nt = D->n_tiles_n, ksp = D->k_splits;
-            const int num_tiles = n_mt * nt * ksp, nk = D->K / CH_BK / ksp;
-            const uint32_t tx_bytes = CH_A_BYTES + (uint32_t)bn * CH_BK * 2;
-            bool need_wait = ph > p.ph_begin;    // the activations were written by the previous phase of this launch
-            if (lane == 0 && ph + 1 < p.ph_end) {
-                ptx::prefetch_tensormap(&D[1].tmA);
-                ptx::prefetch_tensormap(&D[1].tmW);
-                ch_prefetch_l1(&D[1].kind);
-            }
+        for (int i = 0; i < n_ph; ++i) {
+            const ChainPhase& D = p.ph[i];
+            if (D.kind != CH_GEMM) continue;
+            const int nt = D.n_tiles_n, ksp = D.k_splits;
+            const int num_tiles = n_mt * nt * ksp, nk = D.K / CH_BK / ksp;
+            const uint32_t a_bytes = (uint32_t)D.a_bytes;
+            bool need_wait = i > 0;    // the activations were written by the previous phase of this launch
             for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
                 const int mn = tile / ksp, ks = tile - mn * ksp;
-                const int m_blk = mn / nt, n_blk = mn - m_blk * nt;
-                int kb0 = 0;
+                const int m_blk = mn / nt;
                 if (need_wait) {
-                    // weights do not depend on the previous phase: their first tiles are in flight while we wait at the barrier
-                    const int pre = nk < CH_STAGES ? nk : CH_STAGES;
-                    const int st0 = stage;
-                    for (int i = 0; i < pre; ++i) {
-                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                        if (lane == 0) {
-                            ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
-                            ptx::tma_load_2d(smem + stage * CH_STAGE_BYTES + CH_A_BYTES, &D->tmW, &full_bar[stage],
-                                             (ks * nk + i) * CH_BK, n_blk * bn);
-                        }
-                        __syncwarp();
-                        if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
-                    }
                     if (lane == 0) {
-                        ch_grid_poll(bar, (unsigned)(ph - p.ph_begin) * grid);
+                        ch_grid_poll(bar, (unsigned)i * grid);
+                        if (tracing) p.trace[8 * (p.ph0 + i) + 2] = clock64();
                         ch_fence_proxy_async_all();
-                        int s2 = st0;
-                        for (int i = 0; i < pre; ++i) {
-                            ptx::tma_load_2d(smem + s2 * CH_STAGE_BYTES, &D->tmA, &full_bar[s2], (ks * nk + i) * CH_BK, m_blk * CH_BM);
-                            if (++s2 == CH_STAGES) s2 = 0;
-                        }
                     }
                     __syncwarp();
                     need_wait = false;
-                    kb0 = pre;
                 }
-                for (int kb = kb0; kb < nk; ++kb) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (lane == 0) {
-                        uint8_t* sa = smem + stage * CH_STAGE_BYTES;
-                        ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
-                        ptx::tma_load_2d(sa, &D->tmA, &full_bar[stage], (ks * nk + kb) * CH_BK, m_blk * CH_BM);
-                        ptx::tma_load_2d(sa + CH_A_BYTES, &D->tmW, &full_bar[stage], (ks * nk + kb) * CH_BK, n_blk * bn);
-                    }
-                    __syncwarp();
+                for (int kb = 0; kb < nk; ++kb) {
+                    ch_mbar_wait(empty_a + stage * 8, phase ^ 1);
+                    ch_expect_tx_elect(full_a + stage * 8, a_bytes);
+                    ch_tma_load_2d_elect(smem_a + stage * CH_STAGE_BYTES, &D.tmA, full_a + stage * 8, (ks * nk + kb) * CH_BK, m_blk * CH_BM);
+                    if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (tracing && lane == 0 && tile == (int)blockIdx.x) p.trace[8 * (p.ph0 + i) + 3] = clock64();
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== TMA producer of the WEIGHT tiles =====================
+        // Weights do not depend on the previous phase: this warp never looks at the grid barrier, it runs ahead as far as the
+        // ring lets it (the weight tiles of the next phase are in flight while the CTA waits for the others).
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int i = 0; i < n_ph; ++i) {
+            const ChainPhase& D = p.ph[i];
+            if (D.kind != CH_GEMM) continue;
+            const int bn = D.bn, nt = D.n_tiles_n, ksp = D.k_splits;
+            const int num_tiles = n_mt * nt * ksp, nk = D.K / CH_BK / ksp;
+            const uint32_t w_bytes = (uint32_t)bn * CH_BK * 2;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
+                const int mn = tile / ksp, ks = tile - mn * ksp;
+                const int n_blk = mn % nt;
+                for (int kb = 0; kb < nk; ++kb) {
+                    ch_mbar_wait(empty_a + stage * 8, phase ^ 1);
+                    ch_expect_tx_elect(full_a + stage * 8, w_bytes);
+                    ch_tma_load_2d_elect(smem_a + stage * CH_STAGE_BYTES + CH_A_BYTES, &D.tmW, full_a + stage * 8,
+                                         (ks * nk + kb) * CH_BK, n_blk * bn);
                     if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
+    } else if (warp == 3) {
+        // ===================== L2 prefetcher =====================
+        // The weights of a decode step are read once per step and never hit L2 on their own (tens of GB of K/V stream through
+        // it in between).  Every weight box this CTA will load in ANY phase of the launch is requested into L2 right away: the
+        // launch streams its weights at HBM speed while the first phases run, the later k-loops run at L2 latency.
+        // LayerNorm / bias vectors likewise.
+        if (lane < n_ph && p.ph[lane].kind == CH_GEMM) {
+            ptx::prefetch_tensormap(&p.ph[lane].tmA);
+            ptx::prefetch_tensormap(&p.ph[lane].tmW);
+        }
+        for (int i = 0; i < n_ph; ++i) {
+            const ChainPhase& D = p.ph[i];
+            if (D.kind == CH_GEMM) {
+                const int bn = D.bn, nt = D.n_tiles_n, ksp = D.k_splits;
+                const int num_tiles = n_mt * nt * ksp, nk = D.K / CH_BK / ksp;
+                for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {   // (row tiles sharing a weight box: an L2 hit)
+                    const int mn = tile / ksp, ks = tile - mn * ksp;
+                    const int n_blk = mn % nt;
+                    for (int kb = lane; kb < nk; kb += 32) ch_tma_prefetch_2d(&D.tmW, (ks * nk + kb) * CH_BK, n_blk * bn);
+                }
+                if (D.bias != nullptr)
+                    for (int j = lane * 32; j < D.N; j += 32 * 32) ch_prefetch_l2(D.bias + j);
+            } else {
+                for (int j = lane * 32; j < p.d; j += 32 * 32) {
+                    ch_prefetch_l2(D.gamma + j);
+                    ch_prefetch_l2(D.beta + j);
+                    if (D.bias != nullptr) ch_prefetch_l2(D.bias + j);
+                }
+            }
+        }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer (converged warp, elected lane issues) =====================
+        // tcgen05.mma / tcgen05.commit take their operands from UNIFORM registers: the loop state below is derived from kernel
+        // parameters and uniform counters only, so the descriptors are computed on the uniform datapath.
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int ph = p.ph_begin; ph < p.ph_end; ++ph) {
-            const ChainPhase* D = p.table + ph;
-            if (D->kind != CH_GEMM) continue;
-            const int bn = D->bn, ksp = D->k_splits;
-            const int num_tiles = n_mt * D->n_tiles_n * ksp, nk = D->K / CH_BK / ksp;
+        for (int i = 0; i < n_ph; ++i) {
+            const ChainPhase& D = p.ph[i];
+            if (D.kind != CH_GEMM) continue;
+            const int bn = D.bn, ksp = D.k_splits;
+            const int num_tiles = n_mt * D.n_tiles_n * ksp, nk = D.K / CH_BK / ksp;
             const uint32_t idesc = ptx::make_idesc_bf16(CH_BM, (uint32_t)bn, 0, 0);
             for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
-                ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue drained this accumulator
+                ch_mbar_wait(tempty_a + acc * 8, acc_phase ^ 1);   // epilogue drained this accumulator
                 ptx::tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * CH_MAX_BN;
+                const uint32_t d_tmem = tmem_u + acc * CH_MAX_BN;
                 for (int kb = 0; kb < nk; ++kb) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ch_mbar_wait(full_a + stage * 8, phase);
                     ptx::tcgen05_fence_after();
-                    if (lane == 0) {
-                        const uint32_t sa = ptx::smem_u32(smem + stage * CH_STAGE_BYTES);
-                        const uint64_t da = ptx::make_smem_desc_sw128(sa, 1024, 16);
-                        const uint64_t db = ptx::make_smem_desc_sw128(sa + CH_A_BYTES, 1024, 16);
-#pragma unroll
-                        for (int k = 0; k < CH_BK / 16; ++k) ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                        ptx::umma_commit(&empty_bar[stage]);
-                        if (kb == nk - 1) ptx::umma_commit(&tmem_full_bar[acc]);
+                    if (tracing && lane == 0) {
+                        if (kb == 0 && tile == (int)blockIdx.x) p.trace[8 * (p.ph0 + i) + 4] = clock64();
+                        if (p.ph0 + i == 16 && kb < 32) p.trace[4096 + 2 * kb] = clock64();   // (dev) k-block timeline of fc1, layer 1
                     }
-                    __syncwarp();
+                    const uint32_t sa = smem_a + stage * CH_STAGE_BYTES;
+                    const uint64_t da = ptx::make_smem_desc_sw128(sa, 1024, 16);
+                    const uint64_t db = ptx::make_smem_desc_sw128(sa + CH_A_BYTES, 1024, 16);
+                    ptx::umma_f16_elect(d_tmem, da, db, idesc, kb != 0);
+                    ptx::umma_f16_elect(d_tmem, da + 2, db + 2, idesc, 1);
+                    ptx::umma_f16_elect(d_tmem, da + 4, db + 4, idesc, 1);
+                    ptx::umma_f16_elect(d_tmem, da + 6, db + 6, idesc, 1);
+                    ptx::umma_commit_elect(empty_a + stage * 8);
+                    if (kb == nk - 1) ptx::umma_commit_elect(tfull_a + acc * 8);
+                    if (tracing && lane == 0 && p.ph0 + i == 16 && kb < 32) p.trace[4096 + 2 * kb + 1] = clock64();
                     if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -241,23 +344,30 @@ __global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const Chain
         const int half = (warp - 4) >> 2;       // column-slab share (GEMM) / row group (LN)
         float4* st4 = reinterpret_cast<float4*>(staging + (warp - 4) * 32 * 32);
         const int rrow = lane >> 3, rchunk = lane & 7;
+        long long* const trace = (tracing && et == 0) ? p.trace + 8 * p.ph0 : nullptr;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int ph = p.ph_begin; ph < p.ph_end; ++ph) {
-            const ChainPhase* D = p.table + ph;
-            if (lane == 0 && ph + 1 < p.ph_end) ch_prefetch_l1(&D[1].kind);
-            if (D->kind == CH_GEMM) {
-                const int bn = D->bn, nt = D->n_tiles_n, ksp = D->k_splits, N = D->N, epi = D->epi;
+        for (int i = 0; i < n_ph; ++i) {
+            const ChainPhase& D = p.ph[i];
+            // The barrier word is ONE monotonic counter: it is only meaningful if no CTA arrives for phase i before every CTA
+            // has arrived for phase i - 1.  So the thread that arrives for this CTA waits for the previous barrier at the start
+            // of EVERY phase, also in CTAs that have no tile of it (they must not run ahead and be counted twice).
+            if (trace != nullptr) trace[8 * i + 0] = clock64();
+            if (i > 0 && et == 0) ch_grid_poll(bar, (unsigned)i * grid);
+            if (trace != nullptr) trace[8 * i + 1] = clock64();
+            if (D.kind == CH_GEMM) {
+                const int bn = D.bn, nt = D.n_tiles_n, ksp = D.k_splits, N = D.N, epi = D.epi;
                 const int num_tiles = n_mt * nt * ksp;
                 const int slabs = bn >> 5, spw = (slabs + 1) >> 1;
-                const float* __restrict__ bias = D->bias;
-                const long long ldo = D->ldo, sstride = D->split_stride;
-                void* const outp = D->out;
+                const float* __restrict__ bias = D.bias;
+                const long long ldo = D.ldo, sstride = D.split_stride;
+                void* const outp = D.out;
                 for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
                     const int mn = tile / ksp, ks = tile - mn * ksp;
                     const int m_blk = mn / nt, n_blk = mn - m_blk * nt;
-                    ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+                    ch_mbar_wait(tfull_a + acc * 8, acc_phase);
                     ptx::tcgen05_fence_after();
+                    if (trace != nullptr && tile == (int)blockIdx.x) trace[8 * i + 5] = clock64();
                     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * CH_MAX_BN;
                     const int row0 = m_blk * CH_BM + q * 32;
 #pragma unroll 1
@@ -277,8 +387,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const Chain
                         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (epi != CH_EPI_PARTIAL && bias != nullptr && col_ok) bb = __ldg(reinterpret_cast<const float4*>(bias + n0));
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int rr = i * 4 + rrow;
+                        for (int r8 = 0; r8 < 8; ++r8) {
+                            const int rr = r8 * 4 + rrow;
                             const int row = row0 + rr;
                             const float4 f = st4[rr * 8 + (rchunk ^ (rr & 7))];
                             if (row < p.M && col_ok) {
@@ -307,20 +417,17 @@ __global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const Chain
                 }
             } else {
                 // ---- LayerNorm phase: x[r] += bias + sum of slabs (fixed order); out[r] = LN(x[r]) as bf16
-                if (ph > p.ph_begin) {
-                    if (et == 0) ch_grid_poll(bar, (unsigned)(ph - p.ph_begin) * grid);
-                    ch_named_bar(1, CH_EPI_WARPS * 32);
-                }
+                if (i > 0) ch_named_bar(1, CH_EPI_WARPS * 32);   // thread 0 of the group has seen the barrier (above)
                 const int d = p.d, nvec = d >> 2;
                 const int gt = et & 127, gw = gt >> 5;              // thread / warp inside the 128-thread row group
-                const int n_parts = D->n_parts;
-                const long long pstride = D->split_stride;
-                float* const xp = D->x;
-                const float* const partp = D->parts;
-                const float4* const biasp = reinterpret_cast<const float4*>(D->bias);
-                const float4* const gammap = reinterpret_cast<const float4*>(D->gamma);
-                const float4* const betap = reinterpret_cast<const float4*>(D->beta);
-                bf16* const lnout = reinterpret_cast<bf16*>(D->out);
+                const int n_parts = D.n_parts;
+                const long long pstride = D.split_stride;
+                float* const xp = D.x;
+                const float* const partp = D.parts;
+                const float4* const biasp = reinterpret_cast<const float4*>(D.bias);
+                const float4* const gammap = reinterpret_cast<const float4*>(D.gamma);
+                const float4* const betap = reinterpret_cast<const float4*>(D.beta);
+                bf16* const lnout = reinterpret_cast<bf16*>(D.out);
                 float* red0 = ln_red + half * 8;
                 float* red1 = red0 + 4;
                 const float inv_d = 1.0f / (float)d;
@@ -382,12 +489,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const Chain
                 }
             }
             // ---- this CTA's share of the phase is written: arrive at the grid barrier (the last phase needs none)
-            if (ph + 1 < p.ph_end) {
+            if (trace != nullptr) trace[8 * i + 6] = clock64();
+            if (i + 1 < n_ph) {
                 ch_named_bar(1, CH_EPI_WARPS * 32);
                 if (et == 0) {
-                    __threadfence();
+                    // bar.sync ordered the group's writes before this thread; the release below is cumulative at gpu scope
                     ch_fence_proxy_async_all();   // the next phase reads these rows through TMA
                     ch_red_release(bar, 1u);
+                    if (trace != nullptr) trace[8 * i + 7] = clock64();
                 }
             }
         }
@@ -396,27 +505,34 @@ __global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const Chain
     ptx::tcgen05_fence_before();
     __syncthreads();
     if (warp == 2) ptx::tmem_dealloc<CH_TMEM_COLS>(tmem_base);
-    // leave the barrier counter at zero for the next launch: the last CTA to get here resets it (nobody polls it any more:
-    // a CTA gets here only after all of its warps have passed every poll of the launch)
+    // leave the counters at zero for the next launch: the last CTA to get here resets them (nobody polls any more: a CTA gets
+    // here only after all of its warps have passed every poll of the launch)
     if (threadIdx.x == 0) {
-        const unsigned total = (unsigned)(p.ph_end - p.ph_begin) * grid;
-        const unsigned old = atomicAdd(bar, 1u);
-        if (old == total - 1) atomicExch(bar, 0u);
+        const unsigned old = atomicAdd(bar + 1, 1u);   // exit counter: separate word, exits must not be mistaken for arrivals
+        if (old == grid - 1) {
+            atomicExch(bar, 0u);
+            atomicExch(bar + 1, 0u);
+        }
     }
 }
 
 // tile width / split-K of one chain GEMM: same cost model as gemm_tc.cu pick_config (skinny M: bytes a CTA has to pull, one
 // wave, the partial slabs its consumer re-reads), tile width limited to CH_MAX_BN
-void pick_chain_config(int M, int N, int K, int max_splits, int sms, int& bn_out, int& splits_out) {
+void pick_chain_config(int M, int a_rows, int N, int K, int max_splits, int sms, int& bn_out, int& splits_out) {
     const int mt = ceil_div(M, CH_BM), nkb = K / CH_BK;
     double best = 1e30;
     bn_out = 32; splits_out = 1;
+    // (dev) WB_CHAIN_BN / WB_CHAIN_SPLITS: force the tile width / cap the split count
+    static const int force_bn = std::getenv("WB_CHAIN_BN") ? std::atoi(std::getenv("WB_CHAIN_BN")) : 0;
+    static const int cap_splits = std::getenv("WB_CHAIN_SPLITS") ? std::atoi(std::getenv("WB_CHAIN_SPLITS")) : 0;
+    if (cap_splits > 0) max_splits = std::min(max_splits, cap_splits);
     for (int bn : {32, 64, 128}) {
+        if (force_bn > 0 && bn != force_bn) continue;
         for (int s = 1; s <= max_splits; s *= 2) {
             if (nkb % s != 0) continue;
             const long long ctas = (long long)mt * ceil_div(N, bn) * s;
             const double waves = (double)((ctas + sms - 1) / sms);
-            const double ingest = (double)(CH_BM + bn) * (K / s) * 2.0;
+            const double ingest = (double)(a_rows + bn) * (K / s) * 2.0;
             const double partial = s > 1 ? (double)M * N * 4.0 * s * 2.0 / 6000.0 : 0.0;
             const double t = waves * (ingest / 40.0 + 1500.0) + partial;
             if (t < best) { best = t; bn_out = bn; splits_out = s; }
@@ -425,7 +541,7 @@ void pick_chain_config(int M, int N, int K, int max_splits, int sms, int& bn_out
 }
 }  // namespace
 
-size_t chain_table_bytes(int dec_layers) { return (size_t)(2 + 9 * dec_layers) * sizeof(ChainPhase); }
+size_t chain_table_bytes(int dec_layers) { return (size_t)(2 + 9 * dec_layers) * sizeof(ChainPhase); }   // host table
 size_t chain_sync_bytes() { return 256; }
 
 static bool& chain_enabled() {
@@ -437,7 +553,7 @@ bool chain_path_enabled() { return chain_enabled(); }
 
 bool Session::chain_supported() const {
     const ModelConfig& g = m->cfg;
-    return chain_table != nullptr && m->dtype == BF16 && batch >= 1 && g.d_model % 64 == 0 && g.d_model <= 1024 && g.ffn % 64 == 0 &&
+    return chain_sync != nullptr && m->dtype == BF16 && batch >= 1 && g.d_model % 64 == 0 && g.d_model <= 1024 && g.ffn % 64 == 0 &&
            chain_grid > 0;
 }
 
@@ -447,17 +563,22 @@ bool Session::chain_supported() const {
 void Session::build_chain_table() {
     const ModelConfig& g = m->cfg;
     const int d = g.d_model, B = batch, L = g.dec_layers;
-    WB_REQUIRE(chain_grid > 0 && chain_table != nullptr, "fused chains: no table");
-    std::vector<ChainPhase> t((size_t)2 + 9 * L);
-    std::memset(t.data(), 0, t.size() * sizeof(ChainPhase));
+    WB_REQUIRE(chain_grid > 0, "fused chains are not available on this device");
+    chain_host.assign(chain_table_bytes(L), 0);
+    ChainPhase* t = reinterpret_cast<ChainPhase*>(chain_host.data());
     const long long part_stride = (long long)B * d;
+    // Only the activation rows that exist travel: a CTA's k-loop is bound by the boxes it pulls (~600 cycles per 24 KB stage
+    // with every SM pulling: the chip-wide L2 throughput cap, tools/chain_trace.py), and rows past the batch are never stored.
+    // (The MMA still covers 128 rows: the rest of the tile holds stale shared memory, rows are independent.)
+    const int a_rows = B >= CH_BM ? CH_BM : (B + 7) / 8 * 8;
     auto gemm_phase = [&](ChainPhase& o, const void* A, int K, const Linear& l, int epi, void* out, long long ldo) -> int {
         WB_REQUIRE(l.k == K && K % CH_BK == 0 && l.n % 8 == 0, "fused chains: unsupported Linear shape");
         int bn = 64, splits = 1;
-        pick_chain_config(B, l.n, K, epi == CH_EPI_PARTIAL ? MAX_K_SPLITS : 1, chain_grid, bn, splits);
+        pick_chain_config(B, a_rows, l.n, K, epi == CH_EPI_PARTIAL ? MAX_K_SPLITS : 1, chain_grid, bn, splits);
         o.kind = CH_GEMM; o.bn = bn; o.K = K; o.N = l.n; o.n_tiles_n = ceil_div(l.n, bn); o.k_splits = splits; o.epi = epi;
         o.split_stride = part_stride; o.ldo = ldo; o.bias = epi == CH_EPI_PARTIAL ? nullptr : l.b; o.out = out;
-        o.tmA = make_tmap_bf16_2d(A, K, B, K, CH_BM);
+        o.tmA = make_tmap_bf16_2d(A, K, B, K, a_rows);
+        o.a_bytes = a_rows * CH_BK * 2;
         o.tmW = make_tmap_bf16_2d(l.w, l.k, l.n, l.k, bn);
         return splits;
     };
@@ -485,14 +606,13 @@ void Session::build_chain_table() {
             ln_phase(o[7], m->dec_ln, s, Y.fc2.b);
         }
     }
-    WB_CHECK_CUDA(cudaMemcpy(chain_table, t.data(), t.size() * sizeof(ChainPhase), cudaMemcpyHostToDevice));
     chain_batch = B;
 }
 
 void Session::init_chain() {
     chain_grid = 0;
     chain_batch = -1;
-    if (m->dtype != BF16 || chain_table == nullptr) return;
+    if (m->dtype != BF16 || chain_sync == nullptr) return;
     int dev = 0, sms = 0;
     WB_CHECK_CUDA(cudaGetDevice(&dev));
     WB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -505,10 +625,18 @@ void Session::init_chain() {
 }
 
 void Session::launch_chain(int ph_begin, int ph_end, cudaStream_t st) {
-    ChainParams p{};
-    p.table = reinterpret_cast<const ChainPhase*>(chain_table);
-    p.ph_begin = ph_begin; p.ph_end = ph_end; p.M = batch; p.d = m->cfg.d_model; p.eps = 1e-5f;
-    p.state = state; p.sync = chain_sync;
+    static const bool serial = std::getenv("WB_CHAIN_SERIAL") != nullptr;   // (dev) one launch per phase: kernel boundaries instead of grid barriers
+    if (serial && ph_end - ph_begin > 1) {
+        for (int ph = ph_begin; ph < ph_end; ++ph) launch_chain(ph, ph + 1, st);
+        return;
+    }
+    WB_REQUIRE(ph_end > ph_begin && ph_end - ph_begin <= CH_MAX_PHASES && (size_t)ph_end * sizeof(ChainPhase) <= chain_host.size(),
+               "fused chains: bad phase range");
+    ChainParams p;
+    std::memset(&p, 0, sizeof(p));
+    std::memcpy(p.ph, chain_host.data() + (size_t)ph_begin * sizeof(ChainPhase), (size_t)(ph_end - ph_begin) * sizeof(ChainPhase));
+    p.n_ph = ph_end - ph_begin; p.ph0 = ph_begin; p.M = batch; p.d = m->cfg.d_model; p.eps = 1e-5f;
+    p.state = state; p.sync = chain_sync; p.trace = step_trace_ptr();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(chain_grid);
     cfg.blockDim = dim3(CH_THREADS);

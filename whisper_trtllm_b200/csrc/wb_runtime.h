@@ -86,8 +86,8 @@ struct Buffers {
     // whole-step kernel (step_mega.cu): attention partials of split items, grid-barrier / per-item arrival counters
     float* mega_part = nullptr; unsigned* mega_sync = nullptr; void* mega_table = nullptr;
     int* result_tokens = nullptr;   // [max_batch, max_tgt] ids in ORIGINAL row order once rows have been compacted away
-    // fused decode chains (step_chain.cu): phase descriptors (tensor maps included) and the grid-barrier word
-    void* chain_table = nullptr; unsigned* chain_sync = nullptr;
+    // fused decode chains (step_chain.cu): the grid-barrier words
+    unsigned* chain_sync = nullptr;
 };
 size_t mega_part_bytes(int max_batch, int heads);
 size_t mega_sync_bytes(int max_batch, int heads);
@@ -158,6 +158,7 @@ struct Session : Buffers {
     void prepare_step(cudaStream_t s);        // host-side work a step needs OUTSIDE a graph capture (phase table, embedding in dx)
     int chain_grid = 0, chain_batch = -1;
     std::vector<int> chain_q_parts;           // split-K slabs of each layer's cross-attention q projection
+    std::vector<unsigned char> chain_host;    // phase descriptors of the step (tensor maps included); a launch copies its slice into its kernel parameters
     int decode_run(int max_steps, int check_every, cudaStream_t s);  // returns final length (syncs)
     // Finished-row compaction: utterances that emitted EOS leave the decode batch; the rows still running
     // move to the front (ids, page-table rows, cross K/V rows) and the following steps run on `batch` = their number.
