@@ -87,6 +87,13 @@ def main():
     for k in range(9):
         c = max(cnt[k], 1)
         print(f"| {NAMES[k]} | {cnt[k]} | " + " | ".join(f"{v / c:.0f}" for v in acc[k]) + " |")
+    print("\nLayerNorm phases, CTA 0 (cycles): leader past barrier -> loads issued -> landed + warp sum -> statistics done -> rows written")
+    for k in (1, 4, 7):
+        d = [0.0] * 4
+        for l in range(L):
+            ss = t[8 * (2 + 9 * l + k): 8 * (2 + 9 * l + k) + 8]
+            d[0] += ss[2] - ss[1]; d[1] += ss[3] - ss[2]; d[2] += ss[4] - ss[3]; d[3] += ss[6] - ss[4]
+        print(f"| {NAMES[k]} | " + " | ".join(f"{v / L:.0f}" for v in d) + " |")
     # per-launch spans: first stamp of the first phase to the last stamp of the last phase
     spans2 = [t[8 * (2 + 9 * l + 2) + 6] - t[8 * (2 + 9 * l)] for l in range(L)]
     spans3 = [t[8 * (2 + 9 * l + (8 if l < L - 1 else 7)) + 6] - t[8 * (2 + 9 * l + 3)] for l in range(L)]
@@ -94,11 +101,14 @@ def main():
           f"(from the epilogue leader's first stamp: the kernel prologue is not included)")
     if t[4096] != 0:
         base = t[8 * 16]
-        print("\nk-block timeline of phase 16 (fc1, layer 1), cycles since the phase start of the epilogue leader:")
-        print("| kb | data landed (MMA warp) | MMAs issued | stage free again (producer) |")
-        print("|---|---|---|---|")
-        for kb in range(16):
-            print(f"| {kb} | {t[4096 + 2 * kb] - base} | {t[4096 + 2 * kb + 1] - base} | {t[4096 + 64 + kb] - base if t[4096 + 64 + kb] else '-'} |")
+        print("\nring-stage timeline of phase 16 (fc1, layer 1; one stage = one group of k-blocks), cycles since the phase start of the "
+              "epilogue leader:")
+        print("| stage | data landed (MMA warp) | MMAs issued |")
+        print("|---|---|---|")
+        for kb in range(32):
+            if t[4096 + 2 * kb] == 0:
+                break
+            print(f"| {kb} | {t[4096 + 2 * kb] - base} | {t[4096 + 2 * kb + 1] - base} |")
     eng.close()
 
 

@@ -285,6 +285,25 @@ CUtensorMap make_tmap_bf16_2d(const void* ptr, long long ld_elems, int rows, int
     return m;
 }
 
+// The same row-major bf16 [rows, cols] matrix seen as a 3-D tensor {64 (k inside a k-block), rows, cols / 64 (k-block)} with
+// 128-byte swizzle: a box {64, box_rows, box_k} lands in shared memory as box_k consecutive [box_rows x 128 B] K-major swizzled
+// slices - box_k k-blocks of a GEMM operand with ONE TMA operation (decode chains, step_chain.cu).
+CUtensorMap make_tmap_bf16_kgroups(const void* ptr, long long ld_elems, int rows, int cols, int box_rows, int box_k) {
+    WB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base must be 16-byte aligned");
+    WB_REQUIRE((ld_elems * 2) % 16 == 0 && cols % 64 == 0, "TMA row pitch must be a multiple of 16 bytes, K a multiple of 64");
+    WB_REQUIRE(box_rows >= 1 && box_rows <= 256 && box_k >= 1 && box_k <= cols / 64, "bad TMA box");
+    CUtensorMap m;
+    cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)(cols / 64)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld_elems * 2, 128};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)box_k};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error(-3, "cuTensorMapEncodeTiled (3-D) failed with code " + std::to_string((int)r));
+    return m;
+}
+
 int sm_count() {
     static int n = 0;
     if (n == 0) {

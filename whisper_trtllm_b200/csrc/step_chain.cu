@@ -31,14 +31,17 @@
 
 namespace wb {
 
-CUtensorMap make_tmap_bf16_2d(const void* ptr, long long ld_elems, int rows, int cols, int box_rows);   // gemm_tc.cu
+CUtensorMap make_tmap_bf16_kgroups(const void* ptr, long long ld_elems, int rows, int cols, int box_rows, int box_k);   // gemm_tc.cu
 long long*& step_trace_ptr();                                                                            // step_mega.cu
 
 namespace {
 constexpr int CH_BM = 128, CH_BK = 64, CH_MAX_BN = 128;
-constexpr int CH_STAGES = 6;
-constexpr uint32_t CH_A_BYTES = CH_BM * CH_BK * 2;                 // 16 KB
-constexpr uint32_t CH_STAGE_BYTES = CH_A_BYTES + CH_MAX_BN * CH_BK * 2;   // 32 KB
+// One stage of the ring holds a GROUP of kgroup consecutive k-blocks: [kgroup activation slices | kgroup weight slices], each
+// fetched by ONE TMA operation (3-D tensor maps: {64 k, rows, k-block}).  The TMA unit of an SM completes roughly one operation
+// per ~200 cycles whatever its box size (two per k-block made every k-loop run at 395 cycles per k-block, B and tile width
+// regardless: profiles/r02_chain_trace_*_v3_uniform_issue.md), so the boxes are made as deep as a 48 KB stage allows.
+constexpr int CH_STAGES = 4;
+constexpr uint32_t CH_STAGE_BYTES = 48 * 1024;
 constexpr int CH_EPI_WARPS = 8;
 constexpr int CH_THREADS = (4 + CH_EPI_WARPS) * 32;                // 384
 constexpr uint32_t CH_STAGING_BYTES = CH_EPI_WARPS * 32 * 32 * 4;  // one 32x32 fp32 transpose tile per epilogue warp
@@ -52,12 +55,14 @@ enum { CH_EPI_PARTIAL = 0, CH_EPI_BF16 = 1, CH_EPI_GELU_BF16 = 2 };
 // One phase of a chain.  GEMM: out = epi(A[M, K] W[N, K]^T) on 128 x bn tiles, k_splits slabs; LN: the consumer side of a
 // split-K GEMM fused with the LayerNorm in front of the next Linear.
 struct alignas(128) ChainPhase {
-    CUtensorMap tmA;            // activations [M, K] bf16, box {64, 128}
-    CUtensorMap tmW;            // weights [N, K] bf16, box {64, bn}
+    CUtensorMap tmA;            // activations [M, K] bf16 as {64, M, K / 64}, box {64, a_rows, kgroup}
+    CUtensorMap tmW;            // weights [N, K] bf16 as {64, N, K / 64}, box {64, bn, kgroup}
     int kind;
     int bn, K, N, n_tiles_n, k_splits, epi;
     int n_parts;                // LN: slabs to add to x (0: plain LayerNorm of x)
-    int a_bytes;                // GEMM: bytes of one activation box ({64, a_rows}: only the rows that exist are loaded)
+    int a_bytes;                // GEMM: bytes of one activation box ({64, a_rows, kgroup}: only the rows that exist are loaded)
+    int kgroup;                 // GEMM: k-blocks per TMA operation / ring stage
+    int w_off;                  // GEMM: byte offset of the weight slices inside a stage (= a_bytes)
     long long split_stride;     // GEMM (partial epilogue) / LN: floats between consecutive slabs
     long long ldo;              // GEMM: elements between output rows
     const float* bias;          // GEMM: epilogue bias (bf16 epilogues); LN: bias of the split-K GEMM that produced the slabs
@@ -65,7 +70,7 @@ struct alignas(128) ChainPhase {
     const float* parts;         // LN: slabs
     const float* gamma; const float* beta;
     float* x;                   // LN: fp32 residual stream [M, d], updated in place
-    int pad[6];
+    int pad[4];
 };
 static_assert(sizeof(ChainPhase) == 384, "ChainPhase layout");
 
@@ -104,13 +109,18 @@ __device__ __forceinline__ float4 ch_ld_cg_f4(const float* p) {   // written by 
 }
 // Converged-warp TMA forms (see ptx::umma_f16_elect): every lane executes the call with warp-uniform operands, the elected
 // lane issues; operands stay in uniform registers.
-__device__ __forceinline__ void ch_tma_load_2d_elect(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+__device__ __forceinline__ void ch_tma_load_3d_elect(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
         "{\n\t.reg .pred q;\n\t"
         "elect.sync _|q, 0xffffffff;\n\t"
-        "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
-        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+// TMA prefetch of one box into L2 (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void ch_tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void ch_expect_tx_elect(uint32_t bar, uint32_t bytes) {
     asm volatile(
@@ -118,11 +128,6 @@ __device__ __forceinline__ void ch_expect_tx_elect(uint32_t bar, uint32_t bytes)
         "elect.sync _|q, 0xffffffff;\n\t"
         "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
         ::"r"(bar), "r"(bytes) : "memory");
-}
-// TMA prefetch of one box into L2 (no shared-memory destination, no completion tracking)
-__device__ __forceinline__ void ch_tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
-                 : "memory");
 }
 __device__ __forceinline__ void ch_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void ch_named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
@@ -217,8 +222,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const __gri
         for (int i = 0; i < n_ph; ++i) {
             const ChainPhase& D = p.ph[i];
             if (D.kind != CH_GEMM) continue;
-            const int nt = D.n_tiles_n, ksp = D.k_splits;
-            const int num_tiles = n_mt * nt * ksp, nk = D.K / CH_BK / ksp;
+            const int nt = D.n_tiles_n, ksp = D.k_splits, kg = D.kgroup;
+            const int num_tiles = n_mt * nt * ksp, nk = D.K / CH_BK / ksp, ng = nk / kg;
             const uint32_t a_bytes = (uint32_t)D.a_bytes;
             bool need_wait = i > 0;    // the activations were written by the previous phase of this launch
             for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
@@ -233,10 +238,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const __gri
                     __syncwarp();
                     need_wait = false;
                 }
-                for (int kb = 0; kb < nk; ++kb) {
+                for (int g = 0; g < ng; ++g) {
                     ch_mbar_wait(empty_a + stage * 8, phase ^ 1);
                     ch_expect_tx_elect(full_a + stage * 8, a_bytes);
-                    ch_tma_load_2d_elect(smem_a + stage * CH_STAGE_BYTES, &D.tmA, full_a + stage * 8, (ks * nk + kb) * CH_BK, m_blk * CH_BM);
+                    ch_tma_load_3d_elect(smem_a + stage * CH_STAGE_BYTES, &D.tmA, full_a + stage * 8, 0, m_blk * CH_BM, ks * nk + g * kg);
                     if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
                 }
                 if (tracing && lane == 0 && tile == (int)blockIdx.x) p.trace[8 * (p.ph0 + i) + 3] = clock64();
@@ -251,17 +256,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const __gri
         for (int i = 0; i < n_ph; ++i) {
             const ChainPhase& D = p.ph[i];
             if (D.kind != CH_GEMM) continue;
-            const int bn = D.bn, nt = D.n_tiles_n, ksp = D.k_splits;
-            const int num_tiles = n_mt * nt * ksp, nk = D.K / CH_BK / ksp;
-            const uint32_t w_bytes = (uint32_t)bn * CH_BK * 2;
+            const int bn = D.bn, nt = D.n_tiles_n, ksp = D.k_splits, kg = D.kgroup;
+            const int num_tiles = n_mt * nt * ksp, nk = D.K / CH_BK / ksp, ng = nk / kg;
+            const uint32_t w_bytes = (uint32_t)(bn * kg) * CH_BK * 2, w_off = (uint32_t)D.w_off;
             for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
                 const int mn = tile / ksp, ks = tile - mn * ksp;
                 const int n_blk = mn % nt;
-                for (int kb = 0; kb < nk; ++kb) {
+                for (int g = 0; g < ng; ++g) {
                     ch_mbar_wait(empty_a + stage * 8, phase ^ 1);
                     ch_expect_tx_elect(full_a + stage * 8, w_bytes);
-                    ch_tma_load_2d_elect(smem_a + stage * CH_STAGE_BYTES + CH_A_BYTES, &D.tmW, full_a + stage * 8,
-                                         (ks * nk + kb) * CH_BK, n_blk * bn);
+                    ch_tma_load_3d_elect(smem_a + stage * CH_STAGE_BYTES + w_off, &D.tmW, full_a + stage * 8, 0, n_blk * bn, ks * nk + g * kg);
                     if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -279,12 +283,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const __gri
         for (int i = 0; i < n_ph; ++i) {
             const ChainPhase& D = p.ph[i];
             if (D.kind == CH_GEMM) {
-                const int bn = D.bn, nt = D.n_tiles_n, ksp = D.k_splits;
-                const int num_tiles = n_mt * nt * ksp, nk = D.K / CH_BK / ksp;
+                const int bn = D.bn, nt = D.n_tiles_n, ksp = D.k_splits, kg = D.kgroup;
+                const int num_tiles = n_mt * nt * ksp, nk = D.K / CH_BK / ksp, ng = nk / kg;
                 for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {   // (row tiles sharing a weight box: an L2 hit)
                     const int mn = tile / ksp, ks = tile - mn * ksp;
                     const int n_blk = mn % nt;
-                    for (int kb = lane; kb < nk; kb += 32) ch_tma_prefetch_2d(&D.tmW, (ks * nk + kb) * CH_BK, n_blk * bn);
+                    for (int g = lane; g < ng; g += 32) ch_tma_prefetch_3d(&D.tmW, 0, n_blk * bn, ks * nk + g * kg);
                 }
                 if (D.bias != nullptr)
                     for (int j = lane * 32; j < D.N; j += 32 * 32) ch_prefetch_l2(D.bias + j);
@@ -308,30 +312,33 @@ __global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const __gri
         for (int i = 0; i < n_ph; ++i) {
             const ChainPhase& D = p.ph[i];
             if (D.kind != CH_GEMM) continue;
-            const int bn = D.bn, ksp = D.k_splits;
-            const int num_tiles = n_mt * D.n_tiles_n * ksp, nk = D.K / CH_BK / ksp;
+            const int bn = D.bn, ksp = D.k_splits, kg = D.kgroup;
+            const int num_tiles = n_mt * D.n_tiles_n * ksp, nk = D.K / CH_BK / ksp, ng = nk / kg;
             const uint32_t idesc = ptx::make_idesc_bf16(CH_BM, (uint32_t)bn, 0, 0);
+            const uint32_t a_slice = (uint32_t)D.a_bytes / (uint32_t)kg, w_slice = (uint32_t)bn * CH_BK * 2, w_off = (uint32_t)D.w_off;
             for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
                 ch_mbar_wait(tempty_a + acc * 8, acc_phase ^ 1);   // epilogue drained this accumulator
                 ptx::tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_u + acc * CH_MAX_BN;
-                for (int kb = 0; kb < nk; ++kb) {
+                for (int g = 0; g < ng; ++g) {
                     ch_mbar_wait(full_a + stage * 8, phase);
                     ptx::tcgen05_fence_after();
                     if (tracing && lane == 0) {
-                        if (kb == 0 && tile == (int)blockIdx.x) p.trace[8 * (p.ph0 + i) + 4] = clock64();
-                        if (p.ph0 + i == 16 && kb < 32) p.trace[4096 + 2 * kb] = clock64();   // (dev) k-block timeline of fc1, layer 1
+                        if (g == 0 && tile == (int)blockIdx.x) p.trace[8 * (p.ph0 + i) + 4] = clock64();
+                        if (p.ph0 + i == 16 && g < 32) p.trace[4096 + 2 * g] = clock64();   // (dev) ring-stage timeline of fc1, layer 1
                     }
                     const uint32_t sa = smem_a + stage * CH_STAGE_BYTES;
-                    const uint64_t da = ptx::make_smem_desc_sw128(sa, 1024, 16);
-                    const uint64_t db = ptx::make_smem_desc_sw128(sa + CH_A_BYTES, 1024, 16);
-                    ptx::umma_f16_elect(d_tmem, da, db, idesc, kb != 0);
-                    ptx::umma_f16_elect(d_tmem, da + 2, db + 2, idesc, 1);
-                    ptx::umma_f16_elect(d_tmem, da + 4, db + 4, idesc, 1);
-                    ptx::umma_f16_elect(d_tmem, da + 6, db + 6, idesc, 1);
+                    for (int sl = 0; sl < kg; ++sl) {
+                        const uint64_t da = ptx::make_smem_desc_sw128(sa + sl * a_slice, 1024, 16);
+                        const uint64_t db = ptx::make_smem_desc_sw128(sa + w_off + sl * w_slice, 1024, 16);
+                        ptx::umma_f16_elect(d_tmem, da, db, idesc, (g | sl) != 0);
+                        ptx::umma_f16_elect(d_tmem, da + 2, db + 2, idesc, 1);
+                        ptx::umma_f16_elect(d_tmem, da + 4, db + 4, idesc, 1);
+                        ptx::umma_f16_elect(d_tmem, da + 6, db + 6, idesc, 1);
+                    }
                     ptx::umma_commit_elect(empty_a + stage * 8);
-                    if (kb == nk - 1) ptx::umma_commit_elect(tfull_a + acc * 8);
-                    if (tracing && lane == 0 && p.ph0 + i == 16 && kb < 32) p.trace[4096 + 2 * kb + 1] = clock64();
+                    if (g == ng - 1) ptx::umma_commit_elect(tfull_a + acc * 8);
+                    if (tracing && lane == 0 && p.ph0 + i == 16 && g < 32) p.trace[4096 + 2 * g + 1] = clock64();
                     if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -458,6 +465,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const __gri
                         }
                     }
                     float s = warp_sum(((v[0].x + v[0].y) + (v[0].z + v[0].w)) + ((v[1].x + v[1].y) + (v[1].z + v[1].w)));
+                    if (trace != nullptr) trace[8 * i + 3] = clock64();     // (LN phases) loads landed, row sum of this warp
                     if (lane == 0) red0[gw] = s;
                     ch_named_bar(2 + half, 128);
                     const float mean = ((red0[0] + red0[1]) + (red0[2] + red0[3])) * inv_d;
@@ -473,6 +481,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const __gri
                     if (lane == 0) red1[gw] = ss;
                     ch_named_bar(2 + half, 128);
                     const float rstd = rsqrtf(((red1[0] + red1[1]) + (red1[2] + red1[3])) * inv_d + p.eps);
+                    if (trace != nullptr) trace[8 * i + 4] = clock64();     // statistics done
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         const int t = gt + j * 128;
@@ -577,9 +586,17 @@ void Session::build_chain_table() {
         pick_chain_config(B, a_rows, l.n, K, epi == CH_EPI_PARTIAL ? MAX_K_SPLITS : 1, chain_grid, bn, splits);
         o.kind = CH_GEMM; o.bn = bn; o.K = K; o.N = l.n; o.n_tiles_n = ceil_div(l.n, bn); o.k_splits = splits; o.epi = epi;
         o.split_stride = part_stride; o.ldo = ldo; o.bias = epi == CH_EPI_PARTIAL ? nullptr : l.b; o.out = out;
-        o.tmA = make_tmap_bf16_2d(A, K, B, K, a_rows);
-        o.a_bytes = a_rows * CH_BK * 2;
-        o.tmW = make_tmap_bf16_2d(l.w, l.k, l.n, l.k, bn);
+        // k-blocks per TMA operation: as many as a stage holds, dividing the k-blocks of a tile
+        const int nk = K / CH_BK / splits;
+        int kg = 1;
+        for (int c : {2, 4})
+            if (nk % c == 0 && (size_t)c * (a_rows + bn) * CH_BK * 2 <= CH_STAGE_BYTES) kg = c;
+        WB_REQUIRE((size_t)kg * (a_rows + bn) * CH_BK * 2 <= CH_STAGE_BYTES, "fused chains: tile does not fit a ring stage");
+        o.kgroup = kg;
+        o.tmA = make_tmap_bf16_kgroups(A, K, B, K, a_rows, kg);
+        o.a_bytes = kg * a_rows * CH_BK * 2;
+        o.w_off = o.a_bytes;
+        o.tmW = make_tmap_bf16_kgroups(l.w, l.k, l.n, l.k, bn, kg);
         return splits;
     };
     auto ln_phase = [&](ChainPhase& o, const LNorm& n, int n_parts, const float* bias) {
