@@ -472,7 +472,7 @@ def main():
                 log(f"[rank 0] parity probe: {probe}")
             except Exception as e:   # the probe never hides a number: it reports its own failure
                 probe = {"error": repr(e)}
-        if not args.no_microbench:
+        if not args.no_microbench and world == 1:
             micro = decode_step_microbench(eng, cfg, B, es, peaks)
             log(f"[rank 0] decode-step microbench: {micro}")
 
@@ -549,7 +549,7 @@ def main():
             line["decode_step_us"] = micro
         if weak is not None:
             line["weak_scaling"] = weak
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # rank 0 at N = 1 only: at N > 1 the other ranks' host threads spin in NCCL
             r = cpu_reference_rtfx(args.size, args.max_length, 16, 128)
             line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}

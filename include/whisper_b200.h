@@ -107,6 +107,12 @@ WB_API int wb_model_weight_bytes(const wb_model* m, size_t* bytes);
 WB_API int wb_session_workspace_bytes(const wb_model* m, int max_batch, int enc_chunk, size_t* bytes);
 WB_API int wb_session_create(wb_model* m, int max_batch, int enc_chunk, void* workspace, size_t workspace_bytes, wb_session** out);
 WB_API int wb_session_destroy(wb_session* s);
+/* Per-session override of a process-wide A/B switch (the wb_set_* functions below change the default for every session of the
+ * process; a session option wins for that session only).  name: "small_batch_path" (wb_set_small_batch_path != 0),
+ * "decode_chain_path" (wb_set_decode_chain_path), "cuda_graphs" (wb_set_cuda_graphs); value: 1 on, 0 off, -1 inherit the
+ * process-wide switch again.  Takes effect at the next decode step (a captured step graph of the other kind is rebuilt).
+ * The reference has no equivalent (one TensorRT execution context per engine, runtime/session.py:53-61). */
+WB_API int wb_session_set_option(wb_session* session, const char* name, int value);
 
 /* WhisperEncoder.__call__(input) -> hidden_states (run.py:81-91): mel fp32 [B, 80, 3000] on device.
  * Also projects the cross-attention K/V of every decoder layer once (oracle branch modeling_whisper.py:484-487).

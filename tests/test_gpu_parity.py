@@ -559,3 +559,48 @@ def test_partial_batch_after_full_batch_on_sub_sessions_bf16():
     finally:
         _abi.call("wb_set_decode_attention_backend", 0)
         _abi.call("wb_set_lean_decode_gemm", 0)
+
+
+def test_session_options_override_the_process_wide_switches():
+    """wb_session_set_option: a session picks its own decode-step path (whole-step kernel / fused chains / CUDA graph) whatever
+    the process-wide wb_set_* switches say, and two sessions of one process can differ; unknown names fail loudly."""
+    from whisper_trtllm_b200 import WhisperB200Error
+    steps = 10
+    cfg = synth.make_config("tiny.en", max_length=steps + 1)
+    sd = synth.make_weights(cfg, seed=41)
+    mel = synth.make_mel(24, seed=2).to(DEV)
+    a = WhisperEngine(cfg, sd, dtype="bfloat16", max_batch=24, device=DEV)
+    b = WhisperEngine(cfg, sd, dtype="bfloat16", max_batch=24, device=DEV)
+    b.set_option("decode_chain_path", 0)
+    b.set_option("cuda_graphs", 0)
+    n0 = a.launch_count()
+    ids_a = a.generate(mel).cpu()
+    na = a.launch_count() - n0
+    ids_b = b.generate(mel).cpu()
+    nb = a.launch_count() - n0 - na
+    L = cfg["decoder_layers"]
+    assert nb - na >= steps * 6 * L        # 11 kernels per layer instead of 4 (the encoder's launches are the same in both)
+    assert float((ids_a[:, :3] == ids_b[:, :3]).all(dim=1).float().mean()) >= 0.95
+    forced = ids_a.long()
+    _, la = a.generate(mel, forced_tokens=forced, dump_logits_steps=steps)
+    _, lb = b.generate(mel, forced_tokens=forced, dump_logits_steps=steps)
+    for s in range(steps):
+        assert _rel(la[s], lb[s]) < 6e-3, s
+    b.set_option("decode_chain_path", -1)   # inherit again: same launch count as `a`
+    n1 = a.launch_count()
+    b.generate(mel)
+    assert a.launch_count() - n1 <= na + 4 * steps
+    small = WhisperEngine(cfg, sd, dtype="bfloat16", max_batch=4, device=DEV)
+    n2 = a.launch_count()
+    small.generate(mel[:4])
+    with_mega = a.launch_count() - n2
+    small.set_option("small_batch_path", 0)
+    n3 = a.launch_count()
+    small.generate(mel[:4])
+    assert a.launch_count() - n3 > with_mega + steps * 4
+    with pytest.raises(WhisperB200Error):
+        a.set_option("no_such_option", 1)
+    with pytest.raises(WhisperB200Error):
+        a.set_option("cuda_graphs", 7)
+    for e in (a, b, small):
+        e.close()

@@ -54,6 +54,7 @@ SIGNATURES = {
     "wb_session_workspace_bytes": (c_int, [c_void_p, c_int, c_int, POINTER(c_size_t)]),
     "wb_session_create": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, POINTER(c_void_p)]),
     "wb_session_destroy": (c_int, [c_void_p]),
+    "wb_session_set_option": (c_int, [c_void_p, c_char_p, c_int]),
     "wb_encode": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "wb_set_encoder_output": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "wb_decode_begin": (c_int, [c_void_p, c_int, c_void_p]),

@@ -193,6 +193,13 @@ int wb_session_create(wb_model* m, int max_batch, int enc_chunk, void* workspace
         *out = reinterpret_cast<wb_session*>(new wb::Session(M(m), max_batch, enc_chunk, workspace, workspace_bytes));
     });
 }
+int wb_session_set_option(wb_session* session, const char* name, int value) {
+    return guarded([&] {
+        WB_NOT_NULL(session); WB_NOT_NULL(name);
+        SS(session)->set_option(name, value);
+    });
+}
+
 int wb_session_destroy(wb_session* s) {
     return guarded([&] { delete SS(s); });
 }

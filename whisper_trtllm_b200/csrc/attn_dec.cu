@@ -15,6 +15,7 @@
 //     instruction covers 4 complete rows = 512 contiguous bytes; K and V rows of UNROLL iterations are all in
 //     flight before the first use (16-byte L1-bypassing loads);
 //   - each 8-lane group keeps its own running (max, sum, acc[8]) and the groups/warps are merged once per item.
+#include <atomic>
 #include <cstdlib>
 
 #include "wb_internal.h"
@@ -356,45 +357,43 @@ __global__ void __launch_bounds__(128) self_attn_warp_kernel(DecAttnArgs a) {
 
 template <typename T, bool kPaged, int THREADS, int UNROLL, bool kPipe = false>
 void launch(const DecAttnArgs& a, cudaStream_t stream) {
-    static int blocks_per_sm = 0, sms = 0;
+    static std::atomic<int> per_sm[WB_MAX_DEVICES];     // resident CTAs per SM of this instantiation, per device
+    const int dev = current_device(), sms = device_sm_count();
+    int blocks_per_sm = per_sm[dev].load(std::memory_order_relaxed);
     if (blocks_per_sm == 0) {
-        int dev = 0;
-        WB_CHECK_CUDA(cudaGetDevice(&dev));
-        WB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         WB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, decode_attn_kernel<T, kPaged, THREADS, UNROLL, kPipe>, THREADS, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
+        per_sm[dev].store(blocks_per_sm, std::memory_order_relaxed);
     }
     const int items = a.B * a.H;
-    const int grid = std::min(items, sms * blocks_per_sm);
+    // persistent CTAs walk the items round-robin: size the grid so that every CTA gets the SAME number of items (2048 items on
+    // 592 slots = 3.46 rounds would leave 54 % of the slots idle during the 4th; 512 CTAs x 4 items do not)
+    const int slots = sms * blocks_per_sm;
+    const int rounds = ceil_div(items, slots);
+    const int grid = ceil_div(items, rounds);
     launch_kernel(decode_attn_kernel<T, kPaged, THREADS, UNROLL, kPipe>, dim3(grid), dim3(THREADS), 0, stream, true, a);
 }
 }  // namespace
 
-static int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        WB_CHECK_CUDA(cudaGetDevice(&dev));
-        WB_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    }
-    return n;
-}
+static int num_sms() { return device_sm_count(); }
 
 bool decode_attention_bulk_supported(const DecAttnArgs& a);                 // attn_dec_bulk.cu
 void decode_attention_bulk(const DecAttnArgs& a, cudaStream_t stream);
 // 0 = 16-byte load kernel (256 threads, 4 x 2 loads in flight per lane), 1 = cp.async.bulk ring kernel for cross attention,
 // 2..9 = tuning variants of the load kernel for bf16 cross attention (threads, unroll); default (128, 8)
-static int g_dec_attn_backend = 0;
+static std::atomic<int> g_dec_attn_backend{0};
 // paged self-attention: one CTA per item (default) vs one warp per item.  Measured on B200 (B = 256, medium.en, whole
 // 447-step loop): CTA-per-item 4.231 s, warp-per-item 4.263 s per 256 utterances.
 // paged self-attention variants, us per launch averaged over the 447 steps (B = 256, medium.en, one B200 run):
 //   0 warp per item, 4 deep 48.5 (default) | 1 CTA (128 threads, 4 deep) 55.7 | 2 CTA (128, 8) 59.3 | 3 CTA (64, 8) 53.4 |
 //   4 CTA (256, 4) 70.2 | 5 warp, 8 deep, loads forced into one batch 53.1 | 6 warp, 8 deep 52.9
-static int g_self_attn_variant = 0;
+static std::atomic<int> g_self_attn_variant{0};
 void set_self_attention_variant(int v) { g_self_attn_variant = v; }
 void set_decode_attention_backend(int b) { g_dec_attn_backend = b; }
 
 void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
+    const int g_dec_attn_backend = wb::g_dec_attn_backend.load(std::memory_order_relaxed);     // one consistent read per call
+    const int g_self_attn_variant = wb::g_self_attn_variant.load(std::memory_order_relaxed);
     if (g_dec_attn_backend == 1 && decode_attention_bulk_supported(a)) {
         decode_attention_bulk(a, stream);
         return;

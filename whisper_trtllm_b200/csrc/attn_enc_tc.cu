@@ -201,22 +201,29 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 for (int i = 0; i < TKV; ++i)
                     if (i >= valid) s[i] = -INFINITY;
             }
-            float mx = s[0];
+            // row maximum: four independent chains (a single 63-deep FMNMX chain is 250 cycles of pure latency per tile)
+            float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
 #pragma unroll
-            for (int i = 1; i < TKV; ++i) mx = fmaxf(mx, s[i]);
+            for (int i = 4; i < TKV; i += 4) {
+                mx0 = fmaxf(mx0, s[i]); mx1 = fmaxf(mx1, s[i + 1]); mx2 = fmaxf(mx2, s[i + 2]); mx3 = fmaxf(mx3, s[i + 3]);
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
             const float m_new = fmaxf(m_run, mx);
             const float corr = fast_exp2((m_run - m_new) * LOG2E);   // 0 on the first tile (m_run = -inf)
             const float mb = m_new * LOG2E;
-            float ps = 0.f;
+            // (exp2 in bf16x2 was tried: sm_100a has no packed SFU form, `ex2.approx.ftz.bf16x2` becomes two MUFU.EX2.BF16)
+            float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;    // four independent chains for the row sum
             uint32_t pk[TKV / 2];
 #pragma unroll
-            for (int i = 0; i < TKV; i += 2) {
-                const float p0 = fast_exp2(fmaf(s[i], LOG2E, -mb));
-                const float p1 = fast_exp2(fmaf(s[i + 1], LOG2E, -mb));
-                ps += p0 + p1;
-                __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
-                pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+            for (int i = 0; i < TKV; i += 4) {
+                const float p0 = fast_exp2(fmaf(s[i], LOG2E, -mb)), p1 = fast_exp2(fmaf(s[i + 1], LOG2E, -mb));
+                const float p2 = fast_exp2(fmaf(s[i + 2], LOG2E, -mb)), p3 = fast_exp2(fmaf(s[i + 3], LOG2E, -mb));
+                ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(p0, p1), t1 = __floats2bfloat162_rn(p2, p3);
+                pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t0);
+                pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&t1);
             }
+            const float ps = (ps0 + ps1) + (ps2 + ps3);
             l_run = l_run * corr + ps;
             m_run = m_new;
             // P row r -> 128B-swizzled K-major tile: 16-byte chunk c of row r lives at chunk (c ^ (r & 7)).
@@ -262,11 +269,8 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 void encoder_attention_tc(const void* qkv, void* out, int B, int S, int H, cudaStream_t stream) {
     WB_REQUIRE(qkv && out && B > 0 && S > 0 && H > 0, "bad encoder attention arguments");
     const int d = H * DH;
-    static bool configured = false;
-    if (!configured) {
-        WB_CHECK_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        configured = true;
-    }
+    static PerDeviceOnce configured;
+    configured([] { WB_CHECK_CUDA(cudaFuncSetAttribute(enc_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL)); });
     const CUtensorMap tmQ = make_tmap_bf16_2d(qkv, 3LL * d, B * S, 3 * d, TQ);
     const CUtensorMap tmKV = make_tmap_bf16_2d(qkv, 3LL * d, B * S, 3 * d, TKV);
     dim3 grid(ceil_div(S, TQ), H, B), block(NUM_THREADS);

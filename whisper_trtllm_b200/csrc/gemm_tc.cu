@@ -14,6 +14,7 @@
 #include "wb_epilogue.cuh"
 #include "wb_ptx.cuh"
 
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 
@@ -304,15 +305,7 @@ CUtensorMap make_tmap_bf16_kgroups(const void* ptr, long long ld_elems, int rows
     return m;
 }
 
-int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        WB_CHECK_CUDA(cudaGetDevice(&dev));
-        WB_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    }
-    return n;
-}
+int sm_count() { return device_sm_count(); }
 
 bool gemm_tc_supported(const GemmArgs& a) {
     if (a.in_dtype != BF16) return false;
@@ -325,11 +318,8 @@ bool gemm_tc_supported(const GemmArgs& a) {
 template <int BN, bool kLean>
 static void launch_tc(const GemmArgs& a, int k_splits, cudaStream_t stream) {
     using Cfg = TcCfg<BN, kLean>;
-    static bool configured = false;
-    if (!configured) {
-        WB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, kLean>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
-    }
+    static PerDeviceOnce configured;
+    configured([] { WB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, kLean>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)); });
     const CUtensorMap tmA = make_tmap_bf16_2d(a.A, a.lda, a.M, a.K, BM);
     const CUtensorMap tmW = make_tmap_bf16_2d(a.W, a.ldw, a.N, a.K, BN);
     const int mt = ceil_div(a.M, BM), nt = ceil_div(a.N, BN);
@@ -339,9 +329,11 @@ static void launch_tc(const GemmArgs& a, int k_splits, cudaStream_t stream) {
                   k_splits, a.split_stride, ep, a.active);
 }
 
-static int g_force_bn = 0;
+// Process-wide A/B switches (wb_set_*): atomics, read once per launch; sessions can override the ones that select their step
+// path with wb_session_set_option.  Defaults are the production configuration.
+static std::atomic<int> g_force_bn{0};
 void set_gemm_tc_block_n(int bn) { g_force_bn = bn; }
-static bool g_lean_decode = false;   // skinny GEMMs use the co-residency-friendly variant (set for multi-stream decoding)
+static std::atomic<bool> g_lean_decode{false};   // skinny GEMMs use the co-residency-friendly variant (set for multi-stream decoding)
 void set_lean_decode_gemm(bool on) { g_lean_decode = on; }
 
 // Tile width / split-K choice.  Large M (encoder): the widest tile that still gives every SM a tile.  Skinny M (decode,
@@ -381,7 +373,7 @@ void gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     const bool auto_split = a.k_splits == 0;
     pick_config(a, auto_split ? std::max(1, a.max_k_splits) : 1, bn, splits);
     if (!auto_split) splits = a.k_splits;
-    if (g_force_bn) bn = g_force_bn;
+    if (const int forced = g_force_bn.load(std::memory_order_relaxed)) bn = forced;
     WB_REQUIRE(splits >= 1 && (a.K / BK) % splits == 0, "k_splits must divide K / 64");
     if (splits > 1 || auto_split)
         WB_REQUIRE(a.out_dtype == F32 && a.bias == nullptr && a.res == nullptr && a.act == 0 && a.out_mode == 0 && a.out2 == nullptr,
@@ -397,7 +389,7 @@ void gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     }
 }
 
-static int g_gemm_backend = 0;
+static std::atomic<int> g_gemm_backend{0};
 void set_gemm_backend(int backend) { g_gemm_backend = backend; }
 int get_gemm_backend() { return g_gemm_backend; }
 

@@ -78,11 +78,8 @@ void bandwidth_probe(const void* buf, size_t bytes, int mode, int ctas_per_sm, u
         probe_ldg_kernel<<<sms * ctas_per_sm, 256, 0, stream>>>(reinterpret_cast<const uint4*>(buf), bytes / 16, sink);
     } else {
         const size_t smem = PB_STAGES * PB_BYTES + 2 * PB_STAGES * 8;
-        static bool configured = false;
-        if (!configured) {
-            WB_CHECK_CUDA(cudaFuncSetAttribute(probe_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
+        static PerDeviceOnce configured;
+        configured([&] { WB_CHECK_CUDA(cudaFuncSetAttribute(probe_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
         probe_bulk_kernel<<<sms * ctas_per_sm, 128, smem, stream>>>(reinterpret_cast<const uint8_t*>(buf), bytes / PB_BYTES, sink);
     }
     WB_CHECK_LAUNCH();

@@ -488,16 +488,29 @@ void Session::decode_begin(int B, cudaStream_t st) {
 
 // small batches (B <= 16, bf16) run the whole decoder for one token in ONE persistent cooperative kernel (step_mega.cu); the
 // switch exists for A/B measurements and the parity tests (0 = always the multi-kernel step)
-static bool& whole_step_kernel_enabled() {
-    static bool on = true;
+static std::atomic<bool>& whole_step_kernel_enabled() {
+    static std::atomic<bool> on{true};
     return on;
 }
 void set_small_batch_path(bool on) { whole_step_kernel_enabled() = on; }
 
 // (not when several sessions decode concurrently on their own streams: a cooperative grid needs every SM to itself)
-bool Session::use_mega() const { return whole_step_kernel_enabled() && exclusive && get_gemm_backend() == 0 && mega_supported(); }
+// a session option (wb_session_set_option) wins over the process-wide switch; -1 = inherit
+static inline bool opt_or(int session_opt, bool global) { return session_opt < 0 ? global : session_opt != 0; }
+bool Session::use_mega() const {
+    return opt_or(opt_small_batch_path, whole_step_kernel_enabled()) && exclusive && get_gemm_backend() == 0 && mega_supported();
+}
 bool chain_path_enabled();   // step_chain.cu
-bool Session::use_chain() const { return chain_path_enabled() && exclusive && get_gemm_backend() == 0 && chain_supported() && !use_mega(); }
+bool Session::use_chain() const {
+    return opt_or(opt_decode_chain_path, chain_path_enabled()) && exclusive && get_gemm_backend() == 0 && chain_supported() && !use_mega();
+}
+void Session::set_option(const std::string& name, int value) {
+    WB_REQUIRE(value >= -1 && value <= 1, "option values: -1 (inherit the process-wide switch), 0 (off), 1 (on)");
+    if (name == "small_batch_path") opt_small_batch_path = value;
+    else if (name == "decode_chain_path") opt_decode_chain_path = value;
+    else if (name == "cuda_graphs") opt_cuda_graphs = value;
+    else throw Error(-1, "unknown session option '" + name + "' (small_batch_path, decode_chain_path, cuda_graphs)");
+}
 
 // ids of the current decode rows -> result buffer, original row order
 void Session::publish_results(cudaStream_t st) {
@@ -674,15 +687,16 @@ void Session::decode_step_large(cudaStream_t st) {
     }
 }
 
-static bool& graphs_enabled() {
-    static bool on = true;
+static std::atomic<bool>& graphs_enabled() {
+    static std::atomic<bool> on{true};
     return on;
 }
 void set_cuda_graphs(bool on) { graphs_enabled() = on; }
 
 bool Session::graph_ok() const {
     const bool timing_this_step = prof_class != 0 && (prof_step < 0 || steps_enqueued == prof_step);
-    return graphs_enabled() && step_warm && forced_tokens == nullptr && logits_dump == nullptr && !timing_this_step;
+    return opt_or(opt_cuda_graphs, graphs_enabled()) && !graph_capture_failed && step_warm && forced_tokens == nullptr &&
+           logits_dump == nullptr && !timing_this_step;
 }
 
 void Session::build_step_graph(cudaStream_t st) {
@@ -740,7 +754,7 @@ void Session::enqueue_step() {
             try {
                 build_step_graph(st);
             } catch (const Error& e) {
-                graphs_enabled() = false;   // capture not possible here: stay on eager launches
+                graph_capture_failed = true;   // capture not possible for THIS session: it stays on eager launches
                 cudaGetLastError();         // do not leave the (non-sticky) capture error for the next caller to trip over
                 static bool warned = false;
                 if (!warned) {              // a silent perf fallback is a bug report waiting to happen: say it once

@@ -22,6 +22,7 @@
 // bf16 activations into every Linear, split-K partials summed in slab order): models/whisper/model.py:321-369,
 // layers/normalization.py:6-30, modeling_whisper.py:710-751.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -32,7 +33,7 @@
 namespace wb {
 
 CUtensorMap make_tmap_bf16_kgroups(const void* ptr, long long ld_elems, int rows, int cols, int box_rows, int box_k);   // gemm_tc.cu
-long long*& step_trace_ptr();                                                                            // step_mega.cu
+std::atomic<long long*>& step_trace_ptr();                                                                            // step_mega.cu
 
 namespace {
 constexpr int CH_BM = 128, CH_BK = 64, CH_MAX_BN = 128;
@@ -553,8 +554,8 @@ void pick_chain_config(int M, int a_rows, int N, int K, int max_splits, int sms,
 size_t chain_table_bytes(int dec_layers) { return (size_t)(2 + 9 * dec_layers) * sizeof(ChainPhase); }   // host table
 size_t chain_sync_bytes() { return 256; }
 
-static bool& chain_enabled() {
-    static bool on = true;
+static std::atomic<bool>& chain_enabled() {
+    static std::atomic<bool> on{true};
     return on;
 }
 void set_chain_path(bool on) { chain_enabled() = on; }

@@ -25,7 +25,9 @@
 // (tcgen05 needs M = 128 row tiles and a TMEM round trip per phase: at <= 16 rows mma.sync from registers is the right tool.)
 // Measurements of every build of this file: profiles/r01_kernel_variants.md; per-phase clock stamps: tools/step_trace.py.
 #include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "wb_runtime.h"
@@ -913,14 +915,14 @@ void fill_geometry(PhaseDesc& o, int ks, bool rows16, int grid) {
 // attention flavour of the whole-step kernel: 8 lanes per key with CUDA-core dot products (default) / mma.sync blocks of 16 keys.
 // Measured (profiles/r01_kernel_variants.md): the mma.sync flavour needs 2.7x fewer instructions per key and is still 4-13 %
 // SLOWER per step (B = 1 / 8 / 16: 1013 / 1386 / 2047 us vs 979 / 1277 / 1801) - it stays as a tested, switchable variant.
-bool& mega_attention_tc() {
-    static bool on = false;
+std::atomic<bool>& mega_attention_tc() {
+    static std::atomic<bool> on{false};
     return on;
 }
 void set_mega_attention_tc(bool on) { mega_attention_tc() = on; }
 
-long long*& step_trace_ptr() {
-    static long long* ptr = nullptr;
+std::atomic<long long*>& step_trace_ptr() {
+    static std::atomic<long long*> ptr{nullptr};
     return ptr;
 }
 void set_step_trace(long long* dev_ptr) { step_trace_ptr() = dev_ptr; }
@@ -997,10 +999,15 @@ void Session::decode_step_mega(cudaStream_t st) {
     const bool tc = mega_attention_tc();
     auto kernel = nm == 1 ? (tc ? decode_step_mega_kernel<1, true> : decode_step_mega_kernel<1, false>)
                           : (tc ? decode_step_mega_kernel<2, true> : decode_step_mega_kernel<2, false>);
-    static size_t configured[3][2] = {};
-    if (configured[nm][tc] < smem) {
-        WB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[nm][tc] = smem;
+    {   // per device and kernel instance: the largest dynamic shared-memory size requested so far
+        static std::mutex mu;
+        static size_t configured[WB_MAX_DEVICES][3][2] = {};
+        const int dev = current_device();
+        std::lock_guard<std::mutex> lk(mu);
+        if (configured[dev][nm][tc] < smem) {
+            WB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[dev][nm][tc] = smem;
+        }
     }
     int per_sm = 0;
     WB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, MG_THREADS, smem));

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <atomic>
+#include <mutex>
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>
@@ -45,6 +46,42 @@ inline std::atomic<long long>& launch_counter() {
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// Per-DEVICE one-time state.  One process normally drives one GPU (one rank per GPU), but nothing in the C-ABI forbids a
+// host thread per device in one process: kernel attributes (cudaFuncSetAttribute) and device properties are therefore kept
+// per device ordinal, under a mutex (a lock per launch is ~20 ns against ~2 us of launch).
+// ---------------------------------------------------------------------------------------------
+constexpr int WB_MAX_DEVICES = 64;
+inline int current_device() {
+    int d = 0;
+    WB_CHECK_CUDA(cudaGetDevice(&d));
+    WB_REQUIRE(d >= 0 && d < WB_MAX_DEVICES, "device ordinal out of range");
+    return d;
+}
+// runs `fn` once per device (the current one) and `slot`; later calls return immediately
+struct PerDeviceOnce {
+    std::mutex mu;
+    unsigned long long done = 0;
+    template <typename F> void operator()(F&& fn) {
+        const unsigned long long bit = 1ull << current_device();
+        std::lock_guard<std::mutex> lk(mu);
+        if (done & bit) return;
+        fn();
+        done |= bit;
+    }
+};
+// SM count of the current device
+inline int device_sm_count() {
+    static std::atomic<int> n[WB_MAX_DEVICES];
+    const int d = current_device();
+    int v = n[d].load(std::memory_order_relaxed);
+    if (v == 0) {
+        WB_CHECK_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d));
+        n[d].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL): kernels of the decode step are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization so that the NEXT kernel's launch latency and prologue
 // (barrier init, TMEM allocation, descriptor prefetch) overlap the tail of the current one.  Every such kernel
@@ -57,8 +94,8 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 
 // Default OFF: measured on B200 (bench.py A/B, profiles/r01_ab_graph_pdl.md) PDL gave no gain on eager launches
 // (4.61 s vs 4.58 s per 256 utterances) and cost 15 % inside CUDA-graph replays; the graph alone is the win.
-inline bool& pdl_enabled() {
-    static bool on = false;
+inline std::atomic<bool>& pdl_enabled() {
+    static std::atomic<bool> on{false};
     return on;
 }
 
@@ -76,7 +113,7 @@ inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+    cfg.numAttrs = (pdl && pdl_enabled().load(std::memory_order_relaxed)) ? 1 : 0;
     ::wb::launch_counter().fetch_add(1, std::memory_order_relaxed);
     WB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
 }

@@ -116,6 +116,10 @@ struct Session : Buffers {
     bool exclusive = true;            // this session's loop is the only one running on the device (decode_run_multi, n == 1)
     long long step_graph_launches = 0;
     bool step_warm = false;           // one eager step has run (one-time kernel attribute setup done)
+    // per-session overrides of the process-wide A/B switches (wb_session_set_option): -1 inherit, 0 off, 1 on
+    int opt_small_batch_path = -1, opt_decode_chain_path = -1, opt_cuda_graphs = -1;
+    bool graph_capture_failed = false;   // stream capture of the step failed once on this session: eager launches from then on
+    void set_option(const std::string& name, int value);
     bool dx_embedded = false;         // dx holds E[last token] + P[position] of every row (what the whole-step kernel starts from)
     bool graph_ok() const;
     void build_step_graph(cudaStream_t s);

@@ -110,6 +110,12 @@ class WhisperEngine:
         _abi.call("wb_model_set_generation", self._model, sup, len(key[0]), beg, len(key[1]), int(begin_index), forced, len(key[3]))
         self._generation_key = key
 
+    def set_option(self, name: str, value: int):
+        """Per-session override of a process-wide A/B switch (wb_session_set_option): "small_batch_path", "decode_chain_path",
+        "cuda_graphs"; 1 on, 0 off, -1 inherit."""
+        for h, _ in self._subs:
+            _abi.call("wb_session_set_option", h, name.encode(), int(value))
+
     def weight_bytes(self) -> int:
         n = c_size_t()
         _abi.call("wb_model_weight_bytes", self._model, byref(n))
