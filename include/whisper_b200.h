@@ -140,6 +140,18 @@ WB_API int wb_decode_run_multi(wb_session** sessions, int n_sessions, int max_st
  * result buffer in ORIGINAL row order, which wb_decode_tokens returns from then on.  *rows_running = rows still decoding,
  * 0 when the loop has stopped.  Not available with teacher forcing / logits dumps. */
 WB_API int wb_decode_compact(wb_session* s, int* rows_running, wb_stream stream);
+/* In-flight refill: call between two wb_decode_run windows.  (1) Utterances that have emitted EOS or reached
+ * max_length leave the batch: their ids are written to the HOST arrays finished_utt [max_batch] (utterance number: decode_begin's
+ * rows are 0 .. batch-1, every admitted utterance gets the next number), finished_len [max_batch] and finished_ids
+ * [max_batch, max_target_positions] (first finished_len[k] entries valid; nothing is padded after EOS).  (2) The rows still
+ * decoding move to the front.  (3) Up to n_new new utterances (mel_new: DEVICE fp32 [n_new, 80, 3000]) are encoded into the
+ * freed slots and start decoding at position 0 while the others continue where they are: from then on the kernels use per-row
+ * lengths.  *n_admitted tells how many of mel_new were taken (the first ones), *n_rows how many rows decode now (0: nothing left,
+ * the loop is over).  Synchronises `stream`.  Every utterance gets the ids it would get alone (rows are independent).
+ * The reference transcribes utterances one by one (examples/whisper/run.py:263-288); TensorRT-LLM's GPT runtime has the idea
+ * (docs/in_flight_batching.md), its Whisper path does not. */
+WB_API int wb_decode_refill(wb_session* session, const float* mel_new, int n_new, int32_t* finished_utt, int32_t* finished_len,
+                            int32_t* finished_ids, int* n_finished, int* n_admitted, int* n_rows, wb_stream stream);
 /* ids int32 [B, max_target_positions] (row stride max_target_positions), original row order; device pointer owned by the session */
 WB_API int wb_decode_tokens(wb_session* s, const int32_t** tokens_dev, int* row_stride);
 /* raw next-token logits of the last step, fp32 [B, vocab] (the decoder engine's output tensor, model.py:464) */

@@ -604,3 +604,95 @@ def test_session_options_override_the_process_wide_switches():
         a.set_option("cuda_graphs", 7)
     for e in (a, b, small):
         e.close()
+
+
+def _pick_eos(free, min_first=3):
+    """A token that the rows of `free` emit for the first time at different positions (some never): made the EOS, the rows finish
+    at different times."""
+    n = free.shape[0]
+    for t in sorted(set(free[:, 2:].flatten().tolist())):
+        first = [((free[r, 2:] == t).nonzero().flatten().tolist() + [None])[0] for r in range(n)]
+        hit = [f for f in first if f is not None]
+        if len(set(first)) >= 3 and len(hit) >= 2 and None in first and min(hit) >= min_first:
+            return int(t)
+    return None
+
+
+def _own_ids(ref_row, eos, max_length):
+    """ids an utterance gets on its own: up to and including its first EOS (position >= 1), else the full length."""
+    r = ref_row.tolist()
+    for t in range(1, len(r)):
+        if r[t] == eos:
+            return r[:t + 1]
+    return r[:max_length]
+
+
+def test_in_flight_refill_gives_every_utterance_its_own_ids():
+    """wb_decode_refill: 11 utterances through a 4-row engine; every few steps the finished utterances leave and
+    the next ones are encoded into the freed slots, so the rows of the batch sit at DIFFERENT positions (per-row lengths in the
+    embedding, the paged self-attention and the logits processors).  fp32: every utterance gets exactly the ids of the
+    reference's loop (generation/utils.py:1474-1529) run on it - whatever the window, the order of arrival or the batch size."""
+    cfg = synth.make_config("micro", max_length=40)
+    sd = synth.make_weights(cfg, seed=0)
+    mel = synth.make_mel(11, seed=1234)
+    free = R.greedy(mel, sd, cfg)
+    eos_tok = _pick_eos(free)
+    assert eos_tok is not None, "the test case needs rows that finish at different times"
+    cfg3 = dict(cfg, eos_token_id=eos_tok, pad_token_id=eos_tok)
+    ref3 = R.greedy(mel, sd, cfg3)
+    own = [_own_ids(ref3[u], eos_tok, 40) for u in range(11)]
+    assert len({len(o) for o in own}) >= 3
+    eng = WhisperEngine(cfg3, sd, dtype="float32", max_batch=4, enc_chunk=2, device=DEV)
+    for window, src in ((3, mel), (5, mel.to(DEV)), (64, mel), (1, mel[:6])):
+        ids = eng.transcribe_stream(src, window=window).cpu().long()
+        n = src.shape[0]
+        assert ids.shape[0] == n and ids.shape[1] == max(len(o) for o in own[:n])
+        for u in range(n):
+            got = ids[u].tolist()
+            assert got[:len(own[u])] == own[u], (window, u, got, own[u])
+            assert all(t == eos_tok for t in got[len(own[u]):]), (window, u)
+    # fewer utterances than rows, and a single one
+    assert eng.transcribe_stream(mel[:3], window=4).cpu().long()[0].tolist()[:len(own[0])] == own[0]
+    assert eng.transcribe_stream(mel[5:6], window=7).cpu().long()[0].tolist()[:len(own[5])] == own[5]
+    # the engine is still good for the plain batched loop afterwards (page-table rows were swapped, never lost)
+    plain = eng.generate(mel[:4].to(DEV)).cpu().long()
+    assert torch.equal(plain, ref3[:4, :plain.shape[1]])
+    eng.close()
+
+
+def test_in_flight_refill_bf16_large_batch_path():
+    """The same through the bf16 large-batch step (fused chains, warp / CTA paged self-attention, ragged rows): 45 utterances
+    through a 20-row engine agree with the plain batched loop on the same utterances (first tokens of >= 90 % of the rows: the
+    split-K shapes depend on the batch size, so later near-ties may resolve differently), every row ends with EOS or is full."""
+    steps = 23
+    cfg = synth.make_config("tiny.en", max_length=steps + 1)
+    sd = synth.make_weights(cfg, seed=33)
+    mel = synth.make_mel(45, seed=3)
+    eng = WhisperEngine(cfg, sd, dtype="bfloat16", max_batch=20, enc_chunk=8, device=DEV)
+    free = torch.cat([eng.generate(mel[i:i + 20].to(DEV)).cpu() for i in range(0, 45, 20)]).long()
+    eos_tok = _pick_eos(free)
+    if eos_tok is None:     # fall back to the token whose first occurrences are spread over the most positions
+        best = (0, None)
+        for t in sorted(set(free[:, 3:].flatten().tolist())):
+            first = {int((free[r, 3:] == t).nonzero().flatten()[0]) for r in range(free.shape[0]) if (free[r, 3:] == t).any()}
+            best = max(best, (len(first), int(t)), key=lambda x: x[0])
+        eos_tok = best[1]
+    assert eos_tok is not None
+    eng.close()
+    cfg3 = dict(cfg, eos_token_id=eos_tok, pad_token_id=eos_tok)
+    eng = WhisperEngine(cfg3, sd, dtype="bfloat16", max_batch=20, enc_chunk=8, device=DEV)
+    rows = []
+    for i in range(0, 45, 20):
+        g = eng.generate(mel[i:i + 20].to(DEV)).cpu().long()
+        rows += [_own_ids(g[r], eos_tok, steps + 1) for r in range(g.shape[0])]
+    for window in (4, 9):
+        ids = eng.transcribe_stream(mel, window=window).cpu().long()
+        assert ids.shape[0] == 45
+        agree = 0
+        for u in range(45):
+            got = _own_ids(ids[u], eos_tok, steps + 1)
+            assert got[-1] == eos_tok or len(got) == steps + 1, (u, got)
+            k = min(6, len(rows[u]), len(got))
+            agree += int(got[:k] == rows[u][:k])
+        assert agree >= 41, (window, agree)
+    eng.close()

@@ -62,6 +62,8 @@ SIGNATURES = {
     "wb_decode_run": (c_int, [c_void_p, c_int, c_int, POINTER(c_int), c_void_p]),
     "wb_decode_run_multi": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, POINTER(c_int), c_void_p]),
     "wb_decode_compact": (c_int, [c_void_p, POINTER(c_int), c_void_p]),
+    "wb_decode_refill": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                                 c_void_p]),
     "wb_decode_tokens": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int)]),
     "wb_decode_logits": (c_int, [c_void_p, POINTER(c_void_p)]),
     "wb_decode_set_forced_tokens": (c_int, [c_void_p, c_void_p]),

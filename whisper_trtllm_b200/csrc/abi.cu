@@ -248,6 +248,26 @@ int wb_decode_compact(wb_session* s, int* rows_running, wb_stream stream) {
         if (rows_running) *rows_running = n;
     });
 }
+int wb_decode_refill(wb_session* s, const float* mel_new, int n_new, int32_t* finished_utt, int32_t* finished_len, int32_t* finished_ids,
+                     int* n_finished, int* n_admitted, int* n_rows, wb_stream stream) {
+    return guarded([&] {
+        WB_NOT_NULL(s); WB_NOT_NULL(finished_utt); WB_NOT_NULL(finished_len); WB_NOT_NULL(finished_ids);
+        WB_NOT_NULL(n_finished); WB_NOT_NULL(n_rows);
+        std::vector<wb::Session::Finished> fin;
+        int adm = 0;
+        const int rows = SS(s)->decode_refill(mel_new, n_new, fin, &adm, S(stream));
+        const int max_tgt = SS(s)->m->cfg.max_tgt;
+        for (size_t k = 0; k < fin.size(); ++k) {
+            finished_utt[k] = fin[k].utt;
+            finished_len[k] = fin[k].len;
+            std::copy(fin[k].ids.begin(), fin[k].ids.end(), finished_ids + k * (size_t)max_tgt);
+        }
+        *n_finished = (int)fin.size();
+        if (n_admitted) *n_admitted = adm;
+        *n_rows = rows;
+    });
+}
+
 int wb_decode_tokens(wb_session* s, const int32_t** tokens_dev, int* row_stride) {
     return guarded([&] {
         WB_NOT_NULL(s);

@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(DecAttnArgs a) {
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int b = item / a.H, h = item - b * a.H;
         if (a.row_active != nullptr && a.row_active[b] == 0) continue;   // finished utterance: block-uniform skip
+        if (a.row_len != nullptr) n = a.row_len[b];                       // ragged batch (in-flight refill): this row's length
         parity ^= 1;
         float qf[VEC];
         if (a.q_parts != nullptr) {   // q = bias + sum of the split-K partial slabs of the q projection (fp32, fixed order)
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(128) self_attn_warp_kernel(DecAttnArgs a) {
     // early-outs): loop state, the row's unfinished flag, its page ids, q and the new k/v row
     const int* pt = a.page_table + (size_t)b * a.pages_per_seq;
     const int active = a.state->active;
-    const int n = a.state->cur_len;
+    const int n = a.row_len != nullptr ? a.row_len[b] : a.state->cur_len;   // per row when the batch is ragged (in-flight refill)
     const int row_on = a.row_active != nullptr ? a.row_active[b] : 1;
     // the item's page ids live in the warp's registers (lane i holds page i; <= 7 pages for 448 tokens): every row address
     // costs a shuffle instead of a dependent global load in front of each batch of K/V requests

@@ -217,13 +217,9 @@ bool decode_attention_bulk_supported(const DecAttnArgs& a) {
 void decode_attention_bulk(const DecAttnArgs& a, cudaStream_t stream) {
     WB_REQUIRE(decode_attention_bulk_supported(a), "bulk cross-attention needs bf16, contiguous 16-byte aligned K/V");
     WB_REQUIRE((a.q || a.q_parts) && a.out && a.B > 0 && a.H > 0, "bad decode attention arguments");
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        WB_CHECK_CUDA(cudaGetDevice(&dev));
-        WB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        WB_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
-    }
+    static PerDeviceOnce configured;
+    configured([] { WB_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL)); });
+    const int sms = device_sm_count();
     const int grid = std::min(a.B * a.H, sms);
     launch_kernel(cross_attn_bulk_kernel, dim3(grid), dim3(THREADS), SMEM_TOTAL, stream, true, a);
 }

@@ -17,13 +17,15 @@ namespace {
 template <typename T>
 __global__ void __launch_bounds__(128) decoder_embed_kernel(const int* __restrict__ tokens, int tokens_stride,
                                                             const StepState* __restrict__ state, const T* __restrict__ emb,
-                                                            const T* __restrict__ pos, float* __restrict__ x, int d) {
+                                                            const T* __restrict__ pos, float* __restrict__ x, int d,
+                                                            const int* __restrict__ row_len) {
     pdl_wait();
     pdl_trigger();
     if (state->active == 0) return;
     constexpr int VEC = Vec16<T>::N;
     const int b = blockIdx.x;
-    const int p = state->cur_len - 1;  // position == past length (modeling_whisper.py:307-308, model.py:424)
+    // position == past length (modeling_whisper.py:307-308, model.py:424); per row when the batch is ragged (in-flight refill)
+    const int p = (row_len != nullptr ? row_len[b] : state->cur_len) - 1;
     const int tok = tokens[(size_t)b * tokens_stride + p];
     const T* e = emb + (size_t)tok * d;
     const T* pp = pos + (size_t)p * d;
@@ -131,25 +133,33 @@ __global__ void __launch_bounds__(1024) greedy_step_kernel(GreedyArgs a) {
     StepState* st = a.state;
     if (st->active == 0) return;
     const int b = blockIdx.x;
-    const int n = st->cur_len;  // == input_ids.shape[-1] seen by the processors
-    int tok;
-    const int forced = a.force_map != nullptr ? a.force_map[n] : -1;
-    if (forced >= 0) {
-        tok = forced;
-    } else {
-        const int bits = 1 | (n == a.begin_index ? 2 : 0);
-        tok = block_masked_argmax(a.logits + (size_t)b * a.ld, a.V, a.vocab_mask, bits);
+    const bool ragged = a.row_len != nullptr;
+    const int n = ragged ? a.row_len[b] : st->cur_len;  // == input_ids.shape[-1] seen by the processors (of this row)
+    const bool row_on = !ragged || a.unfinished[b] != 0;    // ragged batch: a finished row is frozen (block-uniform)
+    int tok = a.pad_id;
+    if (row_on) {
+        const int forced = a.force_map != nullptr ? a.force_map[n] : -1;
+        if (forced >= 0) {
+            tok = forced;
+        } else {
+            const int bits = 1 | (n == a.begin_index ? 2 : 0);
+            tok = block_masked_argmax(a.logits + (size_t)b * a.ld, a.V, a.vocab_mask, bits);
+        }
     }
     __shared__ int s_tok;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && row_on) {
         const int unf = a.unfinished[b];
         tok = unf ? tok : a.pad_id;
         if (a.forced_tokens != nullptr) tok = a.forced_tokens[(size_t)b * a.tokens_stride + n];
         a.tokens[(size_t)b * a.tokens_stride + n] = tok;
         s_tok = tok;
         if (tok == a.eos_id) a.unfinished[b] = 0;
+        if (ragged) {
+            a.row_len[b] = n + 1;
+            if (n + 1 >= a.max_length) a.unfinished[b] = 0;    // this row is full (stopping_criteria.py:61-70, per row)
+        }
     }
-    if (a.embed_x != nullptr && n < a.tokens_stride) {
+    if (a.embed_x != nullptr && n < a.tokens_stride && row_on) {
         // embedding of the token just chosen = the input of the NEXT step (position n): x[b, :] = E[tok, :] + P[n, :], so that the
         // whole-step decoder kernel (step_mega.cu) starts from the residual stream (model.py:423-425)
         __syncthreads();
@@ -173,10 +183,10 @@ __global__ void __launch_bounds__(1024) greedy_step_kernel(GreedyArgs a) {
             __threadfence();
             int cnt = 0;
             for (int i = 0; i < a.B; ++i) cnt += (*((volatile int*)&a.unfinished[i]) != 0);
-            const int new_len = n + 1;
+            const int new_len = (ragged ? st->cur_len : n) + 1;   // ragged: a step counter; the rows carry their own lengths
             st->n_unfinished = cnt;
             st->done_counter = 0;
-            if (cnt == 0 || new_len >= a.max_length) {
+            if (cnt == 0 || (!ragged && new_len >= a.max_length)) {
                 st->final_len = new_len;
                 st->active = 0;
             }
@@ -212,12 +222,12 @@ __global__ void __launch_bounds__(1024) argmax_rows_kernel(const float* __restri
 }  // namespace
 
 void decoder_embed(const int* tokens, int tokens_stride, const StepState* state, const void* emb, const void* pos,
-                   int dtype, float* x, int B, int d, cudaStream_t stream) {
+                   int dtype, float* x, int B, int d, cudaStream_t stream, const int* row_len) {
     WB_REQUIRE(d % 8 == 0, "d_model must be a multiple of 8");
     if (dtype == F32)
-        launch_kernel(decoder_embed_kernel<float>, dim3(B), dim3(128), 0, stream, true, tokens, tokens_stride, state, (const float*)emb, (const float*)pos, x, d);
+        launch_kernel(decoder_embed_kernel<float>, dim3(B), dim3(128), 0, stream, true, tokens, tokens_stride, state, (const float*)emb, (const float*)pos, x, d, row_len);
     else
-        launch_kernel(decoder_embed_kernel<bf16>, dim3(B), dim3(128), 0, stream, true, tokens, tokens_stride, state, (const bf16*)emb, (const bf16*)pos, x, d);
+        launch_kernel(decoder_embed_kernel<bf16>, dim3(B), dim3(128), 0, stream, true, tokens, tokens_stride, state, (const bf16*)emb, (const bf16*)pos, x, d, row_len);
 }
 
 void embed_tokens(const int* ids, long long ids_stride, int B, int T, int pos0, const void* emb, const void* pos, int dtype,

@@ -270,6 +270,7 @@ size_t layout(Buffers& b, const Model* m, int max_batch, int enc_chunk, void* ba
     c.take(b.mega_table, mega_table_bytes(g.dec_layers));
     c.take(b.result_tokens, B * g.max_tgt * 4);
     c.take(b.chain_sync, chain_sync_bytes());
+    c.take(b.row_len, B * 4);
     return c.off + 1024;
 }
 }  // namespace
@@ -422,14 +423,18 @@ void Session::stem(const float* mel, int B, float* x_out, cudaStream_t st) {
     WB_CHECK_CUDA(cudaMemcpyAsync(x_out, x, (size_t)B * m->cfg.n_ctx * m->cfg.d_model * 4, cudaMemcpyDeviceToDevice, st));
 }
 
-void Session::encode(const float* mel, int B, float* enc_out_f32, cudaStream_t st) {
-    WB_REQUIRE(mel != nullptr && B > 0 && B <= max_batch, "bad encode batch");
+void Session::encode(const float* mel, int B, float* enc_out_f32, cudaStream_t st) { encode_at(mel, B, 0, enc_out_f32, st); }
+
+// encoder + cross-K/V projection of B utterances into the batch slots [slot0, slot0 + B)
+void Session::encode_at(const float* mel, int B, int slot0, float* enc_out_f32, cudaStream_t st) {
+    WB_REQUIRE(mel != nullptr && B > 0 && slot0 >= 0 && slot0 + B <= max_batch, "bad encode batch");
     const ModelConfig& g = m->cfg;
     const int d = g.d_model, dt = m->dtype;
-    for (int b0 = 0; b0 < B; b0 += enc_chunk) {
-        const int bc = std::min(enc_chunk, B - b0);
+    for (int c0 = 0; c0 < B; c0 += enc_chunk) {
+        const int bc = std::min(enc_chunk, B - c0);
+        const int b0 = slot0 + c0;
         const int M = bc * g.n_ctx;
-        { ProfScope ps(this, PROF_STEM, st); stem_chunk(mel + (size_t)b0 * g.n_mels * g.n_frames, bc, st); }
+        { ProfScope ps(this, PROF_STEM, st); stem_chunk(mel + (size_t)c0 * g.n_mels * g.n_frames, bc, st); }
         // ---- transformer layers (pre-LN), fp32 residual stream in x
         for (int l = 0; l < g.enc_layers; ++l) {
             const EncLayer& L = m->enc[l];
@@ -457,7 +462,7 @@ void Session::encode(const float* mel, int B, float* enc_out_f32, cudaStream_t s
             }
         }
         layernorm(x, m->enc_ln.g, m->enc_ln.b, eoff(enc, (size_t)b0 * g.n_ctx * d, dt), dt,
-                  enc_out_f32 ? enc_out_f32 + (size_t)b0 * g.n_ctx * d : nullptr, M, d, 1e-5f, nullptr, st);
+                  enc_out_f32 ? enc_out_f32 + (size_t)c0 * g.n_ctx * d : nullptr, M, d, 1e-5f, nullptr, st);
         project_cross_kv(this, b0, bc, st);
     }
 }
@@ -478,6 +483,9 @@ void Session::decode_begin(int B, cudaStream_t st) {
     row_origin.resize(B);
     for (int i = 0; i < B; ++i) row_origin[i] = i;
     steps_enqueued = 0;
+    ragged = false;
+    refill_mode = false;
+    next_utt = B;
     greedy_init(tokens, g.max_tgt, unfinished, state, B, g.sot, g.pad, g.max_tgt, st);
     // the whole-step kernel starts from the residual stream: embedding of the start token here, of every later token by the
     // greedy kernel of the step that chose it.  ALWAYS written (one tiny kernel): which step path runs is only known when the
@@ -498,7 +506,7 @@ void set_small_batch_path(bool on) { whole_step_kernel_enabled() = on; }
 // a session option (wb_session_set_option) wins over the process-wide switch; -1 = inherit
 static inline bool opt_or(int session_opt, bool global) { return session_opt < 0 ? global : session_opt != 0; }
 bool Session::use_mega() const {
-    return opt_or(opt_small_batch_path, whole_step_kernel_enabled()) && exclusive && get_gemm_backend() == 0 && mega_supported();
+    return opt_or(opt_small_batch_path, whole_step_kernel_enabled()) && exclusive && !ragged && get_gemm_backend() == 0 && mega_supported();
 }
 bool chain_path_enabled();   // step_chain.cu
 bool Session::use_chain() const {
@@ -526,9 +534,44 @@ void Session::publish_results(cudaStream_t st) {
     }
 }
 
+// rows keep[0] < keep[1] < ... move to decode rows 0, 1, ...: ids, cross K/V rows, page-table rows (swapped: the self K/V pages
+// stay where they are and no page is lost), utterance ids.  Stable: row i moves to slot j <= i, which held a row that is leaving or
+// has already moved.  Does not touch `batch`, `unfinished` or the lengths.
+void Session::compact_rows(const std::vector<int>& keep, cudaStream_t st) {
+    const ModelConfig& g = m->cfg;
+    const size_t es = dtype_size(m->dtype);
+    const size_t row_bytes = (size_t)g.max_tgt * 4;
+    const size_t kv_row = (size_t)g.n_heads * g.n_ctx * 64;                   // cross K (or V) elements of one utterance and layer
+    const size_t per_kv = (size_t)max_batch * kv_row;
+    const int old_batch = batch;
+    bool moved = false;
+    for (int j = 0; j < (int)keep.size(); ++j) {
+        const int i = keep[j];
+        if (i == j) continue;
+        moved = true;
+        WB_CHECK_CUDA(cudaMemcpyAsync(tokens + (size_t)j * g.max_tgt, tokens + (size_t)i * g.max_tgt, row_bytes, cudaMemcpyDeviceToDevice, st));
+        for (int l = 0; l < g.dec_layers; ++l) {
+            for (int kv = 0; kv < 2; ++kv) {
+                uint8_t* base_l = (uint8_t*)cross + ((size_t)l * cross_layer_elems() + (size_t)kv * per_kv) * es;
+                WB_CHECK_CUDA(cudaMemcpyAsync(base_l + (size_t)j * kv_row * es, base_l + (size_t)i * kv_row * es, kv_row * es,
+                                              cudaMemcpyDeviceToDevice, st));
+            }
+        }
+        for (int q = 0; q < pages_per_seq; ++q)                               // the self K/V pages stay where they are
+            std::swap(page_table_host[(size_t)j * pages_per_seq + q], page_table_host[(size_t)i * pages_per_seq + q]);
+        row_origin[j] = row_origin[i];
+    }
+    row_origin.resize(keep.size());
+    if (moved) {
+        WB_CHECK_CUDA(cudaMemcpyAsync(page_table, page_table_host.data(), (size_t)old_batch * pages_per_seq * 4, cudaMemcpyHostToDevice, st));
+        WB_CHECK_CUDA(cudaStreamSynchronize(st));                             // page_table_host may change again before the copy ran
+    }
+}
+
 int Session::decode_compact(cudaStream_t st) {
     WB_REQUIRE(batch > 0, "decode_begin was not called");
     WB_REQUIRE(forced_tokens == nullptr && logits_dump == nullptr, "compaction is not available with teacher forcing / logits dumps");
+    WB_REQUIRE(!refill_mode, "wb_decode_compact keeps results by ORIGINAL row: after wb_decode_refill use wb_decode_refill (n_new = 0) instead");
     const ModelConfig& g = m->cfg;
     std::vector<int> unf((size_t)batch);
     StepState hs;
@@ -543,35 +586,108 @@ int Session::decode_compact(cudaStream_t st) {
     // the ids of every current row go to the result buffer first (finished rows are final; running rows are refreshed at the end)
     publish_results(st);
     compacted = true;
-    // stable compaction: running row i moves to slot j <= i; slot j held a finished row or a row that has already moved
-    const size_t es = dtype_size(m->dtype);
-    const size_t row_bytes = (size_t)g.max_tgt * 4;
-    const size_t kv_row = (size_t)g.n_heads * g.n_ctx * 64;                   // cross K (or V) elements of one utterance and layer
-    const size_t per_kv = (size_t)max_batch * kv_row;
-    for (int j = 0; j < (int)keep.size(); ++j) {
-        const int i = keep[j];
-        if (i == j) continue;
-        WB_CHECK_CUDA(cudaMemcpyAsync(tokens + (size_t)j * g.max_tgt, tokens + (size_t)i * g.max_tgt, row_bytes, cudaMemcpyDeviceToDevice, st));
-        for (int l = 0; l < g.dec_layers; ++l) {
-            for (int kv = 0; kv < 2; ++kv) {
-                uint8_t* base_l = (uint8_t*)cross + ((size_t)l * cross_layer_elems() + (size_t)kv * per_kv) * es;
-                WB_CHECK_CUDA(cudaMemcpyAsync(base_l + (size_t)j * kv_row * es, base_l + (size_t)i * kv_row * es, kv_row * es,
-                                              cudaMemcpyDeviceToDevice, st));
-            }
-        }
-        for (int q = 0; q < pages_per_seq; ++q)                               // the self K/V pages stay where they are
-            std::swap(page_table_host[(size_t)j * pages_per_seq + q], page_table_host[(size_t)i * pages_per_seq + q]);
-        row_origin[j] = row_origin[i];
-    }
-    const int old_batch = batch;
+    compact_rows(keep, st);
     batch = (int)keep.size();
-    row_origin.resize(batch);
-    WB_CHECK_CUDA(cudaMemcpyAsync(page_table, page_table_host.data(), (size_t)old_batch * pages_per_seq * 4, cudaMemcpyHostToDevice, st));
     std::vector<int> ones((size_t)batch, 1);
     WB_CHECK_CUDA(cudaMemcpyAsync(unfinished, ones.data(), (size_t)batch * 4, cudaMemcpyHostToDevice, st));
-    WB_CHECK_CUDA(cudaStreamSynchronize(st));                                 // the host vectors above go out of scope
+    WB_CHECK_CUDA(cudaStreamSynchronize(st));                                 // the host vector above goes out of scope
     // the whole-step kernel starts from the residual stream: re-embed the last token of the rows that moved
-    decoder_embed(tokens, g.max_tgt, state, m->emb, m->dec_pos, m->dtype, dx, batch, g.d_model, st);
+    decoder_embed(tokens, g.max_tgt, state, m->emb, m->dec_pos, m->dtype, dx, batch, g.d_model, st, ragged_len());
+    dx_embedded = true;
+    return batch;
+}
+
+// In-flight refill (the idea of docs/in_flight_batching.md of the reference tree, which its Whisper path does
+// not have: it transcribes one utterance at a time, run.py:263-288).  Called between two windows of decode steps:
+//   1. utterances that have emitted EOS (or are full) are handed to the caller with their ids and leave the batch;
+//   2. the rows still decoding move to the front (compact_rows);
+//   3. up to n_new NEW utterances are encoded straight into the freed slots (cross K/V projected there), start token in place;
+//   4. from now on the rows are at different positions: per-row lengths (row_len) drive the embedding, the paged self-attention
+//      and the logits processors / argmax (`ragged`).  When nothing was left running the batch restarts uniform.
+// Rows are independent, so every utterance gets exactly the ids it would get alone (fp32: bit-identical to the reference).
+int Session::decode_refill(const float* mel_new, int n_new, std::vector<Finished>& finished, int* n_admitted, cudaStream_t st) {
+    WB_REQUIRE(begin_batch > 0, "decode_begin was not called");
+    WB_REQUIRE(forced_tokens == nullptr && logits_dump == nullptr, "refill is not available with teacher forcing / logits dumps");
+    WB_REQUIRE(n_new >= 0 && (n_new == 0 || mel_new != nullptr), "bad refill arguments");
+    const ModelConfig& g = m->cfg;
+    finished.clear();
+    refill_mode = true;
+    compacted = false;
+    // ---- 1. snapshot of the loop state
+    std::vector<int> unf((size_t)batch), len((size_t)batch);
+    StepState hs;
+    WB_CHECK_CUDA(cudaMemcpyAsync(&hs, state, sizeof(StepState), cudaMemcpyDeviceToHost, st));
+    if (batch > 0) {
+        WB_CHECK_CUDA(cudaMemcpyAsync(unf.data(), unfinished, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+        if (ragged) WB_CHECK_CUDA(cudaMemcpyAsync(len.data(), row_len, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+    }
+    WB_CHECK_CUDA(cudaStreamSynchronize(st));
+    std::vector<int> keep, gone;
+    for (int i = 0; i < batch; ++i) {
+        if (!ragged) len[i] = hs.cur_len;
+        const bool full = len[i] >= g.max_length;
+        if (unf[i] != 0 && !full) keep.push_back(i);           // still decoding (the window's step budget ran out)
+        else gone.push_back(i);
+    }
+    // ---- 2. finished utterances -> caller
+    if (!gone.empty()) {
+        std::vector<int> rows(gone.size() * (size_t)g.max_tgt);
+        for (size_t k = 0; k < gone.size(); ++k)
+            WB_CHECK_CUDA(cudaMemcpyAsync(rows.data() + k * g.max_tgt, tokens + (size_t)gone[k] * g.max_tgt, (size_t)g.max_tgt * 4,
+                                          cudaMemcpyDeviceToHost, st));
+        WB_CHECK_CUDA(cudaStreamSynchronize(st));
+        for (size_t k = 0; k < gone.size(); ++k) {
+            Finished f;
+            f.utt = row_origin[gone[k]];
+            int n = std::min(len[gone[k]], g.max_length);
+            const int* r = rows.data() + k * g.max_tgt;
+            if (!ragged)                                         // uniform batch: a row that finished early was padded after its EOS
+                for (int t = 1; t < n; ++t)
+                    if (r[t] == g.eos) { n = t + 1; break; }
+            f.len = n;
+            f.ids.assign(r, r + n);
+            finished.push_back(std::move(f));
+        }
+    }
+    // ---- 3. survivors to the front
+    compact_rows(keep, st);
+    std::vector<int> new_len(keep.size());
+    for (size_t j = 0; j < keep.size(); ++j) new_len[j] = len[keep[j]];
+    const int n_live = (int)keep.size();
+    // ---- 4. new utterances into the freed slots
+    const int n_adm = std::min(n_new, max_batch - n_live);
+    if (n_admitted) *n_admitted = n_adm;
+    if (n_adm > 0) {
+        encode_at(mel_new, n_adm, n_live, nullptr, st);
+        std::vector<int> first((size_t)g.max_tgt, g.pad);
+        first[0] = g.sot;
+        for (int k = 0; k < n_adm; ++k) {
+            WB_CHECK_CUDA(cudaMemcpyAsync(tokens + (size_t)(n_live + k) * g.max_tgt, first.data(), (size_t)g.max_tgt * 4, cudaMemcpyHostToDevice, st));
+            row_origin.push_back(next_utt++);
+            new_len.push_back(1);
+        }
+        WB_CHECK_CUDA(cudaStreamSynchronize(st));               // `first` goes out of scope
+    }
+    batch = n_live + n_adm;
+    if (batch == 0) {                                           // nothing left and nothing new: the loop is over
+        hs.active = 0;
+        WB_CHECK_CUDA(cudaMemcpyAsync(state, &hs, sizeof(StepState), cudaMemcpyHostToDevice, st));
+        WB_CHECK_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    }
+    // ---- 5. loop state of the new batch
+    bool uniform = true;
+    for (int i = 1; i < batch; ++i) uniform = uniform && new_len[i] == new_len[0];
+    ragged = !uniform;
+    hs.cur_len = uniform ? new_len[0] : std::max(hs.cur_len, 1);
+    hs.active = 1; hs.final_len = 0; hs.done_counter = 0; hs.n_unfinished = batch;
+    std::vector<int> ones((size_t)batch, 1);
+    WB_CHECK_CUDA(cudaMemcpyAsync(state, &hs, sizeof(StepState), cudaMemcpyHostToDevice, st));
+    WB_CHECK_CUDA(cudaMemcpyAsync(unfinished, ones.data(), (size_t)batch * 4, cudaMemcpyHostToDevice, st));
+    WB_CHECK_CUDA(cudaMemcpyAsync(row_len, new_len.data(), (size_t)batch * 4, cudaMemcpyHostToDevice, st));
+    WB_CHECK_CUDA(cudaStreamSynchronize(st));
+    // the chain / whole-step paths start from the residual stream: embed the last token of every row at ITS position
+    decoder_embed(tokens, g.max_tgt, state, m->emb, m->dec_pos, m->dtype, dx, batch, g.d_model, st, ragged_len());
     dx_embedded = true;
     return batch;
 }
@@ -580,8 +696,9 @@ void Session::decode_step(cudaStream_t st) {
     WB_REQUIRE(batch > 0, "decode_begin was not called");
     const ModelConfig& g = m->cfg;
     const int d = g.d_model, dt = m->dtype, B = batch;
-    const int mode = step_mode();
+    const int mode = step_mode() & 15;
     const bool mega = mode != 0;    // the step starts from the residual stream and its greedy kernel embeds the chosen token
+    WB_REQUIRE(!ragged || forced_tokens == nullptr, "teacher forcing is not available on a refilled (ragged) batch");
     prepare_step(st);
     if (mode == 1) decode_step_mega(st);
     else if (mode == 2) decode_step_chain(st);
@@ -597,6 +714,7 @@ void Session::decode_step(cudaStream_t st) {
         a.pad_id = g.pad; a.eos_id = g.eos; a.max_length = g.max_length;
         a.tokens = tokens; a.tokens_stride = g.max_tgt; a.unfinished = unfinished; a.state = state;
         a.forced_tokens = forced_tokens;
+        a.row_len = ragged ? row_len : nullptr;
         // whole-step kernel: the greedy kernel also embeds the token it chose (the next step starts from the residual stream)
         if (mega) { a.embed_x = dx; a.embed_table = m->emb; a.embed_pos = m->dec_pos; a.embed_d = d; }
         ProfScope ps(this, PROF_GREEDY, st);
@@ -636,7 +754,7 @@ void Session::decode_step_large(cudaStream_t st) {
         if (pre.n_parts > 0) layernorm_preadd(dx, pre, n.g, n.b, dln, dt, B, d, 1e-5f, active, st);
         else layernorm(dx, n.g, n.b, dln, dt, nullptr, B, d, 1e-5f, active, st);
     };
-    decoder_embed(tokens, g.max_tgt, state, m->emb, m->dec_pos, dt, dx, B, d, st);
+    decoder_embed(tokens, g.max_tgt, state, m->emb, m->dec_pos, dt, dx, B, d, st, ragged_len());
     LnPreAdd pending;   // residual update still owed to dx (previous layer's fc2)
     for (int l = 0; l < g.dec_layers; ++l) {
         const DecLayer& L = m->dec[l];
@@ -646,7 +764,7 @@ void Session::decode_step_large(cudaStream_t st) {
         {
             DecAttnArgs a;
             a.dtype = dt; a.q = dqkv; a.q_stride = 3 * d; a.out = datt; a.out_stride = d; a.B = B; a.H = g.n_heads;
-            a.state = state; a.row_active = unfinished;
+            a.state = state; a.row_active = unfinished; a.row_len = ragged_len();
             a.k_new = eoff(dqkv, d, dt); a.v_new = eoff(dqkv, 2 * d, dt); a.new_stride = 3 * d;
             a.k_pages = eoff(self_k, (size_t)l * self_layer_elems(), dt);
             a.v_pages = eoff(self_v, (size_t)l * self_layer_elems(), dt);
@@ -734,13 +852,13 @@ void Session::prepare_step(cudaStream_t st) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     WB_CHECK_CUDA(cudaStreamIsCapturing(st, &cs));
     if (cs != cudaStreamCaptureStatusNone) return;    // enqueue_step prepared the step before it began the capture
-    const int mode = step_mode();
+    const int mode = step_mode() & 15;
     if (mode == 2 && chain_batch != batch) {
         WB_CHECK_CUDA(cudaStreamSynchronize(st));     // queued steps may still read the table
         build_chain_table();
     }
     if (mode != 0 && !dx_embedded) {
-        decoder_embed(tokens, m->cfg.max_tgt, state, m->emb, m->dec_pos, m->dtype, dx, batch, m->cfg.d_model, st);
+        decoder_embed(tokens, m->cfg.max_tgt, state, m->emb, m->dec_pos, m->dtype, dx, batch, m->cfg.d_model, st, ragged_len());
         dx_embedded = true;
     }
 }
@@ -769,7 +887,7 @@ void Session::enqueue_step() {
         step_graph_mode == step_mode()) {
         WB_CHECK_CUDA(cudaGraphLaunch(step_graph, st));
         launch_counter().fetch_add(step_graph_launches, std::memory_order_relaxed);
-        dx_embedded = step_graph_mode != 0;
+        dx_embedded = (step_graph_mode & 15) != 0;
         ++steps_enqueued;
     } else {
         decode_step(st);

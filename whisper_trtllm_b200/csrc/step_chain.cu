@@ -681,7 +681,7 @@ void Session::decode_step_chain(cudaStream_t st) {
         {
             DecAttnArgs a;
             a.dtype = dt; a.q = dqkv; a.q_stride = 3 * d; a.out = datt; a.out_stride = d; a.B = B; a.H = g.n_heads;
-            a.state = state; a.row_active = unfinished;
+            a.state = state; a.row_active = unfinished; a.row_len = ragged_len();
             a.k_new = (uint8_t*)dqkv + (size_t)d * 2; a.v_new = (uint8_t*)dqkv + (size_t)2 * d * 2; a.new_stride = 3 * d;
             a.k_pages = (uint8_t*)self_k + (size_t)l * self_layer_elems() * 2;
             a.v_pages = (uint8_t*)self_v + (size_t)l * self_layer_elems() * 2;

@@ -86,6 +86,9 @@ struct DecAttnArgs {
     // optional per-utterance flags (the greedy loop's `unfinished_sequences`): rows that already emitted EOS are skipped —
     // their K/V are not read at all (their next tokens are pad regardless, generation/utils.py:1506-1510)
     const int* row_active = nullptr;
+    // optional per-utterance lengths (in-flight refill: the rows of a batch are at different positions): when set, row b
+    // appends at slot row_len[b] - 1 and attends over row_len[b] keys instead of state->cur_len
+    const int* row_len = nullptr;
     const void* k_new = nullptr; const void* v_new = nullptr; long long new_stride = 0;  // [b*new_stride + h*64 + j]
     void* k_pages = nullptr; void* v_pages = nullptr;   // [page][H][page_tokens][64]
     const int* page_table = nullptr; int pages_per_seq = 0; int page_tokens = 64;
@@ -93,8 +96,9 @@ struct DecAttnArgs {
 void decode_attention(const DecAttnArgs& a, cudaStream_t stream);
 
 // Decoder embedding: x[b, :] = E[ids[b, cur_len-1], :] + P[cur_len-1, :]  (fp32 residual stream)
+// row_len (optional, in-flight refill): per-row lengths instead of state->cur_len
 void decoder_embed(const int* tokens, int tokens_stride, const StepState* state, const void* emb, const void* pos,
-                   int dtype, float* x, int B, int d, cudaStream_t stream);
+                   int dtype, float* x, int B, int d, cudaStream_t stream, const int* row_len = nullptr);
 
 // stateless variants for the module-level drop-ins (explicit position / dense caches)
 void embed_tokens(const int* ids, long long ids_stride, int B, int T, int pos0, const void* emb, const void* pos, int dtype,
@@ -114,6 +118,9 @@ struct GreedyArgs {
     int* unfinished = nullptr;                      // [B]
     StepState* state = nullptr;
     const int* forced_tokens = nullptr;         // teacher forcing (tests): take ids[b, n] from here instead of argmax
+    // in-flight refill: per-row lengths [B].  Row b writes its token at ids[b, row_len[b]], the processors see its own length,
+    // a row stops growing once it has emitted EOS or reached max_length (no pad is appended: the host pads the results)
+    int* row_len = nullptr;
     // optional (whole-step decoder kernel): also write the embedding of the chosen token, the input of the next step,
     // x[b, :] = E[tok, :] + P[len, :] (fp32 [B, d]; bf16 tables, d % 8 == 0)
     float* embed_x = nullptr; const void* embed_table = nullptr; const void* embed_pos = nullptr; int embed_d = 0;

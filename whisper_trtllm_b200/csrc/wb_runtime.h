@@ -86,6 +86,7 @@ struct Buffers {
     // whole-step kernel (step_mega.cu): attention partials of split items, grid-barrier / per-item arrival counters
     float* mega_part = nullptr; unsigned* mega_sync = nullptr; void* mega_table = nullptr;
     int* result_tokens = nullptr;   // [max_batch, max_tgt] ids in ORIGINAL row order once rows have been compacted away
+    int* row_len = nullptr;         // [max_batch] per-row lengths of a RAGGED batch (in-flight refill); unused while every row is at cur_len
     // fused decode chains (step_chain.cu): the grid-barrier words
     unsigned* chain_sync = nullptr;
 };
@@ -112,7 +113,7 @@ struct Session : Buffers {
     int step_graph_batch = 0;
     int step_graph_generation = -1;
     int step_graph_mode = 0;          // path of the captured step: 0 multi-kernel, 1 whole-step kernel (B <= 16), 2 fused chains
-    int step_mode() const { return use_mega() ? 1 : use_chain() ? 2 : 0; }
+    int step_mode() const { return (use_mega() ? 1 : use_chain() ? 2 : 0) | (ragged ? 16 : 0); }
     bool exclusive = true;            // this session's loop is the only one running on the device (decode_run_multi, n == 1)
     long long step_graph_launches = 0;
     bool step_warm = false;           // one eager step has run (one-time kernel attribute setup done)
@@ -142,6 +143,7 @@ struct Session : Buffers {
     void stem_chunk(const float* mel, int bc, cudaStream_t s);
     void stem(const float* mel, int B, float* x_out, cudaStream_t s);
     void encode(const float* mel, int B, float* enc_out_f32, cudaStream_t s);   // also projects cross K/V
+    void encode_at(const float* mel, int n, int slot0, float* enc_out_f32, cudaStream_t s);   // into batch slots [slot0, slot0 + n)
     void set_encoder_output(const void* enc_states, int dtype, int B, cudaStream_t s);  // external encoder states
     void decode_begin(int B, cudaStream_t s);
     void decode_step(cudaStream_t s);
@@ -168,7 +170,18 @@ struct Session : Buffers {
     // move to the front (ids, page-table rows, cross K/V rows) and the following steps run on `batch` = their number.
     int decode_compact(cudaStream_t s);       // syncs; returns the rows still running (0: the loop has stopped)
     void publish_results(cudaStream_t s);     // current ids -> result_tokens[row_origin]
-    std::vector<int> row_origin;              // original row of decode row i
+    // In-flight refill: between two windows of steps the utterances that have finished leave the batch, the
+    // rows still decoding move to the front and NEW utterances are encoded into the freed slots; from then on the rows of the
+    // batch are at different positions (`ragged`: per-row lengths in row_len, the kernels take them instead of cur_len).
+    // Finished utterances are handed to the caller (ids in the order they were admitted: 0 .. for decode_begin's rows).
+    struct Finished { int utt; int len; std::vector<int> ids; };
+    int decode_refill(const float* mel_new, int n_new, std::vector<Finished>& finished, int* n_admitted, cudaStream_t s);
+    void compact_rows(const std::vector<int>& keep, cudaStream_t s);
+    bool ragged = false;
+    bool refill_mode = false;                 // wb_decode_refill was used since decode_begin: results travel through it, not result_tokens
+    int next_utt = 0;                         // id of the next utterance to be admitted
+    const int* ragged_len() const { return ragged ? row_len : nullptr; }
+    std::vector<int> row_origin;              // original row (utterance id) of decode row i
     std::vector<int> page_table_host;         // host mirror of the page table (rows are swapped, never duplicated)
     bool compacted = false;
     int begin_batch = 0;

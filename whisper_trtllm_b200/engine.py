@@ -281,6 +281,52 @@ class WhisperEngine:
         return ids
 
     @torch.no_grad()
+    def transcribe_stream(self, mel_all: torch.Tensor, window: int = 32, stream=None) -> torch.Tensor:
+        """Greedy transcription of ANY number of utterances with in-flight refill (wb_decode_refill): the engine
+        decodes `max_batch` rows at a time; every `window` steps the utterances that have emitted EOS leave the batch and the next
+        ones of `mel_all` (fp32 [N, 80, 3000], host or device) are encoded into the freed slots and start decoding while the
+        others continue, so the batch stays full until the queue is empty.  Returns int32 [N, L] (L = longest result, rows
+        padded with pad_token_id exactly like the reference's batched loop pads finished rows, generation/utils.py:1506-1510)."""
+        import numpy as np
+        self._single("transcribe_stream()")
+        N = mel_all.shape[0]
+        assert N > 0 and mel_all.dtype == torch.float32
+        cfg = self.config
+        B0 = min(N, self.max_batch)
+
+        def dev(lo, hi):
+            return mel_all[lo:hi].to(self.device, non_blocking=True).contiguous()
+
+        _abi.call("wb_decode_set_forced_tokens", self._session, None)
+        _abi.call("wb_decode_set_logits_dump", self._session, None, 0)
+        self.encode(dev(0, B0), return_hidden=False, stream=stream)
+        self.decode_begin(B0, stream)
+        nxt = B0
+        fin_utt = np.zeros(self.max_batch, dtype=np.int32)
+        fin_len = np.zeros(self.max_batch, dtype=np.int32)
+        fin_ids = np.zeros((self.max_batch, self.max_tgt), dtype=np.int32)
+        results = [None] * N
+        rows = B0
+        while rows > 0:
+            self.decode_run(int(window), check_every=int(window), stream=stream)
+            want = min(self.max_batch, N - nxt)
+            mel_new = dev(nxt, nxt + want) if want > 0 else None
+            n_fin, n_adm, n_rows = c_int(), c_int(), c_int()
+            _abi.call("wb_decode_refill", self._session, ptr(mel_new), want, c_void_p(fin_utt.ctypes.data), c_void_p(fin_len.ctypes.data),
+                      c_void_p(fin_ids.ctypes.data), byref(n_fin), byref(n_adm), byref(n_rows), stream_handle(stream))
+            for k in range(n_fin.value):
+                results[int(fin_utt[k])] = fin_ids[k, :int(fin_len[k])].copy()
+            nxt += n_adm.value
+            rows = n_rows.value
+            self._active = self._shards(max(rows, 1))
+        assert all(r is not None for r in results), "an utterance never finished"
+        L = max(len(r) for r in results)
+        out = torch.full((N, L), cfg["pad_token_id"], dtype=torch.int32)
+        for i, r in enumerate(results):
+            out[i, :len(r)] = torch.from_numpy(r)
+        return out
+
+    @torch.no_grad()
     def transcribe_host(self, mel_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
         """End-to-end call with HOST buffers: H2D copy of the log-mel, encoder, greedy loop, D2H copy of the ids."""
         B = mel_host.shape[0]
