@@ -62,9 +62,12 @@ def load_text_tools(checkpoint_dir: str, config: Dict):
 
 
 class WhisperPipeline:
-    def __init__(self, checkpoint_dir: str, dtype: str = "bfloat16", max_batch: int = 64, device=None, compact_every: int = 32):
+    def __init__(self, checkpoint_dir: str, dtype: str = "bfloat16", max_batch: int = 64, device=None, compact_every: int = 32,
+                 refill: bool = True):
         """``dtype``: "bfloat16" (tcgen05 speed path) or "float32" (token ids identical to the reference's fp32 run).
-        ``compact_every``: every that many tokens the utterances that have emitted EOS leave the decode batch (0 = never)."""
+        ``compact_every``: every that many tokens the utterances that have emitted EOS leave the decode batch (0 = never).
+        ``refill``: when more utterances are queued than the engine has rows, the freed rows are refilled in flight with the
+        next utterances (WhisperEngine.transcribe_stream) instead of decoding batch after batch."""
         from .engine import WhisperEngine
         from .frontend import LogMelFrontend
         self.checkpoint_dir = checkpoint_dir
@@ -72,6 +75,7 @@ class WhisperPipeline:
         self.detokenizer, self.normalizer = load_text_tools(checkpoint_dir, self.config)
         self.max_batch = int(max_batch)
         self.compact_every = int(compact_every)
+        self.refill = bool(refill)
         self.engine = WhisperEngine(self.config, state_dict, dtype=dtype, max_batch=self.max_batch, device=device)
         self.frontend = LogMelFrontend(self.engine.device)
 
@@ -80,6 +84,10 @@ class WhisperPipeline:
     def transcribe_features(self, input_features: torch.Tensor) -> torch.Tensor:
         """log-mel fp32 [n, 80, 3000] (host or device) -> ids int32 [n, max_length] on the host, padded with pad_token_id."""
         L, pad = self.config["max_length"], self.config["pad_token_id"]
+        n = input_features.shape[0]
+        if getattr(self, "refill", False) and n > self.max_batch and hasattr(self.engine, "transcribe_stream"):
+            ids = self.engine.transcribe_stream(input_features.to(torch.float32), window=self.compact_every or 32)
+            return dp.pad_tokens(ids, n, L, pad).cpu()
         rows = []
         for b0 in range(0, input_features.shape[0], self.max_batch):
             mel = input_features[b0:b0 + self.max_batch].to(self.engine.device, torch.float32).contiguous()
@@ -91,6 +99,12 @@ class WhisperPipeline:
     def transcribe_waveforms(self, waves: Sequence) -> torch.Tensor:
         """16 kHz waveforms (any lengths; padded / cut to 30 s) -> ids int32 [n, max_length] on the host."""
         L, pad = self.config["max_length"], self.config["pad_token_id"]
+        waves = list(waves)
+        if getattr(self, "refill", False) and len(waves) > self.max_batch and hasattr(self.engine, "transcribe_stream"):
+            # log-mel of everything first (GPU front-end, batch by batch), then ONE refilled greedy loop over all utterances
+            mel = torch.cat([self.frontend(chunk) for chunk in batches(waves, self.max_batch)], dim=0)
+            ids = self.engine.transcribe_stream(mel, window=self.compact_every or 32)
+            return dp.pad_tokens(ids, len(waves), L, pad).cpu()
         rows = []
         for chunk in batches(list(waves), self.max_batch):
             ids = self.engine.generate(self.frontend(chunk), compact_every=self.compact_every)
