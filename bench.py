@@ -251,7 +251,7 @@ def run_reference(args):
         "note": "ms_per_step is the MEASURED wall time of one sample (what actually ran); value = 30 s x sample utterances / "
                 "(measured + extrapolated remainder of the 447-step loop).  One CPU process regardless of n_gpus.",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def timed_passes(eng, mel_dev, mel_host, ids_host, steps, gather, sync_all, prof_step):
@@ -347,8 +347,32 @@ def decode_step_microbench(eng, cfg, B_max, es, peaks, t_len=224, steps=8):
     return {"length": t_len, "unit": "us per decode step (24 layers + LM head + argmax)", "by_batch": out}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Rank 0 prints ONE JSON line on stdout.  Libraries write there too (NCCL's version banner goes to the C stdout): file
+    descriptor 1 is pointed at stderr for the whole run and the line is written to the saved descriptor at the end."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -553,7 +577,7 @@ def main():
             r = cpu_reference_rtfx(args.size, args.max_length, 16, 128)
             line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
