@@ -1,5 +1,9 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "refill or session_options or finished_rows" > gpurun_out/r2v_pytest.log 2>&1
-echo "rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed|^E  " gpurun_out/r2v_pytest.log | head -30
+python tools/chain_debug.py medium.en 24 2>&1 | grep -v Warn | tail -1
+for pdl in 0 1; do
+  echo "== pdl $pdl"
+  timeout 300 python tools/decode_step_bench.py --batches 32,64,256 --lengths 128,436 --chain 1 --pdl $pdl 2> gpurun_out/r2y_step_pdl$pdl.err | grep "^| [0-9]"
+  tail -2 gpurun_out/r2y_step_pdl$pdl.err
+done
