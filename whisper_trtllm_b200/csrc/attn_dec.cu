@@ -417,7 +417,9 @@ void decode_attention(const DecAttnArgs& a, cudaStream_t stream) {
     // CTA per item, the keys split over its 4 warps.  (dev) WB_SELF_CTA_ITEMS overrides the threshold.
     static const int cta_items_max = std::getenv("WB_SELF_CTA_ITEMS") ? std::atoi(std::getenv("WB_SELF_CTA_ITEMS")) : 1024;
     if (paged && a.dtype == BF16 && g_self_attn_variant == 0 && a.B * a.H <= cta_items_max) {
-        launch<bf16, true, THREADS_SELF, 4>(a, stream);
+        static const int cta_threads = std::getenv("WB_SELF_CTA_THREADS") ? std::atoi(std::getenv("WB_SELF_CTA_THREADS")) : 128;   // (dev)
+        if (cta_threads == 256) launch<bf16, true, 256, 4>(a, stream);
+        else launch<bf16, true, THREADS_SELF, 4>(a, stream);
         return;
     }
     const bool warp_variant = g_self_attn_variant == 0 || g_self_attn_variant == 5 || g_self_attn_variant == 6;
