@@ -696,3 +696,34 @@ def test_in_flight_refill_bf16_large_batch_path():
             agree += int(got[:k] == rows[u][:k])
         assert agree >= 41, (window, agree)
     eng.close()
+
+
+def test_attention_as_phases_of_the_layer_launch_opt_in():
+    """Session option "merge_attention": for small batches the two attention kernels of a layer run as phases of the layer's
+    persistent launch (one launch per decoder layer).  Measured slower than the stand-alone attention kernels, hence opt-in
+    (profiles/r02_kernel_variants.md) - but it must stay correct: same logits as the default 4-launches-per-layer step, fewer
+    launches, also on a ragged (refilled) batch."""
+    steps = 12
+    cfg = synth.make_config("tiny.en", max_length=steps + 1)
+    sd = synth.make_weights(cfg, seed=5)
+    mel = synth.make_mel(40, seed=8)
+    a = WhisperEngine(cfg, sd, dtype="bfloat16", max_batch=24, enc_chunk=8, device=DEV)
+    b = WhisperEngine(cfg, sd, dtype="bfloat16", max_batch=24, enc_chunk=8, device=DEV)
+    b.set_option("merge_attention", 1)
+    ids = a.generate(mel[:24].to(DEV)).cpu()
+    forced = ids.long()
+    n0 = a.launch_count()
+    _, la = a.generate(mel[:24].to(DEV), forced_tokens=forced, dump_logits_steps=steps)
+    na = a.launch_count() - n0
+    _, lb = b.generate(mel[:24].to(DEV), forced_tokens=forced, dump_logits_steps=steps)
+    nb = a.launch_count() - n0 - na
+    L = cfg["decoder_layers"]
+    assert na - nb >= steps * 3 * L - 8          # 4 launches per layer -> 1
+    for s in range(steps):
+        assert _rel(lb[s], la[s]) < 6e-3, s
+    sa = a.transcribe_stream(mel, window=5).cpu()
+    sb = b.transcribe_stream(mel, window=5).cpu()
+    assert sa.shape[0] == sb.shape[0] == 40
+    assert float((sa[:, :4] == sb[:, :4]).all(dim=1).float().mean()) >= 0.9
+    a.close()
+    b.close()

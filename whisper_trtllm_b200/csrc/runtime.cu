@@ -517,7 +517,8 @@ void Session::set_option(const std::string& name, int value) {
     if (name == "small_batch_path") opt_small_batch_path = value;
     else if (name == "decode_chain_path") opt_decode_chain_path = value;
     else if (name == "cuda_graphs") opt_cuda_graphs = value;
-    else throw Error(-1, "unknown session option '" + name + "' (small_batch_path, decode_chain_path, cuda_graphs)");
+    else if (name == "merge_attention") { opt_merge_attention = value; chain_batch = -1; step_graph_batch = -1; }   // phase tables and step graph are rebuilt
+    else throw Error(-1, "unknown session option '" + name + "' (small_batch_path, decode_chain_path, cuda_graphs, merge_attention)");
 }
 
 // ids of the current decode rows -> result buffer, original row order

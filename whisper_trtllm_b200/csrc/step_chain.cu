@@ -50,7 +50,7 @@ constexpr uint32_t CH_TMEM_COLS = 2 * CH_MAX_BN;                   // two accumu
 constexpr uint32_t CH_SMEM_BYTES = CH_STAGES * CH_STAGE_BYTES + CH_STAGING_BYTES + 512 /*barriers, LN scratch*/ + 1024 /*alignment*/;
 constexpr int CH_MAX_PARTS = MAX_K_SPLITS;
 
-enum { CH_GEMM = 0, CH_LN = 1 };
+enum { CH_GEMM = 0, CH_LN = 1, CH_SELF = 2, CH_CROSS = 3 };
 enum { CH_EPI_PARTIAL = 0, CH_EPI_BF16 = 1, CH_EPI_GELU_BF16 = 2 };
 
 // One phase of a chain.  GEMM: out = epi(A[M, K] W[N, K]^T) on 128 x bn tiles, k_splits slabs; LN: the consumer side of a
@@ -71,11 +71,13 @@ struct alignas(128) ChainPhase {
     const float* parts;         // LN: slabs
     const float* gamma; const float* beta;
     float* x;                   // LN: fp32 residual stream [M, d], updated in place
-    int pad[4];
+    // attention phases (small batches: the attention kernels become phases of the layer's launch).  SELF: this layer's K / V pages;
+    // CROSS: this layer's K / V of the encoder frames; q of CROSS = bias + n_parts slabs in `parts` (the cross-q GEMM's split-K output)
+    const bf16* kbase; const bf16* vbase;
 };
 static_assert(sizeof(ChainPhase) == 384, "ChainPhase layout");
 
-constexpr int CH_MAX_PHASES = 6;   // phases of one launch: the descriptors travel as kernel parameters
+constexpr int CH_MAX_PHASES = 11;  // phases of one launch (a whole decoder layer with its two attention phases): kernel parameters
 
 // The phase descriptors of ONE launch live in the kernel parameters (constant bank): every per-phase scalar is a uniform
 // load, the loops they control are provably warp-uniform, and the tensor maps sit where the TMA unit fetches them fastest.
@@ -88,6 +90,12 @@ struct ChainParams {
     int ph0;                    // index of ph[0] in the step's phase list (trace slots only)
     int M, d;
     float eps;
+    // attention phases
+    int H, n_ctx, pages_per_seq;
+    long long cross_bstride;    // elements between the cross K (or V) of consecutive utterances
+    const bf16* qkv;            // fused q | k | v rows of the step [M, 3 d] (SELF: q, and the row to append)
+    bf16* attn_out;             // [M, d]
+    const int* unfinished; const int* row_len; const int* page_table;
     const StepState* state;
     unsigned* sync;             // [0] grid-barrier arrivals, [1] exits: zero between launches
     long long* trace;           // optional (tools/chain_trace.py): SM clock stamps of CTA 0, 8 slots per phase
@@ -162,6 +170,195 @@ __device__ __forceinline__ void ch_grid_poll(const unsigned* counter, unsigned t
             printf("wb: chain grid barrier timeout (block %d thread %d target %u)\n", blockIdx.x, threadIdx.x, target);
             __trap();
         }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Attention phases (batches whose (utterance, head) items fit the worker warps of one launch: B x H <= 8 x SMs).  At these
+// sizes the two attention kernels of a layer were launch-latency bound (13 + 35 us of kernel for 4 + 28 us of bytes at B = 32,
+// plus a kernel boundary each); as phases of the layer's launch they cost a grid barrier instead.  One warp PAIR per item, the
+// keys interleaved between the two warps in blocks, merged through shared memory; 8 lanes per key row, 16-byte loads, online
+// softmax per lane group (same arithmetic as attn_dec.cu: fp32 scores and statistics, __expf, q pre-scaled in the weights).
+// ------------------------------------------------------------------------------------------------------------------------
+struct ChainAttnAcc {
+    float m, l, acc[8];
+};
+
+__device__ __forceinline__ void ch_attn_block(ChainAttnAcc& st, const float (&qf)[8], const Vec16<bf16>* kr, const Vec16<bf16>* vr,
+                                              int first_key, int key_step, int n, int nu) {
+    float sc[8];
+    float mb = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        if (u < nu) {
+            float kf[8];
+            kr[u].unpack(kf);
+            float dot = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dot = fmaf(qf[i], kf[i], dot);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+            sc[u] = (first_key + u * key_step < n) ? dot : -INFINITY;
+            mb = fmaxf(mb, sc[u]);
+        }
+    }
+    const float m_new = fmaxf(st.m, mb);
+    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+    const float scale = __expf(st.m - m_use);
+    st.l *= scale;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st.acc[i] *= scale;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        if (u < nu) {
+            const float pr = __expf(sc[u] - m_use);
+            st.l += pr;
+            float vf[8];
+            vr[u].unpack(vf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) st.acc[i] = fmaf(pr, vf[i], st.acc[i]);
+        }
+    }
+    st.m = m_new;
+}
+
+// merge the four 8-lane key groups of a warp (lanes with equal `sub`): afterwards lanes 0-7 hold the warp's state
+__device__ __forceinline__ void ch_attn_merge_groups(ChainAttnAcc& st) {
+#pragma unroll
+    for (int o = 8; o < 32; o <<= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, st.m, o);
+        const float ol = __shfl_xor_sync(0xffffffffu, st.l, o);
+        const float mm = fmaxf(st.m, om);
+        const float s1 = (st.m == -INFINITY) ? 0.f : __expf(st.m - mm);
+        const float s2 = (om == -INFINITY) ? 0.f : __expf(om - mm);
+        st.l = st.l * s1 + ol * s2;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float oa = __shfl_xor_sync(0xffffffffu, st.acc[i], o);
+            st.acc[i] = st.acc[i] * s1 + oa * s2;
+        }
+        st.m = mm;
+    }
+}
+
+// the second warp of a pair hands its state over through shared memory, the first merges (fixed order) and writes the row
+__device__ __forceinline__ void ch_attn_finish(ChainAttnAcc& st, float* pair_smem, int half, int pair_in_cta, int lane, bf16* out_row) {
+    const int sub = lane & 7;
+    if (half == 1 && lane < 8) {
+        if (sub == 0) { pair_smem[0] = st.m; pair_smem[1] = st.l; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pair_smem[8 + sub * 8 + i] = st.acc[i];
+    }
+    ch_named_bar(4 + pair_in_cta, 64);
+    if (half == 0 && lane < 8) {
+        const float om = pair_smem[0], ol = pair_smem[1];
+        const float mm = fmaxf(st.m, om);
+        const float s1 = (st.m == -INFINITY) ? 0.f : __expf(st.m - mm);
+        const float s2 = (om == -INFINITY) ? 0.f : __expf(om - mm);
+        const float inv = 1.0f / (st.l * s1 + ol * s2);
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (st.acc[i] * s1 + pair_smem[8 + sub * 8 + i] * s2) * inv;
+        Vec16<bf16> v;
+        v.pack(o);
+        st16(out_row + sub * 8, v);
+    }
+}
+
+// cached self-attention of the step: append the new K / V row in place, attend over the row's length
+__device__ __forceinline__ void ch_self_attention(const ChainParams& p, const ChainPhase& D, int wwarp, int lane, float* scratch) {
+    const int sub = lane & 7, grp = lane >> 3;
+    const int half = wwarp & 1, pair_in_cta = wwarp >> 1;
+    const int items = p.M * p.H, d = p.d;
+    int parity = 0;
+    for (int item = (int)blockIdx.x * 4 + pair_in_cta; item < items; item += (int)gridDim.x * 4) {   // pair-uniform trip count
+        const int b = item / p.H, h = item - b * p.H;
+        if (p.unfinished[b] == 0) continue;                  // finished utterance (pair-uniform)
+        const int n = p.row_len != nullptr ? p.row_len[b] : p.state->cur_len;
+        float* pair_smem = scratch + (pair_in_cta * 2 + parity) * 72;
+        parity ^= 1;
+        const int my_page = lane < p.pages_per_seq ? p.page_table[(size_t)b * p.pages_per_seq + lane] : 0;
+        const bf16* qrow = p.qkv + (size_t)b * 3 * d + h * 64 + sub * 8;
+        float qf[8];
+        ld16(qrow).unpack(qf);
+        const Vec16<bf16> k_new = ld16(qrow + d), v_new = ld16(qrow + 2 * d);
+        auto row_off = [&](int s) -> size_t {
+            const int page = __shfl_sync(0xffffffffu, my_page, s >> 6);
+            return (((size_t)page * p.H + h) * 64 + (s & 63)) * 64 + sub * 8;
+        };
+        {   // in-place append at slot n - 1 (this step reads that row from the registers above)
+            const size_t off = row_off(n - 1);
+            if (half == 0 && grp == 0) {
+                st16(const_cast<bf16*>(D.kbase) + off, k_new);
+                st16(const_cast<bf16*>(D.vbase) + off, v_new);
+            }
+        }
+        ChainAttnAcc st;
+        st.m = -INFINITY; st.l = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) st.acc[i] = 0.f;
+        for (int sb = half * 16; sb < n; sb += 32) {         // blocks of 16 keys, alternating between the two warps
+            Vec16<bf16> kr[8], vr[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int s = min(sb + grp + u * 4, n - 1);
+                const size_t off = row_off(s);
+                kr[u] = ld16_issue(D.kbase + off);
+                vr[u] = ld16_issue(D.vbase + off);
+                if (s == n - 1) { kr[u] = k_new; vr[u] = v_new; }
+            }
+            ch_attn_block(st, qf, kr, vr, sb + grp, 4, n, 4);
+        }
+        ch_attn_merge_groups(st);
+        ch_attn_finish(st, pair_smem, half, pair_in_cta, lane, p.attn_out + (size_t)b * d + h * 64);
+    }
+}
+
+// cross-attention over the encoder K / V projected once per utterance; q = bias + split-K slabs of the cross-q GEMM
+__device__ __forceinline__ void ch_cross_attention(const ChainParams& p, const ChainPhase& D, int wwarp, int lane, float* scratch) {
+    const int sub = lane & 7, grp = lane >> 3;
+    const int half = wwarp & 1, pair_in_cta = wwarp >> 1;
+    const int items = p.M * p.H, d = p.d, n = p.n_ctx;
+    int parity = 0;
+    for (int item = (int)blockIdx.x * 4 + pair_in_cta; item < items; item += (int)gridDim.x * 4) {
+        const int b = item / p.H, h = item - b * p.H;
+        if (p.unfinished[b] == 0) continue;
+        float* pair_smem = scratch + (pair_in_cta * 2 + parity) * 72;
+        parity ^= 1;
+        float qf[8];
+        {
+            const int c0 = h * 64 + sub * 8;
+#pragma unroll
+            for (int i = 0; i < 8; i += 4) {
+                float4 t = D.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(D.bias + c0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int s = 0; s < D.n_parts; ++s) {
+                    const float4 u = ch_ld_cg_f4(D.parts + (size_t)s * D.split_stride + (size_t)b * d + c0 + i);
+                    t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                }
+                qf[i] = t.x; qf[i + 1] = t.y; qf[i + 2] = t.z; qf[i + 3] = t.w;
+            }
+        }
+        const size_t base = (size_t)b * p.cross_bstride + (size_t)h * n * 64 + sub * 8;
+        const bf16* kb = D.kbase + base;
+        const bf16* vb = D.vbase + base;
+        ChainAttnAcc st;
+        st.m = -INFINITY; st.l = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) st.acc[i] = 0.f;
+        for (int sb = half * 32; sb < n; sb += 64) {         // blocks of 32 keys, alternating between the two warps
+            Vec16<bf16> kr[8], vr[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const size_t off = (size_t)min(sb + grp + u * 4, n - 1) * 64;
+                kr[u] = ld16_stream(kb + off);
+                vr[u] = ld16_stream(vb + off);
+            }
+            ch_attn_block(st, qf, kr, vr, sb + grp, 4, n, 8);
+        }
+        ch_attn_merge_groups(st);
+        ch_attn_finish(st, pair_smem, half, pair_in_cta, lane, p.attn_out + (size_t)b * d + h * 64);
     }
 }
 
@@ -293,7 +490,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const __gri
                 }
                 if (D.bias != nullptr)
                     for (int j = lane * 32; j < D.N; j += 32 * 32) ch_prefetch_l2(D.bias + j);
-            } else {
+            } else if (D.kind == CH_LN) {
                 for (int j = lane * 32; j < p.d; j += 32 * 32) {
                     ch_prefetch_l2(D.gamma + j);
                     ch_prefetch_l2(D.beta + j);
@@ -423,6 +620,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) decode_chain_kernel(const __gri
                     if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
+            } else if (D.kind == CH_SELF || D.kind == CH_CROSS) {
+                if (i > 0) ch_named_bar(1, CH_EPI_WARPS * 32);   // thread 0 of the group has seen the barrier (above)
+                if (D.kind == CH_SELF) ch_self_attention(p, D, warp - 4, lane, staging);
+                else ch_cross_attention(p, D, warp - 4, lane, staging);
             } else {
                 // ---- LayerNorm phase: x[r] += bias + sum of slabs (fixed order); out[r] = LN(x[r]) as bf16
                 if (i > 0) ch_named_bar(1, CH_EPI_WARPS * 32);   // thread 0 of the group has seen the barrier (above)
@@ -624,7 +825,46 @@ void Session::build_chain_table() {
             ln_phase(o[7], m->dec_ln, s, Y.fc2.b);
         }
     }
+    // Small batches, opt-in (see chain_merge_ok): the two attention kernels of a layer become phases of ONE launch per layer
+    //   SELF, out-proj, LN2, cross-q, CROSS, cross-out, LN3, fc1, fc2, LN1' (final LayerNorm), qkv'
+    chain_merged.clear();
+    if (chain_merge_ok()) {
+        std::vector<ChainPhase> mlist;
+        mlist.push_back(t[0]);
+        mlist.push_back(t[1]);
+        const size_t per_kv = (size_t)max_batch * g.n_heads * g.n_ctx * 64;
+        for (int l = 0; l < L; ++l) {
+            const ChainPhase* o = &t[(size_t)2 + 9 * l];
+            ChainPhase a;
+            std::memset(&a, 0, sizeof(a));
+            a.kind = CH_SELF;
+            a.kbase = (const bf16*)self_k + (size_t)l * self_layer_elems();
+            a.vbase = (const bf16*)self_v + (size_t)l * self_layer_elems();
+            mlist.push_back(a);
+            for (int k = 0; k < 3; ++k) mlist.push_back(o[k]);
+            std::memset(&a, 0, sizeof(a));
+            a.kind = CH_CROSS;
+            a.kbase = (const bf16*)cross + (size_t)l * cross_layer_elems();
+            a.vbase = a.kbase + per_kv;
+            a.parts = dpart; a.n_parts = chain_q_parts[l]; a.split_stride = part_stride; a.bias = m->dec[l].cq.b;
+            mlist.push_back(a);
+            for (int k = 3; k < (l + 1 < L ? 9 : 8); ++k) mlist.push_back(o[k]);
+        }
+        chain_merged.resize(mlist.size() * sizeof(ChainPhase));
+        std::memcpy(chain_merged.data(), mlist.data(), chain_merged.size());
+    }
     chain_batch = B;
+}
+
+// the attention phases need one warp pair per (utterance, head) item in at most two rounds
+// OPT-IN (wb_session_set_option "merge_attention" = 1, or WB_CHAIN_MERGE=1): measured SLOWER than the separate attention kernels -
+// us per step at t = 128, same call: B = 17 2359 vs 1826, B = 32 2496 vs 2208, B = 64 3714 vs 2982 (profiles/r02_kernel_variants.md).
+// One CTA of 384 threads per SM gives the attention phases 8 warps x 8 KB of loads in flight per SM where the stand-alone kernels
+// keep 16 warps x 8 KB: the launch gaps it removes (~10 us per layer) are smaller than what the streaming loses.
+bool Session::chain_merge_ok() const {
+    static const bool env_on = std::getenv("WB_CHAIN_MERGE") != nullptr;   // (dev)
+    return (opt_merge_attention == 1 || (opt_merge_attention < 0 && env_on)) && chain_grid > 0 && pages_per_seq <= 32 &&
+           batch * m->cfg.n_heads <= 8 * chain_grid;
 }
 
 void Session::init_chain() {
@@ -642,18 +882,24 @@ void Session::init_chain() {
     WB_CHECK_CUDA(cudaMemset(chain_sync, 0, chain_sync_bytes()));
 }
 
-void Session::launch_chain(int ph_begin, int ph_end, cudaStream_t st) {
+void Session::launch_chain(int ph_begin, int ph_end, cudaStream_t st, bool merged) {
     static const bool serial = std::getenv("WB_CHAIN_SERIAL") != nullptr;   // (dev) one launch per phase: kernel boundaries instead of grid barriers
     if (serial && ph_end - ph_begin > 1) {
-        for (int ph = ph_begin; ph < ph_end; ++ph) launch_chain(ph, ph + 1, st);
+        for (int ph = ph_begin; ph < ph_end; ++ph) launch_chain(ph, ph + 1, st, merged);
         return;
     }
-    WB_REQUIRE(ph_end > ph_begin && ph_end - ph_begin <= CH_MAX_PHASES && (size_t)ph_end * sizeof(ChainPhase) <= chain_host.size(),
+    const std::vector<unsigned char>& table = merged ? chain_merged : chain_host;
+    WB_REQUIRE(ph_end > ph_begin && ph_end - ph_begin <= CH_MAX_PHASES && (size_t)ph_end * sizeof(ChainPhase) <= table.size(),
                "fused chains: bad phase range");
+    const ModelConfig& g = m->cfg;
     ChainParams p;
     std::memset(&p, 0, sizeof(p));
-    std::memcpy(p.ph, chain_host.data() + (size_t)ph_begin * sizeof(ChainPhase), (size_t)(ph_end - ph_begin) * sizeof(ChainPhase));
-    p.n_ph = ph_end - ph_begin; p.ph0 = ph_begin; p.M = batch; p.d = m->cfg.d_model; p.eps = 1e-5f;
+    std::memcpy(p.ph, table.data() + (size_t)ph_begin * sizeof(ChainPhase), (size_t)(ph_end - ph_begin) * sizeof(ChainPhase));
+    p.n_ph = ph_end - ph_begin; p.ph0 = ph_begin; p.M = batch; p.d = g.d_model; p.eps = 1e-5f;
+    p.H = g.n_heads; p.n_ctx = g.n_ctx; p.pages_per_seq = pages_per_seq;
+    p.cross_bstride = (long long)g.n_heads * g.n_ctx * 64;
+    p.qkv = (const bf16*)dqkv; p.attn_out = (bf16*)datt;
+    p.unfinished = unfinished; p.row_len = ragged_len(); p.page_table = page_table;
     p.state = state; p.sync = chain_sync; p.trace = step_trace_ptr();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(chain_grid);
@@ -675,6 +921,17 @@ void Session::decode_step_chain(cudaStream_t st) {
     const int d = g.d_model, dt = m->dtype, B = batch, L = g.dec_layers;
     WB_REQUIRE(chain_batch == B, "fused chains: the phase table was built for another batch (prepare_step was not called)");
     const int* active = &state->active;
+    if (!chain_merged.empty()) {
+        // small batches: one launch per decoder layer, the attention kernels are phases of it (2 + L launches + LM head + argmax)
+        { ProfScope ps(this, PROF_DEC_GEMM, st); launch_chain(0, 2, st, true); }
+        int ph = 2;
+        for (int l = 0; l < L; ++l) {
+            const int n = l + 1 < L ? 11 : 10;
+            ProfScope ps(this, PROF_DEC_GEMM, st);
+            launch_chain(ph, ph + n, st, true);
+            ph += n;
+        }
+    } else {
     { ProfScope ps(this, PROF_DEC_GEMM, st); launch_chain(0, 2, st); }
     for (int l = 0; l < L; ++l) {
         const int base = 2 + 9 * l;
@@ -703,6 +960,7 @@ void Session::decode_step_chain(cudaStream_t st) {
             decode_attention(a, st);
         }
         { ProfScope ps(this, PROF_DEC_GEMM, st); launch_chain(base + 3, l + 1 < L ? base + 9 : base + 8, st); }
+    }
     }
     {
         // LM head: proj_out shares storage with embed_tokens (modeling_whisper.py:1335,1433), no bias

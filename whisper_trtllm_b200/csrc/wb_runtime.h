@@ -118,7 +118,7 @@ struct Session : Buffers {
     long long step_graph_launches = 0;
     bool step_warm = false;           // one eager step has run (one-time kernel attribute setup done)
     // per-session overrides of the process-wide A/B switches (wb_session_set_option): -1 inherit, 0 off, 1 on
-    int opt_small_batch_path = -1, opt_decode_chain_path = -1, opt_cuda_graphs = -1;
+    int opt_small_batch_path = -1, opt_decode_chain_path = -1, opt_cuda_graphs = -1, opt_merge_attention = -1;
     bool graph_capture_failed = false;   // stream capture of the step failed once on this session: eager launches from then on
     void set_option(const std::string& name, int value);
     bool dx_embedded = false;         // dx holds E[last token] + P[position] of every row (what the whole-step kernel starts from)
@@ -160,10 +160,12 @@ struct Session : Buffers {
     bool use_chain() const;
     void init_chain();                        // constructor: kernel attributes, grid size
     void build_chain_table();                 // phase table for the current batch
-    void launch_chain(int ph_begin, int ph_end, cudaStream_t s);
+    void launch_chain(int ph_begin, int ph_end, cudaStream_t s, bool merged = false);
+    bool chain_merge_ok() const;              // this batch is small enough for the attention kernels to become phases of the layer's launch
     void prepare_step(cudaStream_t s);        // host-side work a step needs OUTSIDE a graph capture (phase table, embedding in dx)
     int chain_grid = 0, chain_batch = -1;
     std::vector<int> chain_q_parts;           // split-K slabs of each layer's cross-attention q projection
+    std::vector<unsigned char> chain_merged;  // same with the attention phases in place (small batches: one launch per decoder layer); empty = not used
     std::vector<unsigned char> chain_host;    // phase descriptors of the step (tensor maps included); a launch copies its slice into its kernel parameters
     int decode_run(int max_steps, int check_every, cudaStream_t s);  // returns final length (syncs)
     // Finished-row compaction: utterances that emitted EOS leave the decode batch; the rows still running
