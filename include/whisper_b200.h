@@ -109,8 +109,10 @@ WB_API int wb_session_create(wb_model* m, int max_batch, int enc_chunk, void* wo
 WB_API int wb_session_destroy(wb_session* s);
 /* Per-session override of a process-wide A/B switch (the wb_set_* functions below change the default for every session of the
  * process; a session option wins for that session only).  name: "small_batch_path" (wb_set_small_batch_path != 0),
- * "decode_chain_path" (wb_set_decode_chain_path), "cuda_graphs" (wb_set_cuda_graphs); value: 1 on, 0 off, -1 inherit the
- * process-wide switch again.  Takes effect at the next decode step (a captured step graph of the other kind is rebuilt).
+ * "decode_chain_path" (wb_set_decode_chain_path), "cuda_graphs" (wb_set_cuda_graphs), "merge_attention" (no process-wide
+ * switch; default off: for small batches the attention kernels run as phases of the layer's persistent launch - one launch per
+ * decoder layer, measured slower than the stand-alone attention kernels); value: 1 on, 0 off, -1 inherit the process-wide
+ * switch again.  Takes effect at the next decode step (a captured step graph of the other kind is rebuilt).
  * The reference has no equivalent (one TensorRT execution context per engine, runtime/session.py:53-61). */
 WB_API int wb_session_set_option(wb_session* session, const char* name, int value);
 
