@@ -156,7 +156,9 @@ WB_API int wb_decode_refill(wb_session* session, const float* mel_new, int n_new
                             int32_t* finished_ids, int* n_finished, int* n_admitted, int* n_rows, wb_stream stream);
 /* ids int32 [B, max_target_positions] (row stride max_target_positions), original row order; device pointer owned by the session */
 WB_API int wb_decode_tokens(wb_session* s, const int32_t** tokens_dev, int* row_stride);
-/* raw next-token logits of the last step, fp32 [B, vocab] (the decoder engine's output tensor, model.py:464) */
+/* raw next-token logits of the last wb_decode_step, fp32 [B, vocab] (the decoder engine's output tensor, model.py:464).
+ * wb_decode_run does NOT materialise logits in the bf16 path (the LM head's epilogue applies the logits processors and reduces
+ * the argmax per column tile) unless a logits dump is set (wb_decode_set_logits_dump): after it the buffer holds scratch. */
 WB_API int wb_decode_logits(wb_session* s, const float** logits_dev);
 /* test hooks: teacher forcing (ids taken from forced[B, max_target_positions]) and per-step logits dump */
 WB_API int wb_decode_set_forced_tokens(wb_session* s, const int32_t* forced_dev);

@@ -727,3 +727,33 @@ def test_attention_as_phases_of_the_layer_launch_opt_in():
     assert float((sa[:, :4] == sb[:, :4]).all(dim=1).float().mean()) >= 0.9
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("size,B,chain", [("tiny.en", 24, 1), ("tiny.en", 40, 0), ("base.en", 130, 1), ("tiny.en", 300, 1)])
+def test_lm_head_fused_with_processors_and_argmax(size, B, chain):
+    """Greedy loop steps that need no logits (bf16, CUDA-graph loop) run the LM head with the logits processors + argmax in its
+    epilogue (gemm_tc.cu: per column tile the maximum of the columns that are not suppressed, reduced by the greedy kernel): the
+    [B, 51864] fp32 logits are neither written nor re-read (reference: run.py:199-205 + logits_process.py:1281-1328 on a
+    materialised tensor).  The ids must be EXACTLY those of the processors + first-max argmax applied to the materialised logits
+    of the same states (teacher-forced dump run of the same engine: same accumulators, so equality is bit-level)."""
+    from whisper_trtllm_b200 import _abi
+    steps = 9
+    cfg = synth.make_config(size, max_length=steps + 1)
+    sd = synth.make_weights(cfg, seed=23)
+    mel = synth.make_mel(B, seed=4).to(DEV)
+    try:
+        _abi.call("wb_set_decode_chain_path", chain)
+        eng = WhisperEngine(cfg, sd, dtype="bfloat16", max_batch=B, enc_chunk=min(B, 16), device=DEV)
+        ids = eng.generate(mel).cpu().long()                       # fused epilogue inside the loop
+        assert ids.shape == (B, steps + 1) and (ids[:, 1] == 50362).all()
+        _, lg = eng.generate(mel, forced_tokens=ids, dump_logits_steps=steps)   # materialised logits of the same states
+        for s in range(steps):
+            want = R.process_logits(lg[s].float().cpu(), s + 1, cfg).argmax(-1)
+            assert torch.equal(want, ids[:, s + 1]), (s, (want != ids[:, s + 1]).nonzero().flatten().tolist()[:5])
+        # suppressed ids never appear, and begin-suppress holds at the first free position
+        sup = set(cfg["suppress_tokens"])
+        assert not (set(ids[:, 2:].flatten().tolist()) & sup)
+        assert not (set(ids[:, 2].tolist()) & set(cfg["begin_suppress_tokens"]))
+        eng.close()
+    finally:
+        _abi.call("wb_set_decode_chain_path", 1)

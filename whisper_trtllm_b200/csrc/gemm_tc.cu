@@ -165,6 +165,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::tcgen05_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
             const int row0 = m_blk * BM + q * 32;
+            if (ept.am_val != nullptr) {
+                // ---- fused logits processors + argmax (LM head): thread == row, no transposition, no logits in HBM
+                const int row = row0 + lane;
+                int bits = 1;
+                if (row < ept.M) bits |= ((ept.am_row_len != nullptr ? ept.am_row_len[row] : ept.am_state->cur_len) == ept.am_begin) ? 2 : 0;
+                float best = -INFINITY;
+                int besti = 0x7fffffff;
+#pragma unroll 1
+                for (int ci = 0; ci < SLABS_PER_WARP; ++ci) {
+                    const int c = half * SLABS_PER_WARP + ci;
+                    if (c >= SLABS) break;
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(t_row + c * 32, v);
+                    ptx::tmem_ld_wait();
+                    const int nb = n_blk * BN + c * 32;
+                    if (nb < ept.N) {                         // (N % 8 == 0: a slab is valid in whole 8-column groups)
+#pragma unroll
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            if (nb + g8 * 8 < ept.N) {
+                                const uint2 mm = __ldg(reinterpret_cast<const uint2*>(ept.am_mask + nb + g8 * 8));   // same address in every lane
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const unsigned mbyte = ((j < 4 ? mm.x : mm.y) >> ((j & 3) * 8)) & 0xffu;
+                                    const float val = __uint_as_float(v[g8 * 8 + j]);
+                                    if ((mbyte & bits) == 0 && val > best) { best = val; besti = nb + g8 * 8 + j; }
+                                }
+                            }
+                        }
+                    }
+                }
+                if (row < ept.M && run) {
+                    const size_t e = (size_t)row * ept.am_stride + (size_t)n_blk * HALVES + half;
+                    ept.am_val[e] = best;
+                    ept.am_idx[e] = besti;
+                }
+                ptx::tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
             const int g0 = ept.m_period_in > 0 ? row0 / ept.m_period_in : 0;   // one division per tile (period >= 128 rows)
 #pragma unroll 1
             for (int ci = 0; ci < SLABS_PER_WARP; ++ci) {
@@ -325,6 +366,7 @@ static void launch_tc(const GemmArgs& a, int k_splits, cudaStream_t stream) {
     const int mt = ceil_div(a.M, BM), nt = ceil_div(a.N, BN);
     const int grid = std::min(mt * nt * k_splits, sm_count());
     EpiParams ep = make_epi(a);
+    if (a.am_count != nullptr) *a.am_count = nt * (Cfg::EPI_WARPS / 4);
     launch_kernel(gemm_tc_kernel<BN, kLean>, dim3(grid), dim3(Cfg::NUM_THREADS), Cfg::SMEM_BYTES, stream, true, tmA, tmW, a.K, mt, nt,
                   k_splits, a.split_stride, ep, a.active);
 }
@@ -366,8 +408,14 @@ static void pick_config(const GemmArgs& a, int max_splits, int& bn_out, int& spl
     }
 }
 
+int gemm_argmax_partials(int N) { return ceil_div(N, 32) * 2; }   // upper bound for every tile width (narrowest tile 32, two halves)
+
 void gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     validate_gemm_common(a);
+    if (a.am_val != nullptr)
+        WB_REQUIRE(a.am_idx != nullptr && a.am_mask != nullptr && a.am_state != nullptr && a.k_splits == 1 && a.out_mode == 0 &&
+                   a.m_period_in == 0 && a.am_stride >= gemm_argmax_partials(a.N),
+                   "fused argmax: needs index / mask / state buffers, no split-K, no row remap, am_stride >= gemm_argmax_partials(N)");
     WB_REQUIRE(gemm_tc_supported(a), "shape/alignment not supported by the tcgen05 GEMM");
     int bn = 256, splits = 1;
     const bool auto_split = a.k_splits == 0;
@@ -397,6 +445,7 @@ void gemm(const GemmArgs& a, cudaStream_t stream) {
     if (g_gemm_backend == 0 && gemm_tc_supported(a)) {
         gemm_tc(a, stream);
     } else {
+        WB_REQUIRE(a.am_val == nullptr, "the fused argmax epilogue exists on the tcgen05 GEMM only");
         if (a.chosen_splits) *a.chosen_splits = 1;   // the CUDA-core kernel never splits: one "partial" slab = the whole product
         gemm_simt(a, stream);
     }

@@ -127,6 +127,33 @@ __device__ int block_masked_argmax(const float* __restrict__ row, int V, const u
     return besti;
 }
 
+// block-wide (value, index) reduction, first maximum wins; result valid in thread 0
+__device__ int block_argmax_reduce(float best, int besti) {
+    __shared__ float rv[32];
+    __shared__ int ri[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        argmax_combine(best, besti, ov, oi);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { rv[warp] = best; ri[warp] = besti; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        best = lane < nw ? rv[lane] : -INFINITY;
+        besti = lane < nw ? ri[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            argmax_combine(best, besti, ov, oi);
+        }
+    }
+    return besti;
+}
+
 __global__ void __launch_bounds__(1024) greedy_step_kernel(GreedyArgs a) {
     pdl_wait();
     pdl_trigger();
@@ -141,6 +168,13 @@ __global__ void __launch_bounds__(1024) greedy_step_kernel(GreedyArgs a) {
         const int forced = a.force_map != nullptr ? a.force_map[n] : -1;
         if (forced >= 0) {
             tok = forced;
+        } else if (a.part_val != nullptr) {
+            // the LM head's epilogue already applied the processors and reduced every column tile (GemmArgs::am_*)
+            float best = -INFINITY;
+            int besti = 0x7fffffff;
+            for (int i = threadIdx.x; i < a.n_parts; i += blockDim.x)
+                argmax_combine(best, besti, a.part_val[(size_t)b * a.part_stride + i], a.part_idx[(size_t)b * a.part_stride + i]);
+            tok = block_argmax_reduce(best, besti);
         } else {
             const int bits = 1 | (n == a.begin_index ? 2 : 0);
             tok = block_masked_argmax(a.logits + (size_t)b * a.ld, a.V, a.vocab_mask, bits);
@@ -254,7 +288,9 @@ void kv_append(const void* past, long long past_bs, long long past_hs, const voi
 
 void greedy_step(const GreedyArgs& a, cudaStream_t stream) {
     WB_REQUIRE(a.V % 4 == 0 && a.ld % 4 == 0, "vocab size / logits pitch must be multiples of 4");
-    launch_kernel(greedy_step_kernel, dim3(a.B), dim3(1024), 0, stream, true, a);
+    WB_REQUIRE(a.part_val != nullptr || a.logits != nullptr, "greedy step needs logits or the LM head's argmax partials");
+    // with partials a row is a few hundred entries: one small block per row
+    launch_kernel(greedy_step_kernel, dim3(a.B), dim3(a.part_val != nullptr ? 256 : 1024), 0, stream, true, a);
 }
 
 void greedy_init(int* tokens, int tokens_stride, int* unfinished, StepState* state, int B, int start_token, int pad_id,

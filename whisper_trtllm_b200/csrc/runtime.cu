@@ -700,6 +700,7 @@ void Session::decode_step(cudaStream_t st) {
     const int mode = step_mode() & 15;
     const bool mega = mode != 0;    // the step starts from the residual stream and its greedy kernel embeds the chosen token
     WB_REQUIRE(!ragged || forced_tokens == nullptr, "teacher forcing is not available on a refilled (ragged) batch");
+    if (!in_loop_step) fuse_argmax_now = false;     // a caller's own wb_decode_step leaves the logits of the step in place (wb_decode_logits)
     prepare_step(st);
     if (mode == 1) decode_step_mega(st);
     else if (mode == 2) decode_step_chain(st);
@@ -716,6 +717,11 @@ void Session::decode_step(cudaStream_t st) {
         a.tokens = tokens; a.tokens_stride = g.max_tgt; a.unfinished = unfinished; a.state = state;
         a.forced_tokens = forced_tokens;
         a.row_len = ragged ? row_len : nullptr;
+        if (fuse_argmax_now && mode != 1) {     // (the whole-step kernel computes its own LM head and writes logits)
+            const int stride = gemm_argmax_partials(g.vocab);
+            a.part_val = logits; a.part_idx = reinterpret_cast<const int*>(logits + (size_t)max_batch * stride);
+            a.n_parts = argmax_parts; a.part_stride = stride;
+        }
         // whole-step kernel: the greedy kernel also embeds the token it chose (the next step starts from the residual stream)
         if (mega) { a.embed_x = dx; a.embed_table = m->emb; a.embed_pos = m->dec_pos; a.embed_d = d; }
         ProfScope ps(this, PROF_GREEDY, st);
@@ -796,14 +802,30 @@ void Session::decode_step_large(cudaStream_t st) {
         pending = lin_split(dffn, g.ffn, L.fc2);
     }
     ln(m->dec_ln, pending);
-    {
-        // LM head: proj_out shares storage with embed_tokens (modeling_whisper.py:1335,1433), no bias
-        GemmArgs a;
-        a.A = dln; a.lda = d; a.W = m->emb; a.ldw = d; a.in_dtype = dt;
-        a.out = logits; a.ldo = g.vocab; a.out_dtype = F32; a.M = B; a.N = g.vocab; a.K = d; a.active = active;
-        ProfScope ps(this, PROF_LM_HEAD, st);
-        gemm(a, st);
+    lm_head(st);
+}
+
+// the logits processors + argmax can move into the LM head's epilogue when nobody needs the logits themselves
+bool Session::lm_head_fusable() const {
+    static const bool off = std::getenv("WB_NO_FUSED_ARGMAX") != nullptr;   // (dev) A/B
+    return !off && m->dtype == BF16 && get_gemm_backend() == 0 && logits_dump == nullptr && m->cfg.d_model % 64 == 0 &&
+           (size_t)2 * gemm_argmax_partials(m->cfg.vocab) <= (size_t)m->cfg.vocab;   // the partials fit the logits buffer
+}
+
+// LM head: proj_out shares storage with embed_tokens (modeling_whisper.py:1335,1433), no bias.  Reads dln [B, d].
+void Session::lm_head(cudaStream_t st) {
+    const ModelConfig& g = m->cfg;
+    GemmArgs a;
+    a.A = dln; a.lda = g.d_model; a.W = m->emb; a.ldw = g.d_model; a.in_dtype = m->dtype;
+    a.out = logits; a.ldo = g.vocab; a.out_dtype = F32; a.M = batch; a.N = g.vocab; a.K = g.d_model; a.active = &state->active;
+    if (fuse_argmax_now) {
+        const int stride = gemm_argmax_partials(g.vocab);
+        a.am_val = logits; a.am_idx = reinterpret_cast<int*>(logits + (size_t)max_batch * stride); a.am_stride = stride;
+        a.am_mask = m->vocab_mask; a.am_state = state; a.am_row_len = ragged_len(); a.am_begin = g.begin_index;
+        a.am_count = &argmax_parts;
     }
+    ProfScope ps(this, PROF_LM_HEAD, st);
+    gemm(a, st);
 }
 
 static std::atomic<bool>& graphs_enabled() {
@@ -867,6 +889,9 @@ void Session::prepare_step(cudaStream_t st) {
 void Session::enqueue_step() {
     cudaStream_t st = loop_stream;
     prepare_step(st);
+    const bool fuse = lm_head_fusable() && (step_mode() & 15) != 1;
+    if (fuse != fuse_argmax_now) { fuse_argmax_now = fuse; step_graph_batch = -1; }   // the captured step is of the other kind
+    struct InLoop { bool& f; InLoop(bool& x) : f(x) { f = true; } ~InLoop() { f = false; } } in_loop(in_loop_step);
     if (graph_ok()) {
         if (step_graph == nullptr || step_graph_batch != batch || step_graph_generation != m->generation_version ||
             step_graph_mode != step_mode()) {

@@ -962,14 +962,7 @@ void Session::decode_step_chain(cudaStream_t st) {
         { ProfScope ps(this, PROF_DEC_GEMM, st); launch_chain(base + 3, l + 1 < L ? base + 9 : base + 8, st); }
     }
     }
-    {
-        // LM head: proj_out shares storage with embed_tokens (modeling_whisper.py:1335,1433), no bias
-        GemmArgs a;
-        a.A = dln; a.lda = d; a.W = m->emb; a.ldw = d; a.in_dtype = dt;
-        a.out = logits; a.ldo = g.vocab; a.out_dtype = F32; a.M = B; a.N = g.vocab; a.K = d; a.active = active;
-        ProfScope ps(this, PROF_LM_HEAD, st);
-        gemm(a, st);
-    }
+    lm_head(st);
 }
 
 }  // namespace wb

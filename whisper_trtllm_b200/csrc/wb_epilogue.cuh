@@ -13,6 +13,8 @@ struct EpiParams {
     int M, N, act;
     int m_period_in, m_valid, m_period_out, m_out_offset;
     int out_mode, hs_heads, hs_batch, hs_b0;
+    float* am_val; int* am_idx; int am_stride;                      // fused logits processors + argmax (see GemmArgs)
+    const unsigned char* am_mask; const StepState* am_state; const int* am_row_len; int am_begin;
 };
 
 inline EpiParams make_epi(const GemmArgs& a) {
@@ -23,6 +25,8 @@ inline EpiParams make_epi(const GemmArgs& a) {
     p.m_period_in = a.m_period_in; p.m_valid = a.m_valid; p.m_period_out = a.m_period_out;
     p.m_out_offset = a.m_out_offset;
     p.out_mode = a.out_mode; p.hs_heads = a.hs_heads; p.hs_batch = a.hs_batch; p.hs_b0 = a.hs_b0;
+    p.am_val = a.am_val; p.am_idx = a.am_idx; p.am_stride = a.am_stride;
+    p.am_mask = a.am_mask; p.am_state = a.am_state; p.am_row_len = a.am_row_len; p.am_begin = a.am_begin;
     return p;
 }
 

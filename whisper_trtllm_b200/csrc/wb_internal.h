@@ -37,7 +37,16 @@ struct GemmArgs {
     int k_splits = 1; long long split_stride = 0; int max_k_splits = 1; int* chosen_splits = nullptr;
     // optional second output (same remap, row-major): fp32 copy of the result
     void* out2 = nullptr; long long ldo2 = 0;
+    // Fused logits processors + argmax (LM head of the greedy loop, tcgen05 path only): instead of storing the [M, N] logits, every
+    // (row, column tile, epilogue half) stores the maximum of its columns that are not suppressed and its column index:
+    //   am_val / am_idx [M, am_stride] with am_stride >= ceil(N / 256) * 2.  The argmax kernel reduces them (first maximum wins).
+    // am_mask: vocab bits (bit 0 always suppressed, bit 1 suppressed when the row's length == am_begin); the row's length is
+    // am_row_len[row] when given, else am_state->cur_len.  `out` is not written.
+    float* am_val = nullptr; int* am_idx = nullptr; int am_stride = 0;
+    int* am_count = nullptr;     // out (host): entries per row actually written (depends on the tile width the launcher picked)
+    const unsigned char* am_mask = nullptr; const StepState* am_state = nullptr; const int* am_row_len = nullptr; int am_begin = 0;
 };
+int gemm_argmax_partials(int N);   // partial entries per row the fused LM head writes for N columns
 
 // prefer_tc: use the tcgen05 kernel when in_dtype == BF16 (falls back to SIMT when shapes do not fit)
 void gemm(const GemmArgs& a, cudaStream_t stream);
@@ -118,6 +127,9 @@ struct GreedyArgs {
     int* unfinished = nullptr;                      // [B]
     StepState* state = nullptr;
     const int* forced_tokens = nullptr;         // teacher forcing (tests): take ids[b, n] from here instead of argmax
+    // partial (maximum, index) entries written by the fused LM head epilogue (GemmArgs::am_*): reduced here instead of scanning
+    // the logits (which are then not needed and `logits` may be null)
+    const float* part_val = nullptr; const int* part_idx = nullptr; int n_parts = 0; int part_stride = 0;
     // in-flight refill: per-row lengths [B].  Row b writes its token at ids[b, row_len[b]], the processors see its own length,
     // a row stops growing once it has emitted EOS or reached max_length (no pad is appended: the host pads the results)
     int* row_len = nullptr;

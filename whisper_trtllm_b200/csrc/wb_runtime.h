@@ -121,6 +121,13 @@ struct Session : Buffers {
     int opt_small_batch_path = -1, opt_decode_chain_path = -1, opt_cuda_graphs = -1, opt_merge_attention = -1;
     bool graph_capture_failed = false;   // stream capture of the step failed once on this session: eager launches from then on
     void set_option(const std::string& name, int value);
+    // LM head fused with the logits processors + argmax (bf16 tcgen05 path, steps of the greedy loop that need no logits):
+    // the [B, V] fp32 logits are neither written nor re-read; partial (max, index) per column tile live in the logits buffer
+    bool fuse_argmax_now = false;            // set by enqueue_step for the step being enqueued / captured
+    bool in_loop_step = false;               // decode_step is running on behalf of the greedy loop (enqueue_step)
+    int argmax_parts = 0;                    // partial entries per row the last fused LM head wrote
+    bool lm_head_fusable() const;
+    void lm_head(cudaStream_t s);            // LM head GEMM of the current step (fused or materialising the logits)
     bool dx_embedded = false;         // dx holds E[last token] + P[position] of every row (what the whole-step kernel starts from)
     bool graph_ok() const;
     void build_step_graph(cudaStream_t s);
